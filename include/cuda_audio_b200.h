@@ -1,0 +1,159 @@
+/*
+ * cuda_audio_b200.h -- C ABI of the B200-native partitioned-convolution reverb engine.
+ *
+ * This is the drop-in boundary for the hot path of limitz/cuda-audio: everything the
+ * reference's `Convolution` class does on the GPU (src/conv.h:30-86, src/conv.cu:142-466)
+ * sits behind these entry points.  Plain pointers and sizes only; no C++/torch types.
+ * The C++ mirror of the reference class (cuda-audio_b200/host/convolution.h) is a thin
+ * wrapper over this ABI; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Reference interface each entry point replaces:
+ *   ca_create            Convolution::Convolution(name, fftSize)       conv.cu:142-195
+ *   ca_load_ir[_device]  Convolution::prepare(idx, wav, nframes)        conv.cu:207-253
+ *                        (+ WavFile PCM decode, wav.cu:4-118, done by the host shim)
+ *   ca_set_params        writes to Convolution::cc[i].value             conv.h:40-50
+ *                        (what handleCC / main.cu:63-70 do)             conv.cu:255-276
+ *   ca_process           Convolution::onProcess(nframes)                conv.cu:287-466
+ *                        with JACK's planar float host buffers          conv.cu:291-294
+ *   ca_get_stats         Convolution::avgRuntime()                      conv.h:61
+ *   ca_destroy           (the reference never frees, conv.h:53-54)
+ *
+ * One engine = `n_instances` independent convolution instances that share a geometry
+ * (period, IR capacity, n_in x n_out) and are processed by ONE set of kernel launches per
+ * period.  One reference `Convolution` object == one instance with n_in = n_out = 2
+ * ("true stereo": outL = IN1*h1.L + IN2*h2.L, outR = IN1*h1.R + IN2*h2.R, conv.cu:392-401).
+ *
+ * All functions return 0 (CA_OK) or a negative error code; none aborts.
+ * Thread model: ca_process* from one thread per engine; ca_set_params from any thread
+ * (lock-free hand-off, applied at the next ca_process*); ca_load_ir* may block.
+ */
+#ifndef CUDA_AUDIO_B200_H
+#define CUDA_AUDIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CA_API_VERSION 1
+#define CA_MAX_TIERS 4
+#define CA_MAX_PREDELAY 8192 /* CONV_MAX_PREDELAY, conv.h:26-28 */
+#define CA_MAX_SPEED 1024    /* CONV_MAX_SPEED,    conv.h:22-24 */
+
+enum ca_error {
+    CA_OK = 0,
+    CA_ERR_INVALID = -1,     /* bad argument / config */
+    CA_ERR_CUDA = -2,        /* CUDA runtime failure (see ca_last_error_string) */
+    CA_ERR_NOMEM = -3,
+    CA_ERR_STATE = -4,       /* e.g. select points at an IR slot that was never loaded */
+    CA_ERR_UNSUPPORTED = -5,
+    CA_ERR_PERIOD = -6       /* nframes != configured period */
+};
+
+enum ca_flags {
+    CA_FLAG_GRAPH = 1u << 0,      /* replay one CUDA graph per period instead of 3 launches   */
+    CA_FLAG_STREAMING = 1u << 1,  /* working set >> L2: evict-first hints on spectra loads     */
+    CA_FLAG_L2_PERSIST = 1u << 2, /* pin IR spectra + FDL in L2 (access-policy window)         */
+    CA_FLAG_PROFILE = 1u << 3     /* record CUDA events around every kernel (ca_get_stats)     */
+};
+
+typedef struct ca_engine ca_engine;
+
+typedef struct ca_config {
+    uint32_t struct_size;   /* sizeof(ca_config) */
+    int32_t device;         /* CUDA device ordinal */
+    uint32_t period;        /* frames per ca_process call (JACK nframes); power of two, 32..1024 */
+    uint32_t n_instances;   /* instances batched in one engine */
+    uint32_t n_in, n_out;   /* 1 or 2 each (2,2 = the reference's true-stereo instance) */
+    uint32_t max_ir_frames; /* IR capacity L; longer IRs are truncated like conv.cu:239 */
+    uint32_t n_ir_slots;    /* size of the IR bank shared by the engine's instances */
+    uint32_t flags;         /* ca_flags */
+    uint32_t mac_split;     /* partition-range split of the MAC per instance; 0 = auto */
+    /* partition-range shard for IRs split across GPUs: this engine convolves
+     * with partitions [part_begin, part_begin + part_count) of the uniform partitioning only;
+     * part_count == 0 means "all". */
+    uint32_t part_begin, part_count;
+    /* non-uniform partitioning: tier j uses block size tier_block[j] (multiple of period,
+     * power of two) for tier_parts[j] partitions; tier 0 must equal period; n_tiers <= 1
+     * means uniform.  The last tier's tier_parts may be 0 (= cover the rest). */
+    uint32_t n_tiers;
+    uint32_t tier_block[CA_MAX_TIERS];
+    uint32_t tier_parts[CA_MAX_TIERS];
+    float sample_rate;      /* only for deadline / xrun accounting; 0 = off */
+} ca_config;
+
+/* Per-input parameter block == Convolution::CC::value (conv.h:40-50). */
+typedef struct ca_params {
+    uint32_t select;    /* IR bank slot used by this input                      */
+    uint32_t predelay;  /* samples, [0, CA_MAX_PREDELAY); input 0's is used     */
+    uint32_t speed;     /* cross-fade / glide length in periods, [0, 1024]      */
+    int32_t vsteps;     /* >= 0: (re)start the glide countdown; < 0: leave it   */
+    float dry, wet;     /* [0,1] */
+    float panDry, panWet; /* [-1,1] */
+    float level;        /* [0,1] */
+} ca_params;
+
+typedef struct ca_stats {
+    uint64_t periods;       /* ca_process* calls so far                                 */
+    uint64_t xruns;         /* calls whose host wall time exceeded period / sample_rate */
+    double mean_us, p50_us, p99_us, max_us; /* host wall time per ca_process* call      */
+    /* CA_FLAG_PROFILE: mean device time per period, CUDA events on the engine's stream */
+    double fwd_us, mac_us, inv_us, total_us;
+    uint64_t gpu_launches;  /* kernels launched by the engine so far                    */
+    uint64_t mac_bytes;     /* algorithmic bytes the FDL MAC streams per period         */
+    uint32_t partitions;    /* P                                                       */
+    uint32_t mac_split;     /* effective split                                          */
+    uint64_t device_bytes;  /* device memory held by the engine                         */
+} ca_stats;
+
+int ca_api_version(void);
+const char *ca_strerror(int code);
+const char *ca_last_error_string(void); /* thread-local detail of the last CUDA failure */
+
+void ca_config_init(ca_config *cfg); /* zero + struct_size + reference defaults (2x2, period 256) */
+
+int ca_create(const ca_config *cfg, ca_engine **out);
+int ca_destroy(ca_engine *e);
+
+/* IR bank.  left/right: planar fp32 time-domain IR (right may be NULL when n_out == 1).
+ * Host pointers; synchronous (the caller may free the buffers on return, main.cu:78-79). */
+int ca_load_ir(ca_engine *e, uint32_t slot, const float *left, const float *right, uint32_t frames);
+/* same with device pointers (current device = engine's); synchronous */
+int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames);
+
+int ca_set_params(ca_engine *e, uint32_t instance, uint32_t input, const ca_params *p);
+int ca_get_params(ca_engine *e, uint32_t instance, uint32_t input, ca_params *p);
+/* jump the wet glide of (instance, input) to `g` (tests: skip the 1-0.8^k fade-in) */
+int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g);
+
+/* Only the first n instances are processed by ca_process* (default: all). */
+int ca_set_active(ca_engine *e, uint32_t n);
+
+/* One period for every active instance.
+ *   in : host, planar [instance][input ][nframes] fp32, contiguous
+ *   out: host, planar [instance][output][nframes] fp32, contiguous
+ * Synchronous: out is complete on return (like conv.cu:455).  Pinned buffers are used
+ * in place; pageable ones are staged through the engine's pinned buffers. */
+int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes);
+
+/* Same with device-resident buffers; asynchronous on the engine's stream.
+ * ca_sync waits for it. */
+int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nframes);
+int ca_sync(ca_engine *e);
+
+/* The engine's CUDA stream (cudaStream_t) so callers can order their own work / events. */
+void *ca_stream(ca_engine *e);
+
+int ca_get_stats(ca_engine *e, ca_stats *s);
+int ca_reset_stats(ca_engine *e);
+
+/* Pinned host memory helpers for callers that want zero staging copies. */
+int ca_host_alloc(void **p, size_t bytes);
+int ca_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDA_AUDIO_B200_H */

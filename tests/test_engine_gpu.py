@@ -1,0 +1,402 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against the oracles.
+
+Tolerances (BASELINE.json north_star): relative L2 <= 1e-5 vs the reference's own conv.cu
+(oracle/_ref, cuFFT path, run live on the same GPU under the parity protocol of SURVEY 8c),
+<= 1e-4 vs the FP64 convolution oracle.  The engine is fp32; observed errors are ~3e-7.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import refgpu
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP64 = 1e-4
+TOL_REF = 1e-5
+
+
+def ca():
+    import cuda_audio_b200 as m
+    return m
+
+
+def make_irs(L, fs, n_in=2, n_out=2, seed0=1000):
+    return [[O.synth_ir(L, fs, seed0 + i * n_out + o) for o in range(n_out)] for i in range(n_in)]
+
+
+def load_true_stereo(eng, irs):
+    """input i uses bank slot i = stereo IR (irs[i][0], irs[i][1])"""
+    for i, pair in enumerate(irs):
+        eng.load_ir(i, pair[0], pair[1] if len(pair) > 1 else None)
+
+
+def test_cfg1_mono_vs_fp64():
+    """BASELINE configs[0]: mono 44.1 kHz, 256-frame period, 1 s synthetic IR, offline render."""
+    m = ca()
+    fs, B, L = 44100, 256, 44100
+    h = O.synth_ir(L, fs, 1000)
+    x = O.synth_audio(B * 400, 2000)
+    with m.Engine(period=B, max_ir_frames=L, n_in=1, n_out=1, n_ir_slots=1, sample_rate=fs) as e:
+        e.load_ir(0, h)
+        e.set_params(0, 0, select=0, wet=1.0, dry=0.0)
+        e.set_glide(0, 0, 1.0)
+        y = e.render(x[None, None, :])[0, 0]
+        st = e.stats()
+    truth = O.fft_conv(x, h)
+    err = O.rel_l2(y, truth)
+    assert st.partitions == 173
+    assert err < TOL_FP64, err
+    assert err < 5e-6, err  # fp32 partitioned convolution sits ~3e-7 from fp64
+    # spot-check with the direct (time-domain) fp64 convolution on sampled outputs
+    idx = np.random.default_rng(0).integers(0, len(x), 512)
+    d = O.direct_conv_at(x, h, idx)
+    assert O.rel_l2(y[idx], d) < TOL_FP64
+
+
+@pytest.mark.parametrize("B", [32, 64, 128, 256, 512, 1024])
+def test_every_period_size_true_stereo(B):
+    m = ca()
+    fs = 48000
+    L = 9 * B + 17  # ragged: last partition partly filled
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 40, 2000 + i) for i in range(2)])
+    pr = [dict(wet=0.8, dry=0.3, level=0.9, panWet=0.25, panDry=-0.5), dict(wet=0.6, dry=0.2, level=1.0, panWet=-0.4, panDry=0.3)]
+    with m.Engine(period=B, max_ir_frames=L, n_ir_slots=2) as e:
+        load_true_stereo(e, irs)
+        for i in range(2):
+            e.set_params(0, i, select=i, **pr[i])
+            e.set_glide(0, i, pr[i]["wet"])
+        y = e.render(x[None])[0]
+    truth = O.engine_truth(x, irs, pr)
+    for o in range(2):
+        assert O.rel_l2(y[o], truth[o]) < 5e-6, (B, o, O.rel_l2(y[o], truth[o]))
+
+
+def test_predelay():
+    m = ca()
+    fs, B, L = 48000, 128, 1000
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 60, 2000 + i, rms=0.5) for i in range(2)])  # loud: clamp fires
+    pr = [dict(wet=1.0, dry=0.5, level=1.0, panWet=0.0, panDry=0.0)] * 2
+    for pd in (0, 1, 77, 128, 1000, 8191):
+        with m.Engine(period=B, max_ir_frames=L) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, select=i, predelay=pd, **pr[i])
+                e.set_glide(0, i, 1.0)
+            y = e.render(x[None])[0]
+        truth = O.engine_truth(x, irs, pr, predelay=pd)
+        assert np.abs(truth).max() > 0.5
+        for o in range(2):
+            assert O.rel_l2(y[o], truth[o]) < 5e-6, (pd, o)
+
+
+def test_clamp_fires():
+    m = ca()
+    fs, B, L = 48000, 64, 300
+    h = 4.0 * O.synth_ir(L, fs, 5)
+    x = O.synth_audio(B * 50, 7, rms=0.6)
+    with m.Engine(period=B, max_ir_frames=L, n_in=1, n_out=1, n_ir_slots=1) as e:
+        e.load_ir(0, h)
+        e.set_params(0, 0, wet=1.0, dry=0.25)
+        e.set_glide(0, 0, 1.0)
+        y = e.render(x[None, None])[0, 0]
+    truth = O.engine_truth(x[None], [[h]], [dict(wet=1.0, dry=0.25)])[0]
+    wet_only = O.fft_conv(x, h)
+    assert (np.abs(wet_only) > 1.0).sum() > 100  # the clamp really is exercised
+    # clamping is discontinuous only in derivative: errors stay at fp32 level
+    assert O.rel_l2(y, truth) < 5e-6
+
+
+def test_impulse_returns_ir_full_cfg2_size():
+    """Size-independent property at BASELINE's full size (48 kHz, B=256, 4 s IR, P=750):
+    a unit impulse on input i must return the IR of path (i, o) on output o."""
+    m = ca()
+    fs, B, L = 48000, 256, 192000
+    irs = make_irs(L, fs)
+    n = L + 4 * B
+    n = (n // B) * B
+    with m.Engine(period=B, max_ir_frames=L) as e:
+        load_true_stereo(e, irs)
+        assert e.stats().partitions == 750
+        for i in range(2):
+            e.set_params(0, i, select=i, wet=1.0, dry=0.0)
+            e.set_glide(0, i, 1.0)
+        x = np.zeros((1, 2, n), np.float32)
+        x[0, 0, 3] = 1.0
+        x[0, 1, B + 5] = 0.5
+        y = e.render(x)[0]
+    for o in range(2):
+        want = np.zeros(n)
+        want[3:3 + L] += irs[0][o][: n - 3]
+        want[B + 5:B + 5 + L] += 0.5 * irs[1][o][: n - B - 5]
+        assert O.rel_l2(y[o], want) < 2e-6, (o, O.rel_l2(y[o], want))
+
+
+def test_cfg2_vs_fp64_sampled():
+    m = ca()
+    fs, B, L = 48000, 256, 192000
+    irs = make_irs(L, fs)
+    n = B * 1200
+    x = np.stack([O.synth_audio(n, 2000 + i) for i in range(2)])
+    pr = [dict(wet=1.0, dry=0.0)] * 2
+    with m.Engine(period=B, max_ir_frames=L) as e:
+        load_true_stereo(e, irs)
+        for i in range(2):
+            e.set_params(0, i, select=i, **pr[i])
+            e.set_glide(0, i, 1.0)
+        y = e.render(x[None])[0]
+    truth = O.engine_truth(x, irs, pr)
+    for o in range(2):
+        assert O.rel_l2(y[o], truth[o]) < 5e-6
+    idx = np.random.default_rng(1).integers(L, n, 256)
+    d = O.direct_conv_at(x[0], irs[0][0], idx) + O.direct_conv_at(x[1], irs[1][0], idx)
+    assert O.rel_l2(y[0][idx], d) < TOL_FP64
+
+
+def test_batch_instances_distinct_irs_and_active_subset():
+    m = ca()
+    fs, B, L, K = 48000, 64, 700, 5
+    irs = [make_irs(L, fs, seed0=1000 + 8 * s) for s in range(K)]
+    x = np.stack([np.stack([O.synth_audio(B * 30, 2000 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    pr = [dict(wet=1.0, dry=0.1)] * 2
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K) as e:
+        for s in range(K):
+            for i in range(2):
+                e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                e.set_params(s, i, select=2 * s + i, **pr[i])
+                e.set_glide(s, i, 1.0)
+        y = e.render(x)
+        for s in range(K):
+            truth = O.engine_truth(x[s], irs[s], pr)
+            for o in range(2):
+                assert O.rel_l2(y[s, o], truth[o]) < 5e-6, (s, o)
+    # subset: only the first 2 instances are processed
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K) as e:
+        for s in range(K):
+            for i in range(2):
+                e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                e.set_params(s, i, select=2 * s + i, **pr[i])
+                e.set_glide(s, i, 1.0)
+        e.set_active(2)
+        y2 = e.render(x[:2])
+        assert np.array_equal(y2, y[:2])
+
+
+def test_shared_ir_bank_and_select():
+    """Two inputs selecting the same / swapped bank slots (reference: cc[i].value.select)."""
+    m = ca()
+    fs, B, L = 48000, 64, 500
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 30, 2000 + i) for i in range(2)])
+    with m.Engine(period=B, max_ir_frames=L) as e:
+        load_true_stereo(e, irs)
+        e.set_params(0, 0, select=1, wet=1.0, dry=0.0)
+        e.set_params(0, 1, select=0, wet=1.0, dry=0.0)
+        e.set_glide(0, 0, 1.0)
+        e.set_glide(0, 1, 1.0)
+        y = e.render(x[None])[0]
+    truth = O.engine_truth(x, [irs[1], irs[0]], [dict(wet=1.0)] * 2)
+    for o in range(2):
+        assert O.rel_l2(y[o], truth[o]) < 5e-6
+
+
+def test_split_graph_and_variants_agree():
+    m = ca()
+    fs, B, L = 48000, 256, 256 * 37 + 5
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 60, 2000 + i) for i in range(2)])
+
+    def run(**kw):
+        with m.Engine(period=B, max_ir_frames=L, **kw) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, select=i, wet=1.0, dry=0.2)
+                e.set_glide(0, i, 1.0)
+            y = e.render(x[None])[0]
+            return y, e.stats()
+
+    y1, s1 = run(mac_split=1)
+    y8, s8 = run(mac_split=8)
+    yg, _ = run(mac_split=8, flags=m.FLAG_GRAPH)
+    yp, sp = run(mac_split=8, flags=m.FLAG_PROFILE)
+    ys, _ = run(mac_split=3, flags=m.FLAG_STREAMING)
+    assert s1.mac_split == 1 and s8.mac_split > 1
+    assert np.array_equal(y8, yg)          # graph replay == plain launches, bitwise
+    assert np.array_equal(y8, yp)
+    assert sp.mac_us > 0 and sp.fwd_us > 0 and sp.inv_us > 0
+    assert O.rel_l2(y8, y1) < 1e-6         # different summation order only
+    assert O.rel_l2(ys, y1) < 1e-6
+    truth = O.engine_truth(x, irs, [dict(wet=1.0, dry=0.2)] * 2)
+    assert O.rel_l2(y1[0], truth[0]) < 5e-6
+
+
+def test_partition_range_shards_sum_to_whole():
+    """a long IR split by partition range; partial outputs sum to the 1-engine
+    result (this is the collective-free check of the multi-GPU sharding math)."""
+    m = ca()
+    fs, B, L = 48000, 128, 128 * 40
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 90, 2000 + i) for i in range(2)])
+
+    def run(pb, pc):
+        with m.Engine(period=B, max_ir_frames=L, part_begin=pb, part_count=pc) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, select=i, wet=1.0, dry=0.0)
+                e.set_glide(0, i, 1.0)
+            return e.render(x[None])[0]
+
+    whole = run(0, 0)
+    parts = run(0, 10).astype(np.float64) + run(10, 17) + run(27, 13)
+    assert O.rel_l2(parts, whole) < 1e-6
+    truth = O.engine_truth(x, irs, [dict(wet=1.0)] * 2)
+    assert O.rel_l2(parts[0], truth[0]) < 5e-6
+
+
+def test_wet_glide_fade_in_matches_formula():
+    """Freshly started engine fades the wet path in as 1 - 0.8^k (conv.cu:27 with vsteps = 0)."""
+    m = ca()
+    fs, B, L = 48000, 64, 64
+    h = np.zeros(L, np.float32)
+    h[0] = 1.0  # identity IR: output = g_t * x
+    x = np.full(B * 30, 0.25, np.float32)
+    with m.Engine(period=B, max_ir_frames=L, n_in=1, n_out=1, n_ir_slots=1) as e:
+        e.load_ir(0, h)
+        e.set_params(0, 0, wet=1.0, dry=0.0)
+        y = e.render(x[None, None])[0, 0]
+    g = 0.0
+    for t in range(30):
+        g = g + (1.0 - g) / 5.0
+        assert np.allclose(y[t * B:(t + 1) * B], 0.25 * g, rtol=2e-6, atol=1e-7), t
+
+
+def test_error_codes():
+    m = ca()
+    with m.Engine(period=64, max_ir_frames=100, n_ir_slots=2) as e:
+        with pytest.raises(m.CaError) as ei:
+            e.set_params(0, 0, select=1)  # slot never loaded: reference would fault (conv.cu:340)
+        assert ei.value.code == -4
+        e.load_ir(0, np.ones(10, np.float32), np.ones(10, np.float32))
+        e.set_params(0, 0, select=0)
+        with pytest.raises(m.CaError) as ei:
+            e.set_params(0, 0, select=7)
+        assert ei.value.code == -1
+        x = np.zeros((1, 2, 32), np.float32)
+        out = np.zeros((1, 2, 32), np.float32)
+        rc = m.lib().ca_process(e._h, x.ctypes.data, out.ctypes.data, 32)
+        assert rc == -6
+    with pytest.raises(m.CaError):
+        m.Engine(period=100, max_ir_frames=100)  # not a power of two
+    with pytest.raises(m.CaError):
+        m.Engine(period=64, max_ir_frames=100, n_in=3)
+
+
+def test_pinned_buffers_and_stats():
+    m = ca()
+    fs, B, L, K = 48000, 256, 2048, 3
+    h = O.synth_ir(L, fs, 3)
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=1) as e:
+        e.load_ir(0, h, h)
+        for s in range(K):
+            for i in range(2):
+                e.set_params(s, i, wet=1.0, dry=0.0)
+                e.set_glide(s, i, 1.0)
+        pin = m.PinnedArray((K, 2, B))
+        pout = m.PinnedArray((K, 2, B))
+        x = O.synth_audio(K * 2 * B * 20, 9).reshape(20, K, 2, B)
+        ys = []
+        for t in range(20):
+            pin.array[...] = x[t]
+            e.process_raw(pin.ptr, pout.ptr)
+            ys.append(pout.array.copy())
+        st = e.stats()
+        assert st.periods == 20 and st.gpu_launches >= 61 and st.p50_us > 0
+        y = np.concatenate(ys, axis=-1)
+        xin = np.concatenate(list(x), axis=-1)
+        truth = O.engine_truth(xin[1], [[h, h], [h, h]], [dict(wet=1.0)] * 2)
+        assert O.rel_l2(y[1, 0], truth[0]) < 5e-6
+        pin.free()
+        pout.free()
+
+
+# ------------------------------------------------------------------------------------------
+# against the real reference (oracle/_ref = unmodified conv.cu + cuFFT), live on this GPU
+# ------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not refgpu.available(), reason="oracle/_ref/libref_conv.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("N,B", [(4096, 64), (65536, 256)])
+def test_vs_reference_conv_cu(N, B):
+    """Parity protocol of SURVEY 8(c): DC/Nyquist-free IRs, >= 80 silent warm-up periods,
+    unclipped levels, predelay 0.  Reference = its own conv.cu through prepare()/onProcess()."""
+    m = ca()
+    fs = 48000
+    L = N - B
+    irs = make_irs(L, fs)
+    warm = 100
+    x = np.stack([np.concatenate([np.zeros(warm * B, np.float32), O.synth_audio(B * 150, 2000 + i)]) for i in range(2)])
+    ref = refgpu.RefGpu(N)
+    ref.prepare(0, irs[0][0], irs[0][1], B)
+    ref.prepare(1, irs[1][0], irs[1][1], B)
+    ref.set_cc(0, select=0, wet=1.0, dry=0.0)
+    ref.set_cc(1, select=1, wet=1.0, dry=0.0)
+    rl, rr = ref.render(x[0], x[1], B)
+    with m.Engine(period=B, max_ir_frames=L) as e:
+        load_true_stereo(e, irs)
+        for i in range(2):
+            e.set_params(0, i, select=i, wet=1.0, dry=0.0)
+        y = e.render(x[None])[0]
+    sl = slice(warm * B, None)
+    assert O.rel_l2(y[0][sl], rl[sl]) < TOL_REF, O.rel_l2(y[0][sl], rl[sl])
+    assert O.rel_l2(y[1][sl], rr[sl]) < TOL_REF, O.rel_l2(y[1][sl], rr[sl])
+
+
+@needs_ref
+def test_vs_reference_defaults_pan_predelay_fade_in():
+    """Reference defaults (wet = dry = 0.5) plus pan / level / predelay, compared from the very
+    first period: exercises the wet fade-in glide, the pan law, predelay and the dry mix."""
+    m = ca()
+    fs, N, B, pd = 48000, 16384, 256, 300
+    L = N - B - pd - B
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 200, 2000 + i) for i in range(2)])
+    cc = [dict(select=0, predelay=pd, panWet=0.3, panDry=-0.2, level=0.8), dict(select=1, panWet=-0.5, panDry=0.4)]
+    ref = refgpu.RefGpu(N)
+    ref.prepare(0, irs[0][0], irs[0][1], B)
+    ref.prepare(1, irs[1][0], irs[1][1], B)
+    ref.set_cc(0, **cc[0])
+    ref.set_cc(1, **cc[1])
+    rl, rr = ref.render(x[0], x[1], B)
+    with m.Engine(period=B, max_ir_frames=L) as e:
+        load_true_stereo(e, irs)
+        e.set_params(0, 0, **cc[0])
+        e.set_params(0, 1, **cc[1])
+        y = e.render(x[None])[0]
+    assert O.rel_l2(y[0], rl) < TOL_REF, O.rel_l2(y[0], rl)
+    assert O.rel_l2(y[1], rr) < TOL_REF, O.rel_l2(y[1], rr)
+
+
+@needs_ref
+def test_restatement_pinned_by_live_reference():
+    """oracle/refconv.c (the CPU restatement) against the compiled reference on quirk-exposing
+    input: white-noise IRs WITHOUT the DC/Nyquist correction, fade-in, clamp active."""
+    fs, N, B = 48000, 8192, 128
+    L = N - B
+    irs = [[O.synth_ir(L, fs, 50 + 2 * i + o, parity_safe=False) for o in range(2)] for i in range(2)]
+    x = np.stack([O.synth_audio(B * 120, 2000 + i, rms=0.4) for i in range(2)])
+    ref = refgpu.RefGpu(N)
+    cpu = O.RefConv(N)
+    for i in range(2):
+        ref.prepare(i, irs[i][0], irs[i][1], B)
+        cpu.prepare(i, irs[i][0], irs[i][1], B)
+        ref.set_cc(i, select=i, wet=0.9, dry=0.3, panWet=0.2 - 0.5 * i)
+        cpu.set_cc(i, select=i, wet=0.9, dry=0.3, panWet=0.2 - 0.5 * i)
+    rl, rr = ref.render(x[0], x[1], B)
+    cl, cr = cpu.render(x[0], x[1], B)
+    assert O.rel_l2(cl, rl) < TOL_REF, O.rel_l2(cl, rl)
+    assert O.rel_l2(cr, rr) < TOL_REF, O.rel_l2(cr, rr)
