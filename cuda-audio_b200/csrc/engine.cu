@@ -54,10 +54,12 @@ template <int BT, int NIN, int NOUT>
 MacVariant mac_pick_v(int variant)
 {
     switch (variant) {
-    case 1: return mac_variant<BT, NIN, NOUT, 1, 4>();   //  96 KB at 2x2: 2 CTAs / SM
+    case 0: return mac_variant<BT, NIN, NOUT, 2, 4>();   // 192 KB at 2x2: 1 CTA / SM
     case 2: return mac_variant<BT, NIN, NOUT, 1, 3>();   //  72 KB at 2x2: 3 CTAs / SM
     case 3: return mac_variant<BT, NIN, NOUT, 2, 2>();   //  96 KB, deeper rows
-    default: return mac_variant<BT, NIN, NOUT, 2, 4>();  // 192 KB at 2x2: 1 CTA / SM
+    case 4: return mac_variant<BT, NIN, NOUT, 1, 2>();   //  48 KB at 2x2: 4 CTAs / SM
+    case 5: return mac_variant<BT, NIN, NOUT, 1, 6>();   // 144 KB at 2x2: 1 CTA / SM, deep
+    default: return mac_variant<BT, NIN, NOUT, 1, 4>();  //  96 KB at 2x2: 2 CTAs / SM (measured best)
     }
 }
 
@@ -321,7 +323,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     e->bt = std::min<uint32_t>(e->B, 256);
     e->tiles = e->B / e->bt;
     e->fft = fft_pick((int)e->R);
-    int variant = 0;
+    int variant = 1;
     if (const char *v = getenv("CA_MAC_VARIANT")) variant = atoi(v);
     e->mac = mac_pick((int)e->bt, (int)e->n_in, (int)e->n_out, variant);
     CA_CUDA(cudaFuncSetAttribute((const void *)e->mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mac.smem));

@@ -202,7 +202,7 @@ def engine_truth(x, irs, params, predelay=0, conv=fft_conv):
             y = conv(x[i], irs[i][o], n)
             wet += pan * p.get("level", 1.0) * p.get("wet", 1.0) * y
         if predelay:
-            wet = np.concatenate([np.zeros(predelay), wet[:n - predelay]])
+            wet = np.concatenate([np.zeros(predelay), wet])[:n]
         wet = np.clip(wet, -1.0, 1.0)
         for i in range(n_in):
             p = params[i]

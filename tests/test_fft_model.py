@@ -1,0 +1,69 @@
+"""CPU check of the index math behind fft_warp.cuh (see tests/_warp_fft_model.py)."""
+import numpy as np
+import pytest
+
+from tests import _warp_fft_model as wm
+
+
+@pytest.mark.parametrize("R", [1, 2, 4, 8, 16, 32])
+def test_warp_fft_layouts_and_split(R):
+    M = 32 * R
+    rng = np.random.default_rng(R)
+    w = rng.standard_normal(2 * M)
+    z = w[0::2] + 1j * w[1::2]
+    Zs = wm.warp_fwd(z, R)
+    Zref = np.fft.fft(z)
+    k = np.array([[wm.brev5(l) + 32 * d for d in range(R)] for l in range(32)])
+    assert np.allclose(Zs, Zref[k])                      # spectral layout: lane l, reg d <-> k = brev5(l) + 32 d
+    Zp = wm.partner(Zs, R)
+    assert np.allclose(Zp, Zref[(M - k) % M])            # conjugate-partner shuffle
+    X = 0.5 * (Zs + np.conj(Zp)) - 0.5j * wm.W(2 * M, k) * (Zs - np.conj(Zp))
+    Xref = np.fft.rfft(w)
+    assert np.allclose(X, Xref[k])                       # R2C split
+    packed = np.zeros(M, complex)
+    packed[k] = X
+    packed[0] = (Zref[0].real + Zref[0].imag) + 1j * (Zref[0].real - Zref[0].imag)
+    assert np.isclose(packed[0].real, Xref[0].real) and np.isclose(packed[0].imag, Xref[M].real)
+    Ys, Yp = packed[k], packed[(M - k) % M]
+    Zc = (Ys + np.conj(Yp)) + 1j * np.conj(wm.W(2 * M, k)) * (Ys - np.conj(Yp))
+    Zc[0, 0] = (packed[0].real + packed[0].imag) + 1j * (packed[0].real - packed[0].imag)
+    zt = wm.warp_inv(Zc, R)
+    y = np.zeros(2 * M)
+    for a in range(32):
+        for b in range(R):
+            n = R * a + b
+            y[2 * n], y[2 * n + 1] = zt[a, b].real, zt[a, b].imag
+    assert np.allclose(y / (2 * M), w)                   # C2R: the 1/(2M) lives in the IR spectra
+
+
+def test_overlap_save_partitioned_model():
+    """Uniform partitioned overlap-save with packed spectra (bin 0 = DC/Nyquist as two REAL
+    products) reproduces linear convolution -- the engine's math in numpy."""
+    rng = np.random.default_rng(0)
+    B, P = 32, 5
+    h = rng.standard_normal(B * P - 7)
+    x = rng.standard_normal(B * 20)
+    hp = np.concatenate([h, np.zeros(B * P - len(h))])
+
+    def pack(X):
+        p = X[:B].copy()
+        p[0] = X[0].real + 1j * X[B].real
+        return p
+
+    H = [pack(np.fft.rfft(np.concatenate([hp[k * B:(k + 1) * B], np.zeros(B)]))) / (2 * B) for k in range(P)]
+    fdl = [np.zeros(B, complex) for _ in range(P)]
+    prev = np.zeros(B)
+    y = []
+    for t in range(len(x) // B):
+        cur = x[t * B:(t + 1) * B]
+        fdl = [pack(np.fft.rfft(np.concatenate([prev, cur])))] + fdl[:-1]
+        prev = cur
+        Y = np.zeros(B, complex)
+        for k in range(P):
+            prod = fdl[k] * H[k]
+            prod[0] = fdl[k][0].real * H[k][0].real + 1j * fdl[k][0].imag * H[k][0].imag
+            Y += prod
+        full = np.concatenate([[Y[0].real], Y[1:], [Y[0].imag]])
+        y.append(np.fft.irfft(full, 2 * B)[B:] * 2 * B)
+    y = np.concatenate(y)
+    assert np.allclose(y, np.convolve(x, h)[:len(x)])
