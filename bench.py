@@ -218,7 +218,7 @@ def run_ours(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "mac_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                traffic = int(json.load(f)["dram_bytes_per_instance"] * K)  # ncu --set full capture, scaled per instance
         except Exception:
             pass
         roof = {"kernel": "k_mac (FDL complex MAC, TMA-staged)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
