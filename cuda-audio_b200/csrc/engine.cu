@@ -42,43 +42,35 @@ typedef void (*inv_fn)(const InvArgs);
 
 struct MacVariant { mac_fn fn; uint32_t smem; int kc; };
 
-template <int BT, int NIN, int NOUT, int MULT, int NSTAGE>
+template <int BT, int NOUT, int MULT, int NSTAGE>
 MacVariant mac_variant()
 {
     constexpr int G = kMacConsumers / (BT / 2);
-    using Cfg = MacCfg<BT, NIN, NOUT, G * MULT, NSTAGE>;
-    return MacVariant{k_mac<BT, NIN, NOUT, G * MULT, NSTAGE>, Cfg::SMEM_BYTES, G * MULT};
+    using Cfg = MacCfg<BT, NOUT, G * MULT, NSTAGE>;
+    return MacVariant{k_mac<BT, NOUT, G * MULT, NSTAGE>, Cfg::SMEM_BYTES, G * MULT};
 }
 
-template <int BT, int NIN, int NOUT>
+// stage = G*MULT rows of (1 + NOUT) arrays of BT complex; BT = 256, NOUT = 2: 12 KB * MULT
+template <int BT, int NOUT>
 MacVariant mac_pick_v(int variant)
 {
     switch (variant) {
-    case 0: return mac_variant<BT, NIN, NOUT, 2, 4>();   // 192 KB at 2x2: 1 CTA / SM
-    case 2: return mac_variant<BT, NIN, NOUT, 1, 3>();   //  72 KB at 2x2: 3 CTAs / SM
-    case 3: return mac_variant<BT, NIN, NOUT, 2, 2>();   //  96 KB, deeper rows
-    case 4: return mac_variant<BT, NIN, NOUT, 1, 2>();   //  48 KB at 2x2: 4 CTAs / SM
-    case 5: return mac_variant<BT, NIN, NOUT, 1, 6>();   // 144 KB at 2x2: 1 CTA / SM, deep
-    default: return mac_variant<BT, NIN, NOUT, 1, 4>();  //  96 KB at 2x2: 2 CTAs / SM (measured best)
+    case 0: return mac_variant<BT, NOUT, 4, 4>();   // 192 KB: 1 CTA / SM
+    case 2: return mac_variant<BT, NOUT, 2, 3>();   //  72 KB: 3 CTAs / SM
+    case 3: return mac_variant<BT, NOUT, 4, 2>();   //  96 KB, longer stages
+    case 4: return mac_variant<BT, NOUT, 1, 4>();   //  48 KB: 4 CTAs / SM
+    case 5: return mac_variant<BT, NOUT, 2, 6>();   // 144 KB: 1 CTA / SM, deep
+    default: return mac_variant<BT, NOUT, 2, 4>();  //  96 KB: 2 CTAs / SM (measured best)
     }
 }
 
-template <int BT>
-MacVariant mac_pick_io(int n_in, int n_out, int variant)
-{
-    if (n_in == 1 && n_out == 1) return mac_pick_v<BT, 1, 1>(variant);
-    if (n_in == 1 && n_out == 2) return mac_pick_v<BT, 1, 2>(variant);
-    if (n_in == 2 && n_out == 1) return mac_pick_v<BT, 2, 1>(variant);
-    return mac_pick_v<BT, 2, 2>(variant);
-}
-
-MacVariant mac_pick(int bt, int n_in, int n_out, int variant)
+MacVariant mac_pick(int bt, int n_out, int variant)
 {
     switch (bt) {
-    case 32: return mac_pick_io<32>(n_in, n_out, variant);
-    case 64: return mac_pick_io<64>(n_in, n_out, variant);
-    case 128: return mac_pick_io<128>(n_in, n_out, variant);
-    default: return mac_pick_io<256>(n_in, n_out, variant);
+    case 32: return n_out == 1 ? mac_pick_v<32, 1>(variant) : mac_pick_v<32, 2>(variant);
+    case 64: return n_out == 1 ? mac_pick_v<64, 1>(variant) : mac_pick_v<64, 2>(variant);
+    case 128: return n_out == 1 ? mac_pick_v<128, 1>(variant) : mac_pick_v<128, 2>(variant);
+    default: return n_out == 1 ? mac_pick_v<256, 1>(variant) : mac_pick_v<256, 2>(variant);
     }
 }
 
@@ -107,7 +99,7 @@ struct ca_engine {
     ca_config cfg{};
     int device = 0;
     uint32_t B = 0, R = 0, P = 0, Lring = 0, k_off = 0, tiles = 1, bt = 0;
-    uint32_t n_inst = 0, n_active = 0, n_in = 0, n_out = 0, n_split = 1, pps = 0;
+    uint32_t n_inst = 0, n_active = 0, n_in = 0, n_out = 0, n_split = 1, nv = 2, ring_len = 16384, ring_out = 0;
     cudaStream_t stream = nullptr;
     // device memory
     unsigned char *d_arena = nullptr;  // [H | X] contiguous (one L2 access-policy window)
@@ -115,7 +107,7 @@ struct ca_engine {
     float2 *d_H = nullptr, *d_X = nullptr, *d_Ypart = nullptr, *d_tw = nullptr;
     float *d_ring = nullptr, *d_in = nullptr, *d_out = nullptr;
     InParamDev *d_par = nullptr;
-    InStateDev *d_st = nullptr;
+    ItemState *d_st = nullptr;
     Ctl *d_ctl = nullptr;
     uint64_t device_bytes = 0;
     // pinned host staging
@@ -193,12 +185,14 @@ int flush_params(ca_engine *e)
 int launch_kernels(ca_engine *e, const float *d_in, float *d_out, bool profile)
 {
     const uint32_t n_items = e->n_active * e->n_in;
-    FwdArgs fa{d_in, e->d_ring, e->d_X, e->d_par, e->d_st, e->d_ctl, e->d_tw, e->d_tw + e->B, n_items, e->n_in, e->Lring};
-    MacArgs ma{e->d_X, e->d_H, e->d_Ypart, e->d_par, e->d_ctl, e->Lring, e->P, e->B, e->k_off, e->n_split, e->pps,
-               (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u};
-    InvArgs ia{e->d_Ypart, d_in, d_out, e->d_par, e->d_ctl, e->d_tw, e->d_tw + e->B, e->n_split, e->n_in, e->n_out};
+    const uint32_t n_alloc = e->n_inst * e->n_in;
+    FwdArgs fa{d_in, e->d_ring, e->d_X, e->d_par, e->d_st, e->d_ctl, e->d_tw, e->d_tw + e->B,
+               n_items, n_alloc, e->n_in, e->nv, e->Lring, e->ring_len, e->ring_out};
+    MacArgs ma{e->d_X, e->d_H, e->d_Ypart, e->d_par, e->d_st, e->d_ctl, n_alloc, e->n_in, e->nv, e->Lring, e->P, e->B, e->k_off,
+               1u, 1u, e->n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u};
+    InvArgs ia{e->d_Ypart, d_in, d_out, nullptr, e->d_par, e->d_ctl, e->d_tw, e->d_tw + e->B, e->n_split, e->n_in, e->n_out, 0u};
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
+    e->fft.fwd<<<(n_items * e->nv + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
     e->mac.fn<<<dim3(e->n_split, e->tiles, e->n_active), kMacThreads, e->mac.smem, e->stream>>>(ma);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
@@ -325,11 +319,12 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     e->fft = fft_pick((int)e->R);
     int variant = 1;
     if (const char *v = getenv("CA_MAC_VARIANT")) variant = atoi(v);
-    e->mac = mac_pick((int)e->bt, (int)e->n_in, (int)e->n_out, variant);
+    e->mac = mac_pick((int)e->bt, (int)e->n_out, variant);
+    e->nv = cfg->max_voices ? cfg->max_voices : 2u;
     CA_CUDA(cudaFuncSetAttribute((const void *)e->mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mac.smem));
 
-    // split of the partition range per instance: enough CTAs to cover the SMs when few
-    // instances run (latency schedule), 1 when the batch alone fills the machine.
+    // split of the row list per instance: enough CTAs to cover the SMs when few instances run
+    // (latency schedule), 1 when the batch alone fills the machine.
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     uint32_t split = cfg->mac_split;
@@ -337,11 +332,12 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         const uint64_t ctas = (uint64_t)e->n_inst * e->tiles;
         split = ctas >= (uint64_t)2 * sms ? 1u : (uint32_t)std::min<uint64_t>(32, (2 * (uint64_t)sms + ctas - 1) / ctas);
     }
-    const uint32_t max_split = std::max<uint32_t>(1, (e->P + e->mac.kc - 1) / e->mac.kc);
-    split = std::max<uint32_t>(1, std::min(split, max_split));
-    e->pps = (e->P + split - 1) / split;
-    e->pps = ((e->pps + e->mac.kc - 1) / e->mac.kc) * e->mac.kc;  // whole stages per split
-    e->n_split = (e->P + e->pps - 1) / e->pps;
+    const uint32_t rows = e->P * e->n_in;  // steady state: one voice per input
+    e->n_split = std::max<uint32_t>(1, std::min(split, std::max<uint32_t>(1, rows / (uint32_t)e->mac.kc)));
+    // time-domain ring per voice: predelay reach + the two blocks of the overlap-save window
+    e->ring_len = 1;
+    while (e->ring_len < kMaxPredelay + 2 * e->B) e->ring_len <<= 1;
+    e->ring_out = std::max(e->Lring, e->ring_len / e->B) + 2;
 
     CA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CA_CUDA(cudaEventCreate(&ev));
@@ -349,7 +345,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
     e->h_bytes = (size_t)cfg->n_ir_slots * e->n_out * e->P * e->B * sizeof(float2);
-    e->x_bytes = n_items * e->Lring * e->B * sizeof(float2);
+    e->x_bytes = n_items * e->nv * e->Lring * e->B * sizeof(float2);
     e->arena_bytes = e->h_bytes + e->x_bytes;
     CA_CUDA(cudaMalloc(&e->d_arena, e->arena_bytes));
     e->d_H = reinterpret_cast<float2 *>(e->d_arena);
@@ -358,21 +354,21 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     const size_t yp_bytes = (size_t)e->n_inst * e->n_split * e->n_out * e->B * sizeof(float2);
     CA_CUDA(cudaMalloc(&e->d_Ypart, yp_bytes));
     CA_CUDA(cudaMemsetAsync(e->d_Ypart, 0, yp_bytes, e->stream));
-    const size_t ring_bytes = n_items * kRing * sizeof(float);
+    const size_t ring_bytes = n_items * e->nv * e->ring_len * sizeof(float);
     CA_CUDA(cudaMalloc(&e->d_ring, ring_bytes));
     CA_CUDA(cudaMemsetAsync(e->d_ring, 0, ring_bytes, e->stream));
     const size_t in_bytes = n_items * e->B * sizeof(float), out_bytes = (size_t)e->n_inst * e->n_out * e->B * sizeof(float);
     CA_CUDA(cudaMalloc(&e->d_in, in_bytes));
     CA_CUDA(cudaMalloc(&e->d_out, out_bytes));
     CA_CUDA(cudaMalloc(&e->d_par, n_items * sizeof(InParamDev)));
-    CA_CUDA(cudaMalloc(&e->d_st, n_items * sizeof(InStateDev)));
-    CA_CUDA(cudaMemsetAsync(e->d_st, 0, n_items * sizeof(InStateDev), e->stream));
+    CA_CUDA(cudaMalloc(&e->d_st, 2 * n_items * sizeof(ItemState)));
+    CA_CUDA(cudaMemsetAsync(e->d_st, 0, 2 * n_items * sizeof(ItemState), e->stream));
     CA_CUDA(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
     CA_CUDA(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
     CA_CUDA(cudaMallocHost(&e->h_in, in_bytes));
     CA_CUDA(cudaMallocHost(&e->h_out, out_bytes));
     for (auto &u : e->h_upload) CA_CUDA(cudaMallocHost(&u, n_items * sizeof(InParamDev)));
-    e->device_bytes = e->arena_bytes + yp_bytes + ring_bytes + in_bytes + out_bytes + n_items * (sizeof(InParamDev) + sizeof(InStateDev));
+    e->device_bytes = e->arena_bytes + yp_bytes + ring_bytes + in_bytes + out_bytes + n_items * (sizeof(InParamDev) + 2 * sizeof(ItemState));
 
     // twiddles, fp64 -> fp32: [W_M^n, n < M | W_2M^k, k < M]
     {
@@ -427,6 +423,7 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     if (cfg->struct_size != sizeof(ca_config)) { g_last_error = "ca_config.struct_size mismatch"; return CA_ERR_INVALID; }
     if (!is_pow2(cfg->period) || cfg->period < 32 || cfg->period > 1024) { g_last_error = "period must be a power of two in [32, 1024]"; return CA_ERR_INVALID; }
     if (cfg->n_in < 1 || cfg->n_in > 2 || cfg->n_out < 1 || cfg->n_out > 2) { g_last_error = "n_in / n_out must be 1 or 2"; return CA_ERR_INVALID; }
+    if (cfg->max_voices > (uint32_t)kMaxVoices) { g_last_error = "max_voices must be <= 4"; return CA_ERR_INVALID; }
     if (!cfg->n_instances || !cfg->max_ir_frames || !cfg->n_ir_slots) { g_last_error = "n_instances, max_ir_frames, n_ir_slots must be > 0"; return CA_ERR_INVALID; }
     if (cfg->n_tiers > 1) { g_last_error = "non-uniform tiers are not available in this build"; return CA_ERR_UNSUPPORTED; }
     int ndev = 0;
@@ -443,12 +440,13 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     return CA_OK;
 }
 
-int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames)
+static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames, uint32_t stride)
 {
     if (!e || !d_left || slot >= e->cfg.n_ir_slots) return CA_ERR_INVALID;
     if (e->n_out == 2 && !d_right) return CA_ERR_INVALID;
     CA_CUDA(cudaSetDevice(e->device));
     IrArgs a{};
+    a.stride = stride;
     a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
     a.H = e->d_H + (size_t)slot * e->n_out * e->P * e->B;
     a.twM = e->d_tw; a.tw2M = e->d_tw + e->B;
@@ -462,6 +460,17 @@ int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const fl
     e->launches += 1;
     e->ir_loaded[slot] = 1;
     return CA_OK;
+}
+
+int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames)
+{
+    return load_ir_dev(e, slot, d_left, d_right, frames, 1);
+}
+
+int ca_load_ir_interleaved_device(ca_engine *e, uint32_t slot, const float *d_lr, uint32_t frames)
+{
+    if (!d_lr) return CA_ERR_INVALID;
+    return load_ir_dev(e, slot, d_lr, d_lr + 1, frames, 2);
 }
 
 int ca_load_ir(ca_engine *e, uint32_t slot, const float *left, const float *right, uint32_t frames)

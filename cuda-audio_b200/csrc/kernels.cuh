@@ -18,8 +18,9 @@
 
 namespace ca {
 
-constexpr uint32_t kRing = 16384;  // predelay ring per (instance, input): >= 8192 + 2*B floats
+constexpr uint32_t kMaxPredelay = 8192;  // CONV_MAX_PREDELAY, conv.h:26-28
 constexpr int kFwdWarps = 4;
+constexpr int kMaxVoices = 4;
 
 // per (instance, input): written by the host (ca_set_params), read by the kernels
 struct InParamDev {
@@ -30,14 +31,28 @@ struct InParamDev {
     uint32_t glide_seq;               // glide-jump command + sequence number
     uint32_t pad;
 };
-// per (instance, input): device-owned state
-struct InStateDev {
-    float g;  // wet glide, conv.cu:15-32: g += (wet - g) / (vsteps + 5) once per period
+
+// per (instance, input): device-owned state, double-buffered by period parity.
+// The reference glides its LIVE IR spectrum toward wet * (selected IR) once per period
+// (f_interpolate, conv.cu:15-32, 339-353): Hlive <- Hlive + (wet*Hsel - Hlive)/(vsteps+5).
+// Hlive is therefore always a linear combination sum_j c_j H_j of loaded IRs whose coefficients
+// follow the same recurrence, and the whole response of input block t carries Hlive(t).
+// A "voice" is one (IR slot, coefficient c, frequency-domain delay line fed with c(t) x(t)):
+// exact for time-varying wet and for IR switches, zero extra bytes in steady state.
+struct ItemState {
+    float c[kMaxVoices];
+    uint32_t slot[kMaxVoices];
+    unsigned long long start[kMaxVoices];  // period at which the voice's delay lines were (re)started
+    uint32_t quiet[kMaxVoices];            // periods since the coefficient reached zero
+    uint32_t active;                       // bit v: voice v is audible or still ringing out
+    uint32_t fresh;                        // bit v: voice v was (re)allocated in this period
     uint32_t vsteps;
-    uint32_t vsteps_seq_seen, glide_seq_seen;
+    uint32_t vsteps_seq_seen, glide_seq_seen, pad;
 };
 struct Ctl {
-    unsigned long long t;  // period counter, advanced by k_inverse
+    // period counter.  k_forward and k_mac read t; k_forward publishes t_next = t + 1; k_inverse reads
+    // only t_next and finally sets t = t_next, so no kernel reads a field another CTA of it writes.
+    unsigned long long t, t_next;
 };
 
 // pan law, conv.cu:386-389 / 418-421
@@ -47,18 +62,65 @@ __device__ __forceinline__ float pan_gain(float pan, int o, int n_out)
     return o == 0 ? (pan >= 0.f ? 1.f - pan : 1.f) : (pan <= 0.f ? 1.f + pan : 1.f);
 }
 
+// One glide step (start of period t) for all voices of one (instance, input).
+__device__ __forceinline__ ItemState step_item_state(ItemState s, const InParamDev &p, unsigned long long t, int nv, uint32_t ring_out)
+{
+    s.fresh = 0;
+    if (s.glide_seq_seen != p.glide_seq) {  // jump: one voice at coefficient glide_cmd, history dropped
+        s.glide_seq_seen = p.glide_seq;
+        s.active = 1u; s.fresh = 1u;
+        s.slot[0] = p.select; s.c[0] = p.glide_cmd; s.start[0] = t; s.quiet[0] = 0;
+    }
+    if (s.vsteps_seq_seen != p.vsteps_seq) { s.vsteps = p.vsteps_cmd; s.vsteps_seq_seen = p.vsteps_seq; }
+    int tv = -1;
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++)
+        if (v < nv && ((s.active >> v) & 1u) && s.slot[v] == p.select) tv = v;
+    if (tv < 0) {  // new target IR: take a free voice, else steal the quietest one
+        float best = 3.0e38f;
+#pragma unroll
+        for (int v = 0; v < kMaxVoices; v++)
+            if (v < nv) {
+                const float score = ((s.active >> v) & 1u) ? fabsf(s.c[v]) : -1.0f;
+                if (score < best) { best = score; tv = v; }
+            }
+#pragma unroll
+        for (int v = 0; v < kMaxVoices; v++)
+            if (v == tv) { s.slot[v] = p.select; s.c[v] = 0.f; s.start[v] = t; s.quiet[v] = 0; }
+        s.active |= 1u << tv;
+        s.fresh |= 1u << tv;
+    }
+    const float d = (float)(s.vsteps + 5u);
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++)
+        if (v < nv && ((s.active >> v) & 1u)) {
+            const float target = (v == tv) ? p.wet : 0.f;
+            s.c[v] = s.c[v] + (target - s.c[v]) / d;  // conv.cu:27
+            if (v != tv) {
+                if (fabsf(s.c[v]) < 1e-9f) {  // inaudible (< -180 dB): stop feeding, let the delay line ring out
+                    s.c[v] = 0.f;
+                    if (++s.quiet[v] > ring_out) s.active &= ~(1u << v);
+                } else s.quiet[v] = 0;
+            }
+        }
+    if (s.vsteps > 0) s.vsteps--;  // conv.cu:345,353
+    return s;
+}
+
 // ------------------------------------------------------------------------------------------
-// forward: one warp per (instance, input)
+// forward (tier 0): one warp per (instance, input, voice)
 // ------------------------------------------------------------------------------------------
 struct FwdArgs {
-    const float *in;  // [inst][n_in][B]
-    float *ring;      // [inst*n_in][kRing]
-    float2 *X;        // FDL [inst*n_in][Lring][B]
+    const float *in;   // [inst][n_in][B]
+    float *ring;       // [(inst*n_in + i)*nv + v][ring_len]: predelayed, gain-scaled input stream
+    float2 *X;         // FDL [(inst*n_in + i)*nv + v][Lring][B]
     const InParamDev *par;
-    InStateDev *st;
-    const Ctl *ctl;
+    ItemState *st;     // [2][inst*n_in]
+    Ctl *ctl;
     const float2 *twM, *tw2M;
-    uint32_t n_items, n_in, Lring;
+    uint32_t n_items;  // active instances * n_in
+    uint32_t n_items_alloc;  // stride between the two state buffers
+    uint32_t n_in, nv, Lring, ring_len, ring_out;
 };
 
 template <int R>
@@ -66,63 +128,68 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
 {
     constexpr int B = 32 * R;
     const int lane = threadIdx.x & 31;
-    const uint32_t item = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
-    if (item >= a.n_items) return;
-    WarpFft<R> f;
-    f.init(a.twM);
+    const uint32_t w = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
+    if (w >= a.n_items * a.nv) return;
+    const uint32_t item = w / a.nv, v = w % a.nv;
     const unsigned long long t = a.ctl->t;
+    if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
 
-    // --- parameters: wet glide (one step per period) and gain of this block ---
+    // --- parameters: every warp of the item recomputes the same state step; voice 0 stores it ---
     const InParamDev p = a.par[item];
-    InStateDev s = a.st[item];
-    if (s.glide_seq_seen != p.glide_seq) { s.g = p.glide_cmd; s.glide_seq_seen = p.glide_seq; }
-    if (s.vsteps_seq_seen != p.vsteps_seq) { s.vsteps = p.vsteps_cmd; s.vsteps_seq_seen = p.vsteps_seq; }
-    s.g = s.g + (p.wet - s.g) / (float)(s.vsteps + 5u);
-    if (s.vsteps > 0) s.vsteps--;
-    const float gain = s.g * p.level;
+    const ItemState s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
+    if (v == 0 && lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+    if (!((s.active >> v) & 1u)) return;
+    float cv = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
+    const float gain = cv * p.level;
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
-    __syncwarp();
-    if (lane == 0) a.st[item] = s;
 
+    const uint32_t mask = a.ring_len - 1;
+    float *ring = a.ring + (size_t)w * a.ring_len;
+    if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
+        for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    }
     // --- predelay ring: the whole response of this block is delayed by pd (conv.cu:97) ---
-    float *ring = a.ring + (size_t)item * kRing;
     const float *x = a.in + (size_t)item * B;
-    const uint32_t base = (uint32_t)((t * (unsigned long long)B) & (kRing - 1));
-    const uint32_t prev = (base - B) & (kRing - 1);
+    const uint32_t base = (uint32_t)((t * (unsigned long long)B) & mask);
+    const uint32_t prev = (base - B) & mask;
+#pragma unroll
+    for (int j = 0; j < R; j++)  // clear the block that becomes reachable by the scatter in this period
+        ring[(base + kMaxPredelay + lane + 32 * j) & mask] = 0.f;
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < R; j++) {
         const int n = lane + 32 * j;
-        const uint32_t idx = (base + pd + n) & (kRing - 1);
+        const uint32_t idx = (base + pd + n) & mask;
         ring[idx] += gain * __ldg(&x[n]);
     }
     __syncwarp();
 
     // --- window [x'(t-1) | x'(t)] in time layout: lane a holds floats [2R a, 2R a + 2R) ---
+    WarpFft<R> f;
+    f.init(a.twM);
     const uint32_t off = ((lane < 16) ? prev : base) + 2 * R * (lane & 15);
-    float2 v[R];
+    float2 z[R];
     if constexpr (R == 1) {
-        v[0] = *reinterpret_cast<const float2 *>(ring + off);
-        if (lane < 16) *reinterpret_cast<float2 *>(ring + off) = make_float2(0.f, 0.f);
+        z[0] = *reinterpret_cast<const float2 *>(ring + off);
     } else {
 #pragma unroll
         for (int j = 0; j < R / 2; j++) {
             const float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
-            v[2 * j] = make_float2(q.x, q.y);
-            v[2 * j + 1] = make_float2(q.z, q.w);
-        }
-        if (lane < 16) {  // block t-1 is consumed: clear it for its next use
-#pragma unroll
-            for (int j = 0; j < R / 2; j++) *reinterpret_cast<float4 *>(ring + off + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+            z[2 * j] = make_float2(q.x, q.y);
+            z[2 * j + 1] = make_float2(q.z, q.w);
         }
     }
+    f.forward(z);
+    f.split_r2c(z, a.tw2M);
 
-    f.forward(v);
-    f.split_r2c(v, a.tw2M);
-
-    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(t % a.Lring);  // ring runs backwards
-    float2 *dst = a.X + ((size_t)item * a.Lring + slot) * B;
+    const unsigned long long n_fire = t + 1ull;  // tier 0 fires every period
+    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);  // ring runs backwards
+    float2 *dst = a.X + ((size_t)w * a.Lring + slot) * B;
 #pragma unroll
-    for (int d = 0; d < R; d++) dst[f.c + 32 * d] = v[d];
+    for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -133,6 +200,7 @@ struct IrArgs {
     float2 *H;          // this slot's spectra [n_out][P][B]
     const float2 *twM, *tw2M;
     uint32_t frames, P, n_out, k_begin;
+    uint32_t stride;    // 1 = planar, 2 = (L, R) interleaved like WavFile::buffer (wav.h:10)
     float scale;        // 1/(2B): both FFT normalisations live in H
 };
 
@@ -153,8 +221,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_ir_fft(const IrArgs a)
         float re = 0.f, im = 0.f;
         if (lane < 16) {  // [h_k | 0]: the IR block sits in the first half of the 2B window
             const size_t n0 = (size_t)(a.k_begin + k) * B + 2 * (R * lane + b);
-            if (n0 < a.frames) re = __ldg(&h[n0]) * a.scale;
-            if (n0 + 1 < a.frames) im = __ldg(&h[n0 + 1]) * a.scale;
+            if (n0 < a.frames) re = __ldg(&h[n0 * a.stride]) * a.scale;
+            if (n0 + 1 < a.frames) im = __ldg(&h[(n0 + 1) * a.stride]) * a.scale;
         }
         v[b] = make_float2(re, im);
     }
@@ -219,122 +287,172 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uin
         : "memory");
 }
 
+// One launch = one tier of one period for every active instance.  The work of an instance is the
+// flattened list of (stream, partition) rows, stream = (input, voice); a row is the FDL spectrum
+// X_s[n - k] plus the n_out IR spectra H_s,o[k] it multiplies.  Rows are cut into n_split
+// contiguous ranges (one CTA each) so few instances still cover all SMs; bins are cut into tiles
+// of BT complex.
 struct MacArgs {
-    const float2 *X;  // FDL [inst*n_in][Lring][S]
-    const float2 *H;  // IR bank [slot][n_out][P][S]
-    float2 *Ypart;    // [inst][n_split][n_out][S]
+    const float2 *X;   // FDL [(inst*n_in + i)*nv + v][Lring][S]
+    const float2 *H;   // IR bank [slot][n_out][P][S]
+    float2 *Ypart;     // [inst][n_split][n_out][S]
     const InParamDev *par;
+    const ItemState *st;  // [2][n_items_alloc]
     const Ctl *ctl;
+    uint32_t n_items_alloc;
+    uint32_t n_in, nv;
     uint32_t Lring, P, S;
-    uint32_t k_off;   // FDL delay of this engine's first partition (partition-range shards)
-    uint32_t n_split, parts_per_split;
+    uint32_t k_off;    // FDL delay of this engine's first partition (partition-range shards)
+    uint32_t m;        // tier block / period: the tier fires when (t_end / period) % m == 0
+    uint32_t t_bias;   // 1 for tier 0 (runs before k_inverse advances ctl->t), 0 for deferred tiers
+    uint32_t n_split;
     uint32_t stream_hint;
 };
 
 constexpr int kMacConsumers = 256;
 constexpr int kMacThreads = kMacConsumers + 32;
+constexpr int kMaxStreams = 2 * kMaxVoices;
 
-template <int BT, int NIN, int NOUT, int KC, int NSTAGE>
+template <int BT, int NOUT, int KC, int NSTAGE>
 struct MacCfg {
-    static constexpr int NARR = NIN * (1 + NOUT);           // rows per partition per stage
-    static constexpr int LR = BT / 2;                       // float4 lanes per row
-    static constexpr int G = kMacConsumers / LR;            // partitions processed concurrently
-    static constexpr uint32_t ROW_BYTES = BT * 8;
-    static constexpr uint32_t STAGE_BYTES = KC * NARR * ROW_BYTES;
+    static constexpr int NARR = 1 + NOUT;                   // arrays per row: X, H_0 .. H_{NOUT-1}
+    static constexpr int LR = BT / 2;                       // float4 lanes per array
+    static constexpr int G = kMacConsumers / LR;            // rows processed concurrently
+    static constexpr uint32_t ARR_BYTES = BT * 8;
+    static constexpr uint32_t STAGE_BYTES = KC * NARR * ARR_BYTES;
     static constexpr uint32_t SMEM_BYTES = NSTAGE * STAGE_BYTES + 2 * NSTAGE * 8 + 16;
     static_assert(KC % G == 0, "stage rows must be a multiple of the row groups");
-    static_assert(G * NIN * NOUT * LR * 16 + G * NIN * NOUT * 8 <= NSTAGE * STAGE_BYTES, "reduction scratch must fit");
+    static_assert(G * NOUT * LR * 16 + G * NOUT * 8 <= NSTAGE * STAGE_BYTES, "reduction scratch must fit");
 };
 
-template <int BT, int NIN, int NOUT, int KC, int NSTAGE>
+template <int BT, int NOUT, int KC, int NSTAGE>
 __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
 {
-    using Cfg = MacCfg<BT, NIN, NOUT, KC, NSTAGE>;
+    using Cfg = MacCfg<BT, NOUT, KC, NSTAGE>;
     constexpr int NARR = Cfg::NARR, LR = Cfg::LR, G = Cfg::G;
     extern __shared__ __align__(128) unsigned char smem[];
     float4 *stage = reinterpret_cast<float4 *>(smem);  // [NSTAGE][KC][NARR][LR] float4
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + NSTAGE * Cfg::STAGE_BYTES);
     uint64_t *empty = full + NSTAGE;
+    __shared__ uint32_t s_rowstart[kMaxStreams + 1];  // prefix sum of rows per stream
+    __shared__ uint32_t s_slot[kMaxStreams];
+    __shared__ float s_pan[2][NOUT];
 
     const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    const uint32_t k_begin = split * a.parts_per_split;
-    const uint32_t k_end = min(a.P, k_begin + a.parts_per_split);
-    const int nparts = k_end > k_begin ? (int)(k_end - k_begin) : 0;
-    const int n_iter = (nparts + KC - 1) / KC;
+    const uint32_t ns = a.n_in * a.nv;
+    const unsigned long long tend = a.ctl->t + a.t_bias;  // periods completed at the end of this tier block
+    const unsigned long long n_fire = tend / a.m;
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMacConsumers / 32); }
         mbar_fence_init();
+        uint32_t acc = 0;
+        for (uint32_t s = 0; s < ns; s++) {
+            const uint32_t i = s / a.nv, v = s % a.nv;
+            const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + inst * a.n_in + i];
+            s_rowstart[s] = acc;
+            uint32_t nk = 0, slot = 0;
+            if ((st.active >> v) & 1u) {
+                // partition k reads the block fired at index n_fire - k_off - k; it is valid when that
+                // block was built after the voice's (re)start: fire * m - 1 >= start
+                const long long first_fire = (long long)((st.start[v] + a.m) / a.m);  // ceil((start + 1) / m)
+                const long long cnt = (long long)n_fire - first_fire + 1 - (long long)a.k_off;
+                nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
+                slot = st.slot[v];
+            }
+            s_slot[s] = slot;
+            acc += nk;
+        }
+        for (uint32_t s = ns; s <= kMaxStreams; s++) s_rowstart[s] = acc;
+        for (uint32_t i = 0; i < 2; i++)
+            for (int o = 0; o < NOUT; o++) s_pan[i][o] = pan_gain(a.par[inst * a.n_in + min(i, a.n_in - 1)].panWet, o, NOUT);
     }
     __syncthreads();
 
-    float4 acc[NIN][NOUT];
-    float2 e0[NIN][NOUT];  // bin 0 = (DC, Nyquist): two real products, not a complex one
+    const uint32_t total = s_rowstart[kMaxStreams];
+    const uint32_t boundary = s_rowstart[a.nv];  // first row of input 1 (== total when n_in == 1)
+    uint32_t rps = (total + a.n_split - 1) / a.n_split;
+    rps = ((rps + KC - 1) / KC) * KC;
+    const uint32_t r_begin = min(total, split * rps), r_end = min(total, r_begin + rps);
+    const int nrows = (int)(r_end - r_begin);
+    const int n_iter = (nrows + KC - 1) / KC;
+
+    float4 acc[NOUT], y[NOUT];
+    float2 e0[NOUT], y0[NOUT];  // bin 0 = (DC, Nyquist): two real products, not a complex one
 #pragma unroll
-    for (int i = 0; i < NIN; i++)
-#pragma unroll
-        for (int o = 0; o < NOUT; o++) { acc[i][o] = make_float4(0.f, 0.f, 0.f, 0.f); e0[i][o] = make_float2(0.f, 0.f); }
+    for (int o = 0; o < NOUT; o++) {
+        acc[o] = y[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        e0[o] = y0[o] = make_float2(0.f, 0.f);
+    }
 
     if (warp == kMacConsumers / 32) {
         // ===== producer warp: every lane issues its own bulk copies =====
-        const unsigned long long t = a.ctl->t;
-        const uint32_t head = (a.Lring - 1u) - (uint32_t)(t % a.Lring);
+        const uint32_t head = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
         const uint64_t pol = a.stream_hint ? l2_policy_evict_first() : l2_policy_evict_last();
-        const uint32_t sel0 = a.par[inst * NIN].select;
-        const uint32_t sel1 = a.par[inst * NIN + (NIN - 1)].select;
         for (int it = 0; it < n_iter; it++) {
             const int st = it % NSTAGE;
             const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
             if (it >= NSTAGE) mbar_wait(&empty[st], ph ^ 1u);
-            const int rows = min(KC, nparts - it * KC);
-            if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)rows * NARR * Cfg::ROW_BYTES);
+            const int rows = min(KC, nrows - it * KC);
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)rows * NARR * Cfg::ARR_BYTES);
             __syncwarp();
             for (int cidx = lane; cidx < rows * NARR; cidx += 32) {
-                const int r = cidx / NARR, arr = cidx % NARR;
-                const int i = arr / (1 + NOUT), w = arr % (1 + NOUT);
-                const uint32_t k = k_begin + it * KC + r;
+                const int r = cidx / NARR, w = cidx % NARR;
+                const uint32_t rho = r_begin + it * KC + r;
+                uint32_t s = 0;
+#pragma unroll
+                for (int q = 1; q < kMaxStreams; q++) s += (rho >= s_rowstart[q]) ? 1u : 0u;
+                const uint32_t k = rho - s_rowstart[s];
                 const float2 *src;
                 if (w == 0) {
                     const uint32_t slot = (head + a.k_off + k) % a.Lring;
-                    src = a.X + ((size_t)(inst * NIN + i) * a.Lring + slot) * a.S + tile * BT;
+                    src = a.X + ((size_t)(inst * ns + s) * a.Lring + slot) * a.S + tile * BT;
                 } else {
-                    src = a.H + (((size_t)(i == 0 ? sel0 : sel1) * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
+                    src = a.H + (((size_t)s_slot[s] * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
                 }
-                float4 *dst = stage + ((size_t)(st * KC + r) * NARR + arr) * LR;
-                tma_load_1d(dst, src, Cfg::ROW_BYTES, &full[st], pol);
+                float4 *dst = stage + ((size_t)(st * KC + r) * NARR + w) * LR;
+                tma_load_1d(dst, src, Cfg::ARR_BYTES, &full[st], pol);
             }
         }
     } else {
-        // ===== consumers: thread (g, q) owns bins (2q, 2q+1) of every G-th partition =====
+        // ===== consumers: thread (g, q) owns bins (2q, 2q+1) of every G-th row =====
         const int q = tid % LR, g = tid / LR;
         const bool bin0 = (q == 0) && (tile == 0);
+        bool second = false;  // rows of input 1 reached: input 0's sum has been folded into y with its pan
         for (int it = 0; it < n_iter; it++) {
             const int st = it % NSTAGE;
             const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-            const int rows = min(KC, nparts - it * KC);
+            const int rows = min(KC, nrows - it * KC);
             mbar_wait(&full[st], ph);
 #pragma unroll
             for (int rr = 0; rr < KC / G; rr++) {
                 const int r = g + rr * G;
                 if (r < rows) {
-                    const float4 *row = stage + ((size_t)(st * KC + r) * NARR) * LR + q;
-#pragma unroll
-                    for (int i = 0; i < NIN; i++) {
-                        const float4 x = row[(i * (1 + NOUT)) * LR];
+                    if (!second && r_begin + it * KC + r >= boundary) {
+                        second = true;
 #pragma unroll
                         for (int o = 0; o < NOUT; o++) {
-                            const float4 h = row[(i * (1 + NOUT) + 1 + o) * LR];
-                            acc[i][o].x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc[i][o].x));
-                            acc[i][o].y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc[i][o].y));
-                            acc[i][o].z = fmaf(x.z, h.z, fmaf(-x.w, h.w, acc[i][o].z));
-                            acc[i][o].w = fmaf(x.z, h.w, fmaf(x.w, h.z, acc[i][o].w));
-                            if (bin0) {
-                                e0[i][o].x = fmaf(x.x, h.x, e0[i][o].x);
-                                e0[i][o].y = fmaf(x.y, h.y, e0[i][o].y);
-                            }
+                            const float pan = s_pan[0][o];
+                            y[o].x = pan * acc[o].x; y[o].y = pan * acc[o].y; y[o].z = pan * acc[o].z; y[o].w = pan * acc[o].w;
+                            y0[o].x = pan * e0[o].x; y0[o].y = pan * e0[o].y;
+                            acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            e0[o] = make_float2(0.f, 0.f);
+                        }
+                    }
+                    const float4 *row = stage + ((size_t)(st * KC + r) * NARR) * LR + q;
+                    const float4 x = row[0];
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) {
+                        const float4 h = row[(1 + o) * LR];
+                        acc[o].x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc[o].x));
+                        acc[o].y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc[o].y));
+                        acc[o].z = fmaf(x.z, h.z, fmaf(-x.w, h.w, acc[o].z));
+                        acc[o].w = fmaf(x.z, h.w, fmaf(x.w, h.z, acc[o].w));
+                        if (bin0) {
+                            e0[o].x = fmaf(x.x, h.x, e0[o].x);
+                            e0[o].y = fmaf(x.y, h.y, e0[o].y);
                         }
                     }
                 }
@@ -342,58 +460,57 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         }
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) {  // fold the last input's sum with its pan (conv.cu:392-401)
+            const float pan = s_pan[second ? 1 : 0][o];
+            y[o].x = fmaf(pan, acc[o].x, y[o].x); y[o].y = fmaf(pan, acc[o].y, y[o].y);
+            y[o].z = fmaf(pan, acc[o].z, y[o].z); y[o].w = fmaf(pan, acc[o].w, y[o].w);
+            y0[o].x = fmaf(pan, e0[o].x, y0[o].x); y0[o].y = fmaf(pan, e0[o].y, y0[o].y);
+        }
     }
 
-    // ===== cross-group reduction (fixed order => deterministic), pan, store partial =====
+    // ===== cross-group reduction (fixed order => deterministic), store the partial spectrum =====
     __syncthreads();  // every TMA write has landed and been consumed: stage memory is free
-    float4 *red = reinterpret_cast<float4 *>(smem);                     // [G][NIN][NOUT][LR]
-    float2 *red0 = reinterpret_cast<float2 *>(red + G * NIN * NOUT * LR);  // [G][NIN][NOUT]
+    float4 *red = reinterpret_cast<float4 *>(smem);                  // [G][NOUT][LR]
+    float2 *red0 = reinterpret_cast<float2 *>(red + G * NOUT * LR);  // [G][NOUT]
     if (tid < kMacConsumers) {
         const int q = tid % LR, g = tid / LR;
 #pragma unroll
-        for (int i = 0; i < NIN; i++)
-#pragma unroll
-            for (int o = 0; o < NOUT; o++) {
-                red[((g * NIN + i) * NOUT + o) * LR + q] = acc[i][o];
-                if (q == 0) red0[(g * NIN + i) * NOUT + o] = e0[i][o];
-            }
+        for (int o = 0; o < NOUT; o++) {
+            red[(g * NOUT + o) * LR + q] = y[o];
+            if (q == 0) red0[g * NOUT + o] = y0[o];
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < NOUT * LR; idx += kMacThreads) {
         const int o = idx / LR, q = idx % LR;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 s0 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NIN; i++) {
-            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-            float2 s0 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const float4 v = red[((g * NIN + i) * NOUT + o) * LR + q];
-                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
-                const float2 u = red0[(g * NIN + i) * NOUT + o];
-                s0.x += u.x; s0.y += u.y;
-            }
-            if (q == 0 && tile == 0) { sacc.x = s0.x; sacc.y = s0.y; }
-            const float pan = pan_gain(a.par[inst * NIN + i].panWet, o, NOUT);
-            y.x = fmaf(pan, sacc.x, y.x); y.y = fmaf(pan, sacc.y, y.y);
-            y.z = fmaf(pan, sacc.z, y.z); y.w = fmaf(pan, sacc.w, y.w);
+        for (int g = 0; g < G; g++) {
+            const float4 v = red[(g * NOUT + o) * LR + q];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            const float2 u = red0[g * NOUT + o];
+            s0.x += u.x; s0.y += u.y;
         }
+        if (q == 0 && tile == 0) { sum.x = s0.x; sum.y = s0.y; }
         float2 *dst = a.Ypart + (((size_t)inst * a.n_split + split) * NOUT + o) * a.S + tile * BT + 2 * q;
-        *reinterpret_cast<float4 *>(dst) = y;
+        *reinterpret_cast<float4 *>(dst) = sum;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// inverse: one CTA per (instance, output)
+// inverse (tier 0): one CTA per (instance, output)
 // ------------------------------------------------------------------------------------------
 struct InvArgs {
     const float2 *Ypart;  // [inst][n_split][n_out][B]
     const float *in;      // [inst][n_in][B]   (dry path)
     float *out;           // [inst][n_out][B]
+    float *accring;       // [inst*n_out + o][acc_len]: output of the deferred tiers, or nullptr
     const InParamDev *par;
     Ctl *ctl;
     const float2 *twM, *tw2M;
-    uint32_t n_split, n_in, n_out;
+    uint32_t n_split, n_in, n_out, acc_len;
 };
 
 constexpr int kInvThreads = 128;
@@ -406,6 +523,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
     const uint32_t item = blockIdx.x;
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const int tid = threadIdx.x;
+    const unsigned long long t = a.ctl->t_next - 1ull;
 
     // --- sum the partial spectra of the MAC splits (fixed order) ---
     for (int f4 = tid; f4 < B / 2; f4 += kInvThreads) {
@@ -444,9 +562,13 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             float *dst = a.out + ((size_t)inst * a.n_out + o) * B + n0;
             const float *x0 = a.in + ((size_t)inst * a.n_in) * B + n0;
             const float *x1 = x0 + B;
+            float *accp = nullptr;
+            if (a.accring) accp = a.accring + (size_t)item * a.acc_len + (uint32_t)((t * (unsigned long long)B) & (a.acc_len - 1)) + n0;
             auto clampf = [](float w) { return fminf(fmaxf(w, -1.0f), 1.0f); };  // conv.cu:98
             if constexpr (R == 1) {
-                float2 y = make_float2(clampf(v[0].x), clampf(v[0].y));
+                float2 w = v[0];
+                if (accp) { const float2 q = *reinterpret_cast<const float2 *>(accp); w.x += q.x; w.y += q.y; *reinterpret_cast<float2 *>(accp) = make_float2(0.f, 0.f); }
+                float2 y = make_float2(clampf(w.x), clampf(w.y));
                 const float2 xa = *reinterpret_cast<const float2 *>(x0);
                 y.x = fmaf(dg[0], xa.x, y.x); y.y = fmaf(dg[0], xa.y, y.y);
                 if (a.n_in > 1) {
@@ -457,7 +579,13 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             } else {
 #pragma unroll
                 for (int j = 0; j < R / 2; j++) {
-                    float4 y = make_float4(clampf(v[2 * j].x), clampf(v[2 * j].y), clampf(v[2 * j + 1].x), clampf(v[2 * j + 1].y));
+                    float4 w = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+                    if (accp) {  // contributions of the long (deferred) tiers to this block; consume and clear
+                        const float4 q = *reinterpret_cast<const float4 *>(accp + 4 * j);
+                        w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w;
+                        *reinterpret_cast<float4 *>(accp + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    float4 y = make_float4(clampf(w.x), clampf(w.y), clampf(w.z), clampf(w.w));
                     const float4 xa = *reinterpret_cast<const float4 *>(x0 + 4 * j);
                     y.x = fmaf(dg[0], xa.x, y.x); y.y = fmaf(dg[0], xa.y, y.y);
                     y.z = fmaf(dg[0], xa.z, y.z); y.w = fmaf(dg[0], xa.w, y.w);
@@ -471,7 +599,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             }
         }
     }
-    if (item == 0 && tid == 0) a.ctl->t = a.ctl->t + 1ull;  // forward + MAC of this period are done
+    if (item == 0 && tid == 0) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
 }
 
 }  // namespace ca

@@ -1,0 +1,174 @@
+#include "convolution.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize) {}
+
+Convolution::~Convolution()
+{
+    if (_engine) ca_destroy(_engine);
+}
+
+void Convolution::fail(int code, const char *what)
+{
+    _lastError = code;
+    _lastErrorText = std::string(what) + ": " + ca_strerror(code) + " (" + ca_last_error_string() + ")";
+    Log::error(name, "%s", _lastErrorText.c_str());
+}
+
+// conv.cu:197-204
+void Convolution::onStart()
+{
+    activate();
+    playback[0] = addOutput("playback_1");
+    playback[1] = addOutput("playback_2");
+    capture[0] = addInput("capture_1");
+    capture[1] = addInput("capture_2");
+}
+
+// conv.cu:207-253: the stereo IR `wav` (device float2 frames, half scale) becomes bank entry idx,
+// truncated to fftSize - nframes frames.  Synchronous: wav may be destroyed on return.
+void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
+{
+    if (!wav.buffer || !wav.numFrames) { fail(CA_ERR_INVALID, "prepare: empty wav"); return; }
+    const size_t cap = _fftSize > nframes ? _fftSize - nframes : 0;
+    const size_t n = std::min(wav.numFrames, cap);
+    if (!n) { fail(CA_ERR_INVALID, "prepare: fftSize too small"); return; }
+    std::vector<float2> host(n);
+    cudaSetDevice(_device);
+    if (cudaMemcpy(host.data(), wav.buffer, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        (void)cudaGetLastError();
+        fail(CA_ERR_CUDA, "prepare: cannot read the wav buffer");
+        return;
+    }
+    HostIR &ir = _irs[idx];
+    ir.left.resize(n);
+    ir.right.resize(n);
+    for (size_t i = 0; i < n; i++) { ir.left[i] = host[i].x; ir.right[i] = host[i].y; }
+    _minPrepareFrames = std::min(_minPrepareFrames, nframes);
+    if (_engine) {
+        // running engine: load in place when the slot and the length fit, else rebuild lazily
+        if (idx < _engineSlots && n <= _engineCapFrames && ca_load_ir(_engine, (uint32_t)idx, ir.left.data(), ir.right.data(), (uint32_t)n) == CA_OK) return;
+        ca_destroy(_engine);
+        _engine = nullptr;
+    }
+}
+
+bool Convolution::buildEngine(size_t period)
+{
+    if (_irs.empty()) { fail(CA_ERR_STATE, "onProcess: no IR prepared"); return false; }
+    ca_config cfg;
+    ca_config_init(&cfg);
+    cfg.device = _device;
+    cfg.period = (uint32_t)period;
+    cfg.n_instances = 1;
+    cfg.n_in = cfg.n_out = 2;
+    size_t longest = 1;
+    for (auto &kv : _irs) longest = std::max(longest, kv.second.left.size());
+    cfg.max_ir_frames = (uint32_t)longest;
+    cfg.n_ir_slots = (uint32_t)(_irs.rbegin()->first + 1);
+    cfg.flags = _flags;
+    cfg.max_voices = 3;  // old IR + new IR + one more switch in flight during a cross-fade
+    cfg.sample_rate = samplerate ? (float)samplerate : _sampleRate;
+    int rc = ca_create(&cfg, &_engine);
+    if (rc) { _engine = nullptr; fail(rc, "ca_create"); return false; }
+    for (auto &kv : _irs) {
+        rc = ca_load_ir(_engine, (uint32_t)kv.first, kv.second.left.data(), kv.second.right.data(), (uint32_t)kv.second.left.size());
+        if (rc) { fail(rc, "ca_load_ir"); ca_destroy(_engine); _engine = nullptr; return false; }
+    }
+    _period = period;
+    _engineSlots = cfg.n_ir_slots;
+    _engineCapFrames = cfg.max_ir_frames;
+    _in.assign(2 * period, 0.f);
+    _out.assign(2 * period, 0.f);
+    _havePushed = false;
+    return true;
+}
+
+// cc[i].value is plain shared state like in the reference (conv.cu:339-427 reads it every period):
+// whatever changed since the last period is forwarded to the engine.
+void Convolution::pushParams(bool force)
+{
+    for (int i = 0; i < 2; i++) {
+        CC::Value &v = cc[i].value;
+        CC::Value &p = _pushed[i];
+        // the engine counts the glide down on the device; mirror it so `vsteps` stays observable
+        const size_t expected = _havePushed ? p.vsteps : (size_t)-1;
+        const bool vstepsChanged = v.vsteps != expected;
+        const bool changed = force || !_havePushed || vstepsChanged || v.select != p.select || v.predelay != p.predelay || v.dry != p.dry ||
+                             v.wet != p.wet || v.panDry != p.panDry || v.panWet != p.panWet || v.level != p.level || v.speed != p.speed;
+        if (changed) {
+            if (_irs.find(v.select) == _irs.end()) {
+                Log::error(name, "select %zu has no IR; keeping %zu", v.select, p.select);  // reference: nullptr deref (conv.cu:340)
+                v.select = _havePushed ? p.select : _irs.begin()->first;
+            }
+            ca_params q;
+            q.select = (uint32_t)v.select;
+            q.predelay = (uint32_t)std::min<size_t>(v.predelay, CA_MAX_PREDELAY - 1);
+            q.speed = (uint32_t)v.speed;
+            q.vsteps = (vstepsChanged || !_havePushed) ? (int32_t)v.vsteps : -1;
+            q.dry = v.dry; q.wet = v.wet; q.panDry = v.panDry; q.panWet = v.panWet; q.level = v.level;
+            const int rc = ca_set_params(_engine, 0, (uint32_t)i, &q);
+            if (rc) fail(rc, "ca_set_params");
+            p = v;
+        }
+        // conv.cu:345,353: one step per period
+        if (v.vsteps > 0) v.vsteps--;
+        p.vsteps = v.vsteps;
+    }
+    _havePushed = true;
+}
+
+// conv.cu:287-466
+void Convolution::onProcess(size_t nframes)
+{
+    auto *IN1 = capture[0] ? (float *)jack_port_get_buffer(capture[0], (jack_nframes_t)nframes) : nullptr;
+    auto *IN2 = capture[1] ? (float *)jack_port_get_buffer(capture[1], (jack_nframes_t)nframes) : nullptr;
+    auto *L = playback[0] ? (float *)jack_port_get_buffer(playback[0], (jack_nframes_t)nframes) : nullptr;
+    auto *R = playback[1] ? (float *)jack_port_get_buffer(playback[1], (jack_nframes_t)nframes) : nullptr;
+    if (!IN1 || !IN2 || !L || !R) return;  // conv.cu:297
+
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!_engine || _period != nframes) {
+        if (_engine) { ca_destroy(_engine); _engine = nullptr; }
+        if (!buildEngine(nframes)) { memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); return; }
+    }
+    pushParams(false);
+    memcpy(_in.data(), IN1, nframes * sizeof(float));
+    memcpy(_in.data() + nframes, IN2, nframes * sizeof(float));
+    const int rc = ca_process(_engine, _in.data(), _out.data(), (uint32_t)nframes);
+    if (rc) { fail(rc, "ca_process"); memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); return; }
+    memcpy(L, _out.data(), nframes * sizeof(float));
+    memcpy(R, _out.data() + nframes, nframes * sizeof(float));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (++_nruns > 0) _runtimeMs += ms;  // conv.cu:462
+}
+
+// handleCC, conv.cu:255-276
+static void handleCC(Convolution::CC &cc, uint8_t m1, uint8_t m2, int v, size_t nb)
+{
+    if (cc.message != m1) return;
+    if (cc.select == m2) { cc.value.select = (size_t)v * nb / 0x80; cc.value.vsteps = cc.value.speed; Log::info("conv", "Selected IR %zu", cc.value.select); }
+    if (cc.predelay == m2) cc.value.predelay = (size_t)v * CONV_MAX_PREDELAY / 0x80;
+    if (cc.dry == m2) cc.value.dry = v / 128.0f;
+    if (cc.wet == m2) cc.value.wet = v / 128.0f;
+    if (cc.panDry == m2) cc.value.panDry = v / 64.0f - 1;
+    if (cc.panWet == m2) cc.value.panWet = v / 64.0f - 1;
+    if (cc.level == m2) cc.value.level = v / 128.0f;
+    if (cc.speed == m2) {
+        cc.value.speed = ((size_t)v * CONV_MAX_SPEED) / 0x80;
+        if (cc.value.vsteps > cc.value.speed) cc.value.vsteps = cc.value.speed;
+    }
+}
+
+// conv.cu:278-285
+void Convolution::onMidiMessage(const RawMidi::Device *sender, const uint8_t *buffer, size_t len)
+{
+    if (len < 3) return;
+    for (auto &c : cc)
+        if (c.device == sender) handleCC(c, buffer[0], buffer[1], buffer[2], _irs.size());
+}

@@ -1,0 +1,100 @@
+// convolution.h -- host-side mirror of the reference's `Convolution` class (src/conv.h:30-86)
+// on top of the B200 engine's C ABI (include/cuda_audio_b200.h).
+//
+// Same public surface, same meaning, so code written against the reference keeps working:
+//   Convolution(name, fftSize)              conv.cu:142   fftSize now only bounds the IR length
+//                                                         (IR <= fftSize - nframes, conv.cu:239)
+//   prepare(idx, wav, nframes = 1024)       conv.cu:207   stereo IR -> bank slot idx
+//   onProcess(nframes)                      conv.cu:287   one JACK period, 2 in -> 2 out
+//   onStart()                               conv.cu:197   activate + register the 4 ports
+//   cc[2] (CC numbers + .value block)       conv.h:33-50  read every period, written by anyone
+//   capture[2], playback[2]                 conv.h:56-57
+//   onMidiMessage(sender, buffer, len)      conv.cu:278   CC -> parameter mapping (handleCC)
+//   avgRuntime()                            conv.h:61     mean ms per onProcess, first 10 skipped
+// Differences, all deliberate: errors are reported (lastError()) instead of assert-aborting;
+// an out-of-range `select` is ignored instead of dereferencing nullptr (conv.cu:340); the
+// destructor frees everything (the reference leaks, conv.h:53-54).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cuda_audio_b200.h"
+#include "jack_client.h"
+#include "rawmidi.h"
+#include "wavfile.h"
+
+#ifndef CONV_DEFAULT_FFTSIZE
+#define CONV_DEFAULT_FFTSIZE (512 * 256)
+#endif
+#ifndef CONV_MAX_SPEED
+#define CONV_MAX_SPEED CA_MAX_SPEED
+#endif
+#ifndef CONV_MAX_PREDELAY
+#define CONV_MAX_PREDELAY CA_MAX_PREDELAY
+#endif
+
+class Convolution : public JackClient, public RawMidi::MessageHandler {
+public:
+    struct CC {
+        RawMidi::Device *device = nullptr;
+        uint8_t message = 0;
+        uint8_t select = 0, predelay = 0, dry = 0, wet = 0, speed = 0, panDry = 0, panWet = 0, level = 0;
+        struct Value {
+            size_t select = 0;    // IR index
+            size_t predelay = 0;  // samples, [0, 8192)
+            size_t speed = 100;   // glide length in periods
+            size_t vsteps = 0;    // glide countdown
+            float dry = 0.5f, wet = 0.5f;
+            float panDry = 0.0f, panWet = 0.0f;
+            float level = 1.0f;
+        } value;
+    } cc[2];
+
+    explicit Convolution(const std::string &name = "Conv", size_t fftSize = CONV_DEFAULT_FFTSIZE);
+    ~Convolution() override;
+
+    JackPort capture[2];
+    JackPort playback[2];
+
+    void onProcess(size_t nframes) override;
+    void onStart() override;
+    double avgRuntime() const { return _nruns > 0 ? _runtimeMs / _nruns : 0.0; }
+
+    void prepare(size_t idx, const WavFile &wav, size_t nframes = 1024);
+
+    void onMidiMessage(const RawMidi::Device *sender, const uint8_t *buffer, size_t len) override;
+
+    // --- additions (not in the reference) ---
+    int lastError() const { return _lastError; }          // ca_error of the last failing call, 0 = none
+    const std::string &lastErrorText() const { return _lastErrorText; }
+    ca_engine *engine() const { return _engine; }          // null until the first onProcess()
+    void setDevice(int device) { _device = device; }       // before the first onProcess()
+    void setFlags(uint32_t flags) { _flags = flags; }      // ca_flags, before the first onProcess()
+    void setSampleRate(float fs) { _sampleRate = fs; }
+    size_t numIRs() const { return _irs.size(); }
+
+private:
+    struct HostIR { std::vector<float> left, right; };
+    bool buildEngine(size_t period);
+    void pushParams(bool force);
+    void fail(int code, const char *what);
+
+    size_t _fftSize;
+    std::map<size_t, HostIR> _irs;  // time-domain IRs kept on the host so the engine can be (re)built
+    size_t _minPrepareFrames = 1024;
+    ca_engine *_engine = nullptr;
+    size_t _period = 0, _engineSlots = 0, _engineCapFrames = 0;
+    int _device = 0;
+    uint32_t _flags = CA_FLAG_GRAPH;
+    float _sampleRate = 48000.f;
+    CC::Value _pushed[2];
+    bool _havePushed = false;
+    std::vector<float> _in, _out;  // planar staging [2][period]
+    double _runtimeMs = 0;
+    int _nruns = -10;  // conv.h:80: discard the first couple of runs
+    int _lastError = 0;
+    std::string _lastErrorText;
+};

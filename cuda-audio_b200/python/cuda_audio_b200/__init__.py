@@ -21,7 +21,7 @@ FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE = 1, 2, 4, 8
 
 EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_create", "ca_destroy",
-    "ca_load_ir", "ca_load_ir_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
+    "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
     "ca_host_alloc", "ca_host_free",
 ]
@@ -37,7 +37,7 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("period", C.c_uint32),
                 ("n_instances", C.c_uint32), ("n_in", C.c_uint32), ("n_out", C.c_uint32),
                 ("max_ir_frames", C.c_uint32), ("n_ir_slots", C.c_uint32), ("flags", C.c_uint32),
-                ("mac_split", C.c_uint32), ("part_begin", C.c_uint32), ("part_count", C.c_uint32),
+                ("mac_split", C.c_uint32), ("max_voices", C.c_uint32), ("part_begin", C.c_uint32), ("part_count", C.c_uint32),
                 ("n_tiers", C.c_uint32), ("tier_block", C.c_uint32 * CA_MAX_TIERS),
                 ("tier_parts", C.c_uint32 * CA_MAX_TIERS), ("sample_rate", C.c_float)]
 
@@ -90,6 +90,7 @@ def lib():
         L.ca_destroy.argtypes = [vp]
         L.ca_load_ir.argtypes = [vp, C.c_uint32, f32p, f32p, C.c_uint32]
         L.ca_load_ir_device.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32]
+        L.ca_load_ir_interleaved_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
         L.ca_set_params.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(Params)]
         L.ca_get_params.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(Params)]
         L.ca_set_glide.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float]
@@ -147,10 +148,10 @@ class Engine:
     """One engine = n_instances batched convolution instances (one reference `Convolution` each)."""
 
     def __init__(self, period=256, max_ir_frames=130048, n_instances=1, n_in=2, n_out=2, n_ir_slots=2, device=0,
-                 flags=0, mac_split=0, part_begin=0, part_count=0, sample_rate=48000.0, tiers=None):
+                 flags=0, mac_split=0, part_begin=0, part_count=0, sample_rate=48000.0, tiers=None, max_voices=0):
         kw = dict(period=period, max_ir_frames=max_ir_frames, n_instances=n_instances, n_in=n_in, n_out=n_out,
                   n_ir_slots=n_ir_slots, device=device, flags=flags, mac_split=mac_split, part_begin=part_begin,
-                  part_count=part_count, sample_rate=sample_rate)
+                  part_count=part_count, sample_rate=sample_rate, max_voices=max_voices)
         if tiers:
             kw.update(n_tiers=len(tiers), tier_block=[t[0] for t in tiers], tier_parts=[t[1] for t in tiers])
         self.cfg = default_config(**kw)

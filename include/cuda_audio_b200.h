@@ -71,6 +71,8 @@ typedef struct ca_config {
     uint32_t n_ir_slots;    /* size of the IR bank shared by the engine's instances */
     uint32_t flags;         /* ca_flags */
     uint32_t mac_split;     /* partition-range split of the MAC per instance; 0 = auto */
+    uint32_t max_voices;    /* IRs that may be audible at once per input during a cross-fade (1..4); 0 = 2.
+                             * 1 = an IR `select` change switches hard instead of gliding (conv.cu:15-32) */
     /* partition-range shard for IRs split across GPUs: this engine convolves
      * with partitions [part_begin, part_begin + part_count) of the uniform partitioning only;
      * part_count == 0 means "all". */
@@ -122,6 +124,8 @@ int ca_destroy(ca_engine *e);
 int ca_load_ir(ca_engine *e, uint32_t slot, const float *left, const float *right, uint32_t frames);
 /* same with device pointers (current device = engine's); synchronous */
 int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames);
+/* device pointer to (L, R) interleaved frames, the layout of WavFile::buffer (wav.h:10) */
+int ca_load_ir_interleaved_device(ca_engine *e, uint32_t slot, const float *d_lr, uint32_t frames);
 
 int ca_set_params(ca_engine *e, uint32_t instance, uint32_t input, const ca_params *p);
 int ca_get_params(ca_engine *e, uint32_t instance, uint32_t input, ca_params *p);

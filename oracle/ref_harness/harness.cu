@@ -11,6 +11,8 @@
  *
  * Exposed as a C ABI so tests/ and bench.py (--impl reference) can call it with ctypes.
  */
+#include <unistd.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
