@@ -37,6 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "cuda-audio_b200", "python"))
 
 FS, B, IR_FRAMES = 48000, 256, 192000           # configs[1]: 48 kHz, 256 frames, 4 s IR
 DEADLINE_MS = 1e3 * B / FS                       # 5.333 ms
+STEADY = 760                                     # > P = 750 periods: every FDL slot holds real data
 METRIC = "sustained RT channels @48kHz/256f, 4s IR; p99 per-period latency (us)"
 WORKLOAD = "true-stereo (4-path) 48 kHz, 256-frame period, 4 s IR (P=750), K independent instances with distinct IRs"
 
@@ -164,7 +165,10 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     # ---- device-resident throughput: `value` ----
-    for _ in range(max(args.warmup, 3)):
+    # Steady state only: the engine skips delay-line slots that are older than a voice's start, so
+    # the first P = 750 periods after start-up do LESS work than a running system.  Warm up past that.
+    warm = max(args.warmup, 3) + STEADY
+    for _ in range(warm):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
     e.sync()
     barrier()
@@ -205,7 +209,7 @@ def run_ours(args):
         e = None
         torch.cuda.empty_cache()
         e_prof = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING | ca.FLAG_PROFILE)
-        for _ in range(5):
+        for _ in range(STEADY):
             e_prof.process_device(x_dev.data_ptr(), y_dev.data_ptr())
         e_prof.sync()
         e_prof.reset_stats()
@@ -234,7 +238,7 @@ def run_ours(args):
         e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH)
         a, b = ca.PinnedArray((1, 2, B)), ca.PinnedArray((1, 2, B))
         a.array[...] = 0.05
-        for _ in range(200):
+        for _ in range(STEADY + 200):
             e1.process_raw(a.ptr, b.ptr)
         e1.reset_stats()
         for _ in range(args.latency_periods):
@@ -249,6 +253,8 @@ def run_ours(args):
         es = build_engine(ca, torch, dev, Kmax, ca.FLAG_STREAMING)
         a, b = ca.PinnedArray((Kmax, 2, B)), ca.PinnedArray((Kmax, 2, B))
         a.array[...] = pin.array[np.arange(Kmax) % K]
+        for _ in range(STEADY):       # fill every instance's delay lines before searching
+            es.process_raw(a.ptr, b.ptr)
 
         def p99_at(k, periods):
             es.set_active(k)
@@ -294,7 +300,7 @@ def run_ours(args):
         deadline_s = B / FS
         out = {
             "metric": METRIC, "value": round(world * K * deadline_s / (ms_dev * 1e-3), 1), "unit": "rt_channels",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 4),
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_dev, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_rate": FS, "period": B, "ir_frames": IR_FRAMES, "partitions": 750,
                        "instances_per_gpu": K, "sharding": "independent instances per GPU, no collective",
