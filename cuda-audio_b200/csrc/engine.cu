@@ -1,7 +1,7 @@
 // engine.cu -- host runtime + C ABI (include/cuda_audio_b200.h) of the B200 convolution engine.
 //
-// Owns the device memory (IR spectra bank, frequency-domain delay lines, predelay rings,
-// parameter blocks), the CUDA stream / graph of the per-period pipeline and the statistics.
+// Owns the device memory (IR spectra bank, frequency-domain delay lines, time rings, parameter
+// blocks), the CUDA stream / graphs of the per-period pipeline and the statistics.
 // No cuFFT, no CPU fallback: if CUDA is not usable every entry point returns CA_ERR_CUDA.
 #include "../../include/cuda_audio_b200.h"
 #include "kernels.cuh"
@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -93,19 +94,33 @@ double now_us()
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
+
+// One tier of the (non-)uniform partitioning.  Tier 0 has block S = period and runs inside every
+// period; tier j >= 1 has block S_j = m * period, covers IR frames [off, off + P*S) and runs after
+// the output of every m-th period has been produced (its result is first needed one period later
+// because off >= S).
+struct Tier {
+    uint32_t S = 0, m = 1, P = 0, off = 0, s_log = 0, bt = 0, tiles = 1, n_split = 1, Lring = 0;
+    float2 *H = nullptr, *X = nullptr, *Ypart = nullptr, *tw = nullptr;
+    size_t h_bytes = 0, x_bytes = 0;
+    MacVariant mac{};
+};
+
 }  // namespace
 
 struct ca_engine {
     ca_config cfg{};
     int device = 0;
-    uint32_t B = 0, R = 0, P = 0, Lring = 0, k_off = 0, tiles = 1, bt = 0;
-    uint32_t n_inst = 0, n_active = 0, n_in = 0, n_out = 0, n_split = 1, nv = 2, ring_len = 16384, ring_out = 0;
+    uint32_t B = 0, R = 0, k_off = 0;
+    uint32_t n_inst = 0, n_active = 0, n_in = 0, n_out = 0, nv = 2, ring_len = 16384, ring_out = 0, acc_len = 0;
+    std::vector<Tier> tiers;
     cudaStream_t stream = nullptr;
     // device memory
-    unsigned char *d_arena = nullptr;  // [H | X] contiguous (one L2 access-policy window)
-    size_t arena_bytes = 0, h_bytes = 0, x_bytes = 0;
-    float2 *d_H = nullptr, *d_X = nullptr, *d_Ypart = nullptr, *d_tw = nullptr;
-    float *d_ring = nullptr, *d_in = nullptr, *d_out = nullptr;
+    unsigned char *d_arena = nullptr;  // every tier's [H | X], contiguous (one L2 access-policy window)
+    size_t arena_bytes = 0;
+    float *d_ring = nullptr, *d_acc = nullptr, *d_in = nullptr, *d_out = nullptr;
     InParamDev *d_par = nullptr;
     ItemState *d_st = nullptr;
     Ctl *d_ctl = nullptr;
@@ -114,6 +129,7 @@ struct ca_engine {
     float *h_in = nullptr, *h_out = nullptr;
     InParamDev *h_upload[2] = {nullptr, nullptr};
     cudaEvent_t upload_done[2] = {nullptr, nullptr};
+    cudaEvent_t out_ready = nullptr;
     int upload_idx = 0;
     // parameters (host shadow)
     std::mutex par_mutex;
@@ -121,21 +137,19 @@ struct ca_engine {
     std::vector<ca_params> user;
     std::atomic<bool> par_dirty{true};
     std::vector<uint8_t> ir_loaded;
-    // kernels
     FftFns fft{};
-    MacVariant mac{};
-    // graph
-    cudaGraphExec_t gexec = nullptr;
+    // graphs: [0] = the period pipeline (tier 0), [mask] = the deferred tiers that fire together
+    std::map<uint32_t, cudaGraphExec_t> graphs;
     const float *g_in = nullptr;
     float *g_out = nullptr;
     uint32_t g_active = 0;
     // profiling
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    double prof_us[3] = {0, 0, 0};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double prof_us[4] = {0, 0, 0, 0};
     uint64_t prof_n = 0;
     // stats
     std::vector<float> wall;  // ring of host wall times (us)
-    uint64_t periods = 0, xruns = 0, launches = 0;
+    uint64_t periods = 0, xruns = 0, launches = 0, t_host = 0;
     double wall_sum = 0, wall_max = 0, deadline_us = 0;
     // pinned-pointer cache
     const void *pin_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -182,55 +196,137 @@ int flush_params(ca_engine *e)
     return CA_OK;
 }
 
-int launch_kernels(ca_engine *e, const float *d_in, float *d_out, bool profile)
+MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
 {
+    return MacArgs{t.X, t.H, t.Ypart, e->d_par, e->d_st, e->d_ctl, e->n_inst * e->n_in, e->n_in, e->nv, t.Lring, t.P, t.S,
+                   e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u};
+}
+
+// tier 0: the period pipeline.  After it the output block is complete.
+int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile)
+{
+    const Tier &t0 = e->tiers[0];
     const uint32_t n_items = e->n_active * e->n_in;
     const uint32_t n_alloc = e->n_inst * e->n_in;
-    FwdArgs fa{d_in, e->d_ring, e->d_X, e->d_par, e->d_st, e->d_ctl, e->d_tw, e->d_tw + e->B,
-               n_items, n_alloc, e->n_in, e->nv, e->Lring, e->ring_len, e->ring_out};
-    MacArgs ma{e->d_X, e->d_H, e->d_Ypart, e->d_par, e->d_st, e->d_ctl, n_alloc, e->n_in, e->nv, e->Lring, e->P, e->B, e->k_off,
-               1u, 1u, e->n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u};
-    InvArgs ia{e->d_Ypart, d_in, d_out, nullptr, e->d_par, e->d_ctl, e->d_tw, e->d_tw + e->B, e->n_split, e->n_in, e->n_out, 0u};
+    FwdArgs fa{d_in, e->d_ring, t0.X, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
+               n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out};
+    MacArgs ma = mac_args(e, t0, 1u);
+    InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
+               t0.n_split, e->n_in, e->n_out, e->acc_len};
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     e->fft.fwd<<<(n_items * e->nv + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    e->mac.fn<<<dim3(e->n_split, e->tiles, e->n_active), kMacThreads, e->mac.smem, e->stream>>>(ma);
+    t0.mac.fn<<<dim3(t0.n_split, t0.tiles, e->n_active), kMacThreads, t0.mac.smem, e->stream>>>(ma);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
     e->fft.inv<<<e->n_active * e->n_out, kInvThreads, 0, e->stream>>>(ia);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
     CA_CUDA(cudaGetLastError());
-    e->launches += 3;
     return CA_OK;
 }
 
+// deferred tiers whose block completed with this period (bit j of mask = tier j fires)
+int launch_tiers(ca_engine *e, uint32_t mask)
+{
+    const uint32_t n_alloc = e->n_inst * e->n_in;
+    for (size_t j = 1; j < e->tiers.size(); j++) {
+        if (!((mask >> j) & 1u)) continue;
+        const Tier &t = e->tiers[j];
+        const uint32_t smem = t.S * sizeof(float2);
+        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B};
+        k_tier_forward<<<e->n_active * e->n_in * e->nv, kTierThreads, smem, e->stream>>>(fa);
+        MacArgs ma = mac_args(e, t, 0u);
+        t.mac.fn<<<dim3(t.n_split, t.tiles, e->n_active), kMacThreads, t.mac.smem, e->stream>>>(ma);
+        TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len};
+        k_tier_inverse<<<e->n_active * e->n_out, kTierThreads, smem, e->stream>>>(ia);
+    }
+    CA_CUDA(cudaGetLastError());
+    return CA_OK;
+}
+
+uint32_t fire_mask(const ca_engine *e)
+{
+    uint32_t mask = 0;
+    for (size_t j = 1; j < e->tiers.size(); j++)
+        if ((e->t_host + 1) % e->tiers[j].m == 0) mask |= 1u << j;
+    return mask;
+}
+
+uint32_t popcount(uint32_t v) { uint32_t c = 0; for (; v; v &= v - 1) c++; return c; }
+
+template <class F>
+int capture_graph(ca_engine *e, cudaGraphExec_t *out, F body)
+{
+    cudaGraph_t g = nullptr;
+    CA_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    const cudaError_t erc = cudaStreamEndCapture(e->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    CA_CUDA(erc);
+    CA_CUDA(cudaGraphInstantiate(out, g, 0));
+    cudaGraphDestroy(g);
+    return CA_OK;
+}
+
+void drop_graphs(ca_engine *e)
+{
+    for (auto &kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+}
+
+// phase 1 of a period: everything the output block depends on
 int run_period(ca_engine *e, const float *d_in, float *d_out)
 {
     int rc = flush_params(e);
     if (rc) return rc;
     const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
     if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
-        if (!e->gexec || e->g_in != d_in || e->g_out != d_out || e->g_active != e->n_active) {
-            if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
-            cudaGraph_t g = nullptr;
-            CA_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-            rc = launch_kernels(e, d_in, d_out, false);
-            e->launches -= 3;
-            cudaError_t erc = cudaStreamEndCapture(e->stream, &g);
-            if (rc) return rc;
-            CA_CUDA(erc);
-            CA_CUDA(cudaGraphInstantiate(&e->gexec, g, 0));
-            cudaGraphDestroy(g);
+        if (e->g_in != d_in || e->g_out != d_out || e->g_active != e->n_active) {
+            drop_graphs(e);
             e->g_in = d_in; e->g_out = d_out; e->g_active = e->n_active;
         }
-        CA_CUDA(cudaGraphLaunch(e->gexec, e->stream));
-        e->launches += 3;
-        return CA_OK;
+        auto it = e->graphs.find(0u);
+        if (it == e->graphs.end()) {
+            cudaGraphExec_t ge = nullptr;
+            rc = capture_graph(e, &ge, [&] { return launch_period(e, d_in, d_out, false); });
+            if (rc) return rc;
+            it = e->graphs.emplace(0u, ge).first;
+        }
+        CA_CUDA(cudaGraphLaunch(it->second, e->stream));
+    } else {
+        rc = launch_period(e, d_in, d_out, profile);
+        if (rc) return rc;
     }
-    rc = launch_kernels(e, d_in, d_out, profile);
-    if (rc) return rc;
+    e->launches += 3;
+    return CA_OK;
+}
+
+// phase 2: the long tiers, off the output's critical path
+int run_deferred(ca_engine *e)
+{
+    const uint32_t mask = fire_mask(e);
+    e->t_host++;
+    const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
+    int rc = CA_OK;
+    if (mask) {
+        if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
+            auto it = e->graphs.find(mask);
+            if (it == e->graphs.end()) {
+                cudaGraphExec_t ge = nullptr;
+                rc = capture_graph(e, &ge, [&] { return launch_tiers(e, mask); });
+                if (rc) return rc;
+                it = e->graphs.emplace(mask, ge).first;
+            }
+            CA_CUDA(cudaGraphLaunch(it->second, e->stream));
+        } else {
+            rc = launch_tiers(e, mask);
+            if (rc) return rc;
+        }
+        e->launches += 3 * popcount(mask);
+    }
     if (profile) {
-        CA_CUDA(cudaEventSynchronize(e->ev[3]));
-        for (int i = 0; i < 3; i++) {
+        CA_CUDA(cudaEventRecord(e->ev[4], e->stream));
+        CA_CUDA(cudaEventSynchronize(e->ev[4]));
+        for (int i = 0; i < 4; i++) {
             float ms = 0;
             CA_CUDA(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
             e->prof_us[i] += 1e3 * ms;
@@ -248,8 +344,6 @@ void record_wall(ca_engine *e, double us)
     if (us > e->wall_max) e->wall_max = us;
     if (e->deadline_us > 0 && us > e->deadline_us) e->xruns++;
 }
-
-bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
 }  // namespace
 
@@ -285,19 +379,86 @@ void ca_config_init(ca_config *cfg)
     cfg->sample_rate = 48000.f;
 }
 
+// Non-uniform partitioning a la Gardner with one period of slack per tier: tier j+1's block is
+// `growth` times tier j's, and tier j carries just enough partitions for tier j+1 to start at an
+// offset >= its own block size.
+int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block)
+{
+    if (!cfg || !is_pow2(cfg->period) || !cfg->max_ir_frames) return CA_ERR_INVALID;
+    if (!growth) growth = 8;
+    if (!max_block) max_block = 16384;
+    if (!is_pow2(growth) || growth < 2 || !is_pow2(max_block)) return CA_ERR_INVALID;
+    uint32_t n = 0, S = cfg->period, off = 0;
+    memset(cfg->tier_block, 0, sizeof(cfg->tier_block));
+    memset(cfg->tier_parts, 0, sizeof(cfg->tier_parts));
+    while (n < CA_MAX_TIERS) {
+        uint32_t next = S * growth;
+        if (next < 256) next = 256;  // long tiers use the CTA-level FFT: block >= 256
+        if (next > max_block && S < max_block) next = max_block;
+        const bool last = (n + 1 == CA_MAX_TIERS) || next > max_block || off + next >= cfg->max_ir_frames;
+        cfg->tier_block[n] = S;
+        if (last) { cfg->tier_parts[n] = 0; n++; break; }
+        const uint32_t parts = (next - off + S - 1) / S;  // reach offset >= next
+        cfg->tier_parts[n] = parts;
+        off += parts * S;
+        S = next;
+        n++;
+    }
+    cfg->n_tiers = n;
+    return CA_OK;
+}
+
 int ca_destroy(ca_engine *e)
 {
     if (!e) return CA_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->gexec) cudaGraphExecDestroy(e->gexec);
+    drop_graphs(e);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->upload_done) if (ev) cudaEventDestroy(ev);
-    cudaFree(e->d_arena); cudaFree(e->d_Ypart); cudaFree(e->d_tw); cudaFree(e->d_ring);
+    if (e->out_ready) cudaEventDestroy(e->out_ready);
+    for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.tw); }
+    cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
+    return CA_OK;
+}
+
+static int plan_tiers(const ca_config *cfg, ca_engine *e)
+{
+    const uint32_t B = cfg->period;
+    const uint32_t nt = cfg->n_tiers > 1 ? cfg->n_tiers : 1;
+    if (nt > CA_MAX_TIERS) { g_last_error = "too many tiers"; return CA_ERR_INVALID; }
+    e->tiers.assign(nt, Tier{});
+    if (nt == 1) {
+        Tier &t = e->tiers[0];
+        const uint32_t P_total = (cfg->max_ir_frames + B - 1) / B;
+        t.S = B; t.m = 1; t.off = 0;
+        if (cfg->part_count) {
+            if (cfg->part_begin + cfg->part_count > P_total) { g_last_error = "partition shard exceeds the IR"; return CA_ERR_INVALID; }
+            t.P = cfg->part_count; e->k_off = cfg->part_begin;
+        } else { t.P = P_total; e->k_off = 0; }
+        t.Lring = e->k_off + t.P;
+        return CA_OK;
+    }
+    if (cfg->part_count) { g_last_error = "partition-range shards and tiers cannot be combined"; return CA_ERR_UNSUPPORTED; }
+    uint32_t off = 0;
+    for (uint32_t j = 0; j < nt; j++) {
+        Tier &t = e->tiers[j];
+        t.S = cfg->tier_block[j];
+        if (j == 0 && t.S != B) { g_last_error = "tier 0 block must equal the period"; return CA_ERR_INVALID; }
+        if (!is_pow2(t.S) || (j > 0 && (t.S <= e->tiers[j - 1].S || t.S < 256 || t.S > 16384))) { g_last_error = "tier blocks must be increasing powers of two, 256..16384 above tier 0"; return CA_ERR_INVALID; }
+        if (j > 0 && off < t.S) { g_last_error = "tier offset must be >= its block size (previous tiers too short)"; return CA_ERR_INVALID; }
+        if (off >= cfg->max_ir_frames) { e->tiers.resize(j); break; }
+        t.m = t.S / B; t.off = off;
+        const uint32_t rest = (cfg->max_ir_frames - off + t.S - 1) / t.S;
+        t.P = (j + 1 == nt || !cfg->tier_parts[j]) ? rest : std::min(cfg->tier_parts[j], rest);
+        t.Lring = t.P;
+        off += t.P * t.S;
+    }
+    if (off < cfg->max_ir_frames) { g_last_error = "tiers do not cover max_ir_frames"; return CA_ERR_INVALID; }
     return CA_OK;
 }
 
@@ -308,55 +469,91 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaSetDevice(cfg->device));
     e->B = cfg->period; e->R = cfg->period / 32;
     e->n_inst = e->n_active = cfg->n_instances; e->n_in = cfg->n_in; e->n_out = cfg->n_out;
-    const uint32_t P_total = (cfg->max_ir_frames + e->B - 1) / e->B;
-    if (cfg->part_count) {
-        if (cfg->part_begin + cfg->part_count > P_total) { g_last_error = "partition shard exceeds the IR"; return CA_ERR_INVALID; }
-        e->P = cfg->part_count; e->k_off = cfg->part_begin;
-    } else { e->P = P_total; e->k_off = 0; }
-    e->Lring = e->k_off + e->P;
-    e->bt = std::min<uint32_t>(e->B, 256);
-    e->tiles = e->B / e->bt;
+    e->nv = cfg->max_voices ? cfg->max_voices : 2u;
+    int rc = plan_tiers(cfg, e);
+    if (rc) return rc;
     e->fft = fft_pick((int)e->R);
     int variant = 1;
     if (const char *v = getenv("CA_MAC_VARIANT")) variant = atoi(v);
-    e->mac = mac_pick((int)e->bt, (int)e->n_out, variant);
-    e->nv = cfg->max_voices ? cfg->max_voices : 2u;
-    CA_CUDA(cudaFuncSetAttribute((const void *)e->mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mac.smem));
-
-    // split of the row list per instance: enough CTAs to cover the SMs when few instances run
-    // (latency schedule), 1 when the batch alone fills the machine.
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-    uint32_t split = cfg->mac_split;
-    if (!split) {
-        const uint64_t ctas = (uint64_t)e->n_inst * e->tiles;
-        split = ctas >= (uint64_t)2 * sms ? 1u : (uint32_t)std::min<uint64_t>(32, (2 * (uint64_t)sms + ctas - 1) / ctas);
-    }
-    const uint32_t rows = e->P * e->n_in;  // steady state: one voice per input
-    e->n_split = std::max<uint32_t>(1, std::min(split, std::max<uint32_t>(1, rows / (uint32_t)e->mac.kc)));
-    // time-domain ring per voice: predelay reach + the two blocks of the overlap-save window
-    e->ring_len = 1;
-    while (e->ring_len < kMaxPredelay + 2 * e->B) e->ring_len <<= 1;
-    e->ring_out = std::max(e->Lring, e->ring_len / e->B) + 2;
 
     CA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CA_CUDA(cudaEventCreate(&ev));
     for (auto &ev : e->upload_done) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
-    e->h_bytes = (size_t)cfg->n_ir_slots * e->n_out * e->P * e->B * sizeof(float2);
-    e->x_bytes = n_items * e->nv * e->Lring * e->B * sizeof(float2);
-    e->arena_bytes = e->h_bytes + e->x_bytes;
+    uint32_t s_max = e->B, reach = e->B;
+    e->arena_bytes = 0;
+    for (size_t j = 0; j < e->tiers.size(); j++) {
+        Tier &t = e->tiers[j];
+        t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
+        t.bt = std::min<uint32_t>(t.S, 256);
+        t.tiles = t.S / t.bt;
+        t.mac = mac_pick((int)t.bt, (int)e->n_out, variant);
+        CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
+        // split of the row list per instance: enough CTAs to cover the SMs when few instances run
+        // (latency schedule), 1 when the batch alone fills the machine.
+        uint32_t split = j == 0 ? cfg->mac_split : 0;
+        if (!split) {
+            const uint64_t ctas = (uint64_t)e->n_inst * t.tiles;
+            split = ctas >= (uint64_t)2 * sms ? 1u : (uint32_t)std::min<uint64_t>(32, (2 * (uint64_t)sms + ctas - 1) / ctas);
+        }
+        const uint32_t rows = t.P * e->n_in;  // steady state: one voice per input
+        t.n_split = std::max<uint32_t>(1, std::min(split, std::max<uint32_t>(1, rows / (uint32_t)t.mac.kc)));
+        t.h_bytes = (size_t)cfg->n_ir_slots * e->n_out * t.P * t.S * sizeof(float2);
+        t.x_bytes = n_items * e->nv * t.Lring * t.S * sizeof(float2);
+        e->arena_bytes += t.h_bytes + t.x_bytes;
+        s_max = std::max(s_max, t.S);
+        reach = std::max(reach, t.off + t.S);
+    }
+    if (e->tiers.size() > 1) {
+        CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
+        CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
+        CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_ir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
+    }
+    // time-domain ring per voice: predelay reach + the longest overlap-save window
+    e->ring_len = 1;
+    while (e->ring_len < kMaxPredelay + 2 * s_max) e->ring_len <<= 1;
+    uint32_t total_periods = 0;
+    for (auto &t : e->tiers) total_periods = std::max(total_periods, (t.off + t.P * t.S) / e->B + 2 * t.m);
+    e->ring_out = std::max(total_periods + e->k_off, e->ring_len / e->B) + 2;
+    e->acc_len = 1;
+    while (e->acc_len < reach + e->B) e->acc_len <<= 1;
+
     CA_CUDA(cudaMalloc(&e->d_arena, e->arena_bytes));
-    e->d_H = reinterpret_cast<float2 *>(e->d_arena);
-    e->d_X = reinterpret_cast<float2 *>(e->d_arena + e->h_bytes);
     CA_CUDA(cudaMemsetAsync(e->d_arena, 0, e->arena_bytes, e->stream));
-    const size_t yp_bytes = (size_t)e->n_inst * e->n_split * e->n_out * e->B * sizeof(float2);
-    CA_CUDA(cudaMalloc(&e->d_Ypart, yp_bytes));
-    CA_CUDA(cudaMemsetAsync(e->d_Ypart, 0, yp_bytes, e->stream));
+    e->device_bytes = e->arena_bytes;
+    {
+        unsigned char *p = e->d_arena;
+        for (auto &t : e->tiers) { t.H = reinterpret_cast<float2 *>(p); p += t.h_bytes; }
+        for (auto &t : e->tiers) { t.X = reinterpret_cast<float2 *>(p); p += t.x_bytes; }
+    }
+    for (auto &t : e->tiers) {
+        const size_t yp_bytes = (size_t)e->n_inst * t.n_split * e->n_out * t.S * sizeof(float2);
+        CA_CUDA(cudaMalloc(&t.Ypart, yp_bytes));
+        CA_CUDA(cudaMemsetAsync(t.Ypart, 0, yp_bytes, e->stream));
+        e->device_bytes += yp_bytes;
+        // twiddles, fp64 -> fp32: [W_S^n, n < S | W_2S^k, k < S]
+        std::vector<float2> tw(2 * (size_t)t.S);
+        for (uint32_t n = 0; n < t.S; n++) {
+            const double a = -2.0 * M_PI * (double)n / (double)t.S, b = -M_PI * (double)n / (double)t.S;
+            tw[n] = make_float2((float)cos(a), (float)sin(a));
+            tw[t.S + n] = make_float2((float)cos(b), (float)sin(b));
+        }
+        CA_CUDA(cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
+        CA_CUDA(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     const size_t ring_bytes = n_items * e->nv * e->ring_len * sizeof(float);
     CA_CUDA(cudaMalloc(&e->d_ring, ring_bytes));
     CA_CUDA(cudaMemsetAsync(e->d_ring, 0, ring_bytes, e->stream));
+    size_t acc_bytes = 0;
+    if (e->tiers.size() > 1) {
+        acc_bytes = (size_t)e->n_inst * e->n_out * e->acc_len * sizeof(float);
+        CA_CUDA(cudaMalloc(&e->d_acc, acc_bytes));
+        CA_CUDA(cudaMemsetAsync(e->d_acc, 0, acc_bytes, e->stream));
+    }
     const size_t in_bytes = n_items * e->B * sizeof(float), out_bytes = (size_t)e->n_inst * e->n_out * e->B * sizeof(float);
     CA_CUDA(cudaMalloc(&e->d_in, in_bytes));
     CA_CUDA(cudaMalloc(&e->d_out, out_bytes));
@@ -368,20 +565,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaMallocHost(&e->h_in, in_bytes));
     CA_CUDA(cudaMallocHost(&e->h_out, out_bytes));
     for (auto &u : e->h_upload) CA_CUDA(cudaMallocHost(&u, n_items * sizeof(InParamDev)));
-    e->device_bytes = e->arena_bytes + yp_bytes + ring_bytes + in_bytes + out_bytes + n_items * (sizeof(InParamDev) + 2 * sizeof(ItemState));
-
-    // twiddles, fp64 -> fp32: [W_M^n, n < M | W_2M^k, k < M]
-    {
-        const uint32_t M = e->B;
-        std::vector<float2> tw(2 * M);
-        for (uint32_t n = 0; n < M; n++) {
-            const double a = -2.0 * M_PI * (double)n / (double)M, b = -M_PI * (double)n / (double)M;
-            tw[n] = make_float2((float)cos(a), (float)sin(a));
-            tw[M + n] = make_float2((float)cos(b), (float)sin(b));
-        }
-        CA_CUDA(cudaMalloc(&e->d_tw, tw.size() * sizeof(float2)));
-        CA_CUDA(cudaMemcpy(e->d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-    }
+    e->device_bytes += ring_bytes + acc_bytes + in_bytes + out_bytes + n_items * (sizeof(InParamDev) + 2 * sizeof(ItemState));
 
     // parameter defaults == Convolution::CC::value defaults (conv.h:42-50)
     e->par.assign(n_items, InParamDev{});
@@ -425,7 +609,6 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     if (cfg->n_in < 1 || cfg->n_in > 2 || cfg->n_out < 1 || cfg->n_out > 2) { g_last_error = "n_in / n_out must be 1 or 2"; return CA_ERR_INVALID; }
     if (cfg->max_voices > (uint32_t)kMaxVoices) { g_last_error = "max_voices must be <= 4"; return CA_ERR_INVALID; }
     if (!cfg->n_instances || !cfg->max_ir_frames || !cfg->n_ir_slots) { g_last_error = "n_instances, max_ir_frames, n_ir_slots must be > 0"; return CA_ERR_INVALID; }
-    if (cfg->n_tiers > 1) { g_last_error = "non-uniform tiers are not available in this build"; return CA_ERR_UNSUPPORTED; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
         (void)cudaGetLastError();
@@ -445,19 +628,31 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
     if (!e || !d_left || slot >= e->cfg.n_ir_slots) return CA_ERR_INVALID;
     if (e->n_out == 2 && !d_right) return CA_ERR_INVALID;
     CA_CUDA(cudaSetDevice(e->device));
-    IrArgs a{};
-    a.stride = stride;
-    a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
-    a.H = e->d_H + (size_t)slot * e->n_out * e->P * e->B;
-    a.twM = e->d_tw; a.tw2M = e->d_tw + e->B;
-    a.frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
-    a.P = e->P; a.n_out = e->n_out; a.k_begin = e->k_off;
-    a.scale = 1.0f / (2.0f * (float)e->B);
-    const uint32_t items = e->n_out * e->P;
-    e->fft.ir<<<(items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(a);
+    frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
+    for (size_t j = 0; j < e->tiers.size(); j++) {
+        const Tier &t = e->tiers[j];
+        float2 *H = t.H + (size_t)slot * e->n_out * t.P * t.S;
+        const float scale = 1.0f / (2.0f * (float)t.S);  // both FFT normalisations live in H
+        if (j == 0) {
+            IrArgs a{};
+            a.stride = stride;
+            a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
+            a.H = H; a.twM = t.tw; a.tw2M = t.tw + t.S;
+            a.frames = frames; a.P = t.P; a.n_out = e->n_out; a.frame_off = e->k_off * e->B; a.scale = scale;
+            const uint32_t items = e->n_out * t.P;
+            e->fft.ir<<<(items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(a);
+        } else {
+            TierIrArgs a{};
+            a.stride = stride;
+            a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
+            a.H = H; a.twM = t.tw; a.tw2M = t.tw + t.S;
+            a.frames = frames; a.P = t.P; a.n_out = e->n_out; a.frame_off = t.off; a.S = t.S; a.s_log = t.s_log; a.scale = scale;
+            k_tier_ir<<<e->n_out * t.P, kTierThreads, t.S * sizeof(float2), e->stream>>>(a);
+        }
+        e->launches += 1;
+    }
     CA_CUDA(cudaGetLastError());
     CA_CUDA(cudaStreamSynchronize(e->stream));
-    e->launches += 1;
     e->ir_loaded[slot] = 1;
     return CA_OK;
 }
@@ -539,6 +734,8 @@ int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nf
     const double t0 = now_us();
     int rc = run_period(e, d_in, d_out);
     if (rc) return rc;
+    rc = run_deferred(e);
+    if (rc) return rc;
     record_wall(e, now_us() - t0);
     return CA_OK;
 }
@@ -557,7 +754,10 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     int rc = run_period(e, e->d_in, e->d_out);
     if (rc) return rc;
     CA_CUDA(cudaMemcpyAsync(dst, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
-    CA_CUDA(cudaStreamSynchronize(e->stream));
+    CA_CUDA(cudaEventRecord(e->out_ready, e->stream));
+    rc = run_deferred(e);  // long tiers keep the GPU busy while the host already has its output
+    if (rc) return rc;
+    CA_CUDA(cudaEventSynchronize(e->out_ready));
     if (dst != out) memcpy(out, e->h_out, out_bytes);
     record_wall(e, now_us() - t0);
     return CA_OK;
@@ -590,12 +790,19 @@ int ca_get_stats(ca_engine *e, ca_stats *s)
         s->fwd_us = e->prof_us[0] / (double)e->prof_n;
         s->mac_us = e->prof_us[1] / (double)e->prof_n;
         s->inv_us = e->prof_us[2] / (double)e->prof_n;
-        s->total_us = s->fwd_us + s->mac_us + s->inv_us;
+        s->tiers_us = e->prof_us[3] / (double)e->prof_n;
+        s->total_us = s->fwd_us + s->mac_us + s->inv_us + s->tiers_us;
     }
     s->gpu_launches = e->launches;
-    // the MAC streams every IR partition spectrum and every FDL slot once
-    s->mac_bytes = (uint64_t)8 * e->B * e->P * (uint64_t)(e->n_in * e->n_out + e->n_in) * e->n_active;
-    s->partitions = e->P; s->mac_split = e->n_split; s->device_bytes = e->device_bytes;
+    // the MAC streams every IR partition spectrum and every FDL slot once per firing
+    const Tier &t0 = e->tiers[0];
+    s->mac_bytes = (uint64_t)8 * t0.S * t0.P * (uint64_t)(e->n_in * e->n_out + e->n_in) * e->n_active;
+    double amort = 0;
+    for (auto &t : e->tiers) amort += 8.0 * t.S * t.P * (double)(e->n_in * e->n_out + e->n_in) / (double)t.m;
+    s->mac_bytes_amortized = (uint64_t)(amort * e->n_active);
+    s->partitions = t0.P; s->mac_split = t0.n_split; s->device_bytes = e->device_bytes;
+    s->n_tiers = (uint32_t)e->tiers.size();
+    for (size_t j = 0; j < e->tiers.size() && j < CA_MAX_TIERS; j++) { s->tier_block[j] = e->tiers[j].S; s->tier_parts[j] = e->tiers[j].P; s->tier_offset[j] = e->tiers[j].off; }
     return CA_OK;
 }
 
@@ -603,7 +810,8 @@ int ca_reset_stats(ca_engine *e)
 {
     if (!e) return CA_ERR_INVALID;
     e->periods = e->xruns = 0; e->wall_sum = e->wall_max = 0;
-    e->prof_us[0] = e->prof_us[1] = e->prof_us[2] = 0; e->prof_n = 0;
+    for (auto &p : e->prof_us) p = 0;
+    e->prof_n = 0;
     return CA_OK;
 }
 

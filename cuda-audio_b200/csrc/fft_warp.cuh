@@ -115,8 +115,9 @@ struct WarpFft {
     float2 lw[5];   // W_{2*half}^{lane & (half-1)} for half = 16 >> s
     float2 twb[R];  // W_M^(b*c)
 
-    // twM: exp(-2 pi i n / M), n < M  (global memory, fp64-accurate values rounded to fp32)
-    __device__ __forceinline__ void init(const float2 *__restrict__ twM)
+    // twM: exp(-2 pi i n / (M * stride)), n < M * stride (global memory, fp64-accurate values rounded
+    // to fp32); stride > 1 lets a larger transform's table serve its 32R-point sub-transforms.
+    __device__ __forceinline__ void init(const float2 *__restrict__ twM, int stride = 1)
     {
         lane = threadIdx.x & 31;
         c = brev5(lane);
@@ -125,10 +126,10 @@ struct WarpFft {
         for (int s = 0; s < 5; s++) {
             const int half = 16 >> s;
             const int j = lane & (half - 1);
-            lw[s] = __ldg(&twM[(j << s) * R]);  // W_32^(j * 16/half) = W_M^(j * (1<<s) * R)
+            lw[s] = __ldg(&twM[(j << s) * R * stride]);  // W_32^(j * 16/half) = W_M^(j * (1<<s) * R)
         }
 #pragma unroll
-        for (int b = 0; b < R; b++) twb[b] = __ldg(&twM[b * c]);
+        for (int b = 0; b < R; b++) twb[b] = __ldg(&twM[b * c * stride]);
     }
 
     // time layout -> spectral layout, unnormalised forward DFT

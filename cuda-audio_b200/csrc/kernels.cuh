@@ -14,7 +14,7 @@
 //
 // Spectra are stored in packed real-FFT format: B complex per partition, bin 0 = (DC, Nyquist).
 #pragma once
-#include "fft_warp.cuh"
+#include "fft_cta.cuh"
 
 namespace ca {
 
@@ -199,7 +199,7 @@ struct IrArgs {
     const float *h[2];  // time-domain IR per output channel (device)
     float2 *H;          // this slot's spectra [n_out][P][B]
     const float2 *twM, *tw2M;
-    uint32_t frames, P, n_out, k_begin;
+    uint32_t frames, P, n_out, frame_off;
     uint32_t stride;    // 1 = planar, 2 = (L, R) interleaved like WavFile::buffer (wav.h:10)
     float scale;        // 1/(2B): both FFT normalisations live in H
 };
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_ir_fft(const IrArgs a)
     for (int b = 0; b < R; b++) {
         float re = 0.f, im = 0.f;
         if (lane < 16) {  // [h_k | 0]: the IR block sits in the first half of the 2B window
-            const size_t n0 = (size_t)(a.k_begin + k) * B + 2 * (R * lane + b);
+            const size_t n0 = (size_t)a.frame_off + (size_t)k * B + 2 * (R * lane + b);
             if (n0 < a.frames) re = __ldg(&h[n0 * a.stride]) * a.scale;
             if (n0 + 1 < a.frames) im = __ldg(&h[(n0 + 1) * a.stride]) * a.scale;
         }
@@ -600,6 +600,110 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
         }
     }
     if (item == 0 && tid == 0) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
+}
+
+// ------------------------------------------------------------------------------------------
+// long tiers of the non-uniform partitioning (block S = 256 * 2^s_log, fired every m periods,
+// AFTER the period's output has been produced: k_inverse has already advanced ctl->t)
+// ------------------------------------------------------------------------------------------
+constexpr int kTierThreads = 256;
+
+struct TierFwdArgs {
+    const float *ring;    // [(item*nv + v)][ring_len]
+    float2 *X;            // FDL of this tier [(item*nv + v)][Lring][S]
+    const ItemState *st;  // [2][n_items_alloc]
+    const Ctl *ctl;
+    const float2 *twM, *tw2M;
+    uint32_t n_items_alloc, nv, Lring, ring_len, S, s_log, m, B;
+};
+
+// one CTA per (instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
+__global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const uint32_t w = blockIdx.x, item = w / a.nv, v = w % a.nv;
+    const unsigned long long tend = a.ctl->t;
+    const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
+    if (!((st.active >> v) & 1u)) return;
+    const uint32_t mask = a.ring_len - 1;
+    const float *ring = a.ring + (size_t)w * a.ring_len;
+    const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
+    for (uint32_t n = threadIdx.x; n < a.S; n += kTierThreads) sm[n] = *reinterpret_cast<const float2 *>(ring + ((start + 2 * n) & mask));
+    __syncthreads();
+    cta_fft_forward(sm, (int)a.S, (int)a.s_log, a.twM);
+    cta_split_r2c(sm, (int)a.S, (int)a.s_log, a.tw2M);
+    const unsigned long long n_fire = tend / a.m;
+    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
+    float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
+    for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) dst[k] = sm[zpos((int)k, (int)a.s_log)];
+}
+
+struct TierInvArgs {
+    const float2 *Ypart;  // [inst][n_split][n_out][S]
+    float *accring;       // [inst*n_out + o][acc_len]
+    const Ctl *ctl;
+    const float2 *twM, *tw2M;
+    uint32_t n_split, n_out, S, s_log, B, off, acc_len;
+};
+
+// one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
+__global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const uint32_t item = blockIdx.x, inst = item / a.n_out, o = item % a.n_out;
+    const unsigned long long tend = a.ctl->t;
+    for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) {
+        float2 y = make_float2(0.f, 0.f);
+        const float2 *src = a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * a.S + k;
+        const size_t stride = (size_t)a.n_out * a.S;
+        for (uint32_t sp = 0; sp < a.n_split; sp++) { const float2 q = src[sp * stride]; y.x += q.x; y.y += q.y; }
+        sm[zpos((int)k, (int)a.s_log)] = y;
+    }
+    __syncthreads();
+    cta_split_c2r(sm, (int)a.S, (int)a.s_log, a.tw2M);
+    cta_fft_inverse(sm, (int)a.S, (int)a.s_log, a.twM);
+    // z[n] = y[2n] + j y[2n+1]; keep y[S, 2S) = z[S/2, S): they belong to output times
+    // [t_end*B - S + off, t_end*B + off)
+    const uint32_t amask = a.acc_len - 1;
+    const uint32_t pos0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask);
+    float *acc = a.accring + (size_t)item * a.acc_len;
+    for (uint32_t n = threadIdx.x; n < a.S / 2; n += kTierThreads) {
+        const float2 z = sm[a.S / 2 + n];
+        float2 *p = reinterpret_cast<float2 *>(acc + ((pos0 + 2 * n) & amask));
+        float2 q = *p;
+        q.x += z.x; q.y += z.y;
+        *p = q;
+    }
+}
+
+struct TierIrArgs {
+    const float *h[2];
+    float2 *H;  // this slot's spectra of this tier [n_out][P][S]
+    const float2 *twM, *tw2M;
+    uint32_t frames, P, n_out, frame_off, stride, S, s_log;
+    float scale;
+};
+
+// one CTA per (output channel, partition): [h_k | 0] -> spectrum
+__global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
+{
+    extern __shared__ __align__(16) float2 sm[];
+    const uint32_t o = blockIdx.x / a.P, k = blockIdx.x % a.P;
+    const float *h = o == 0 ? a.h[0] : a.h[1];
+    for (uint32_t n = threadIdx.x; n < a.S; n += kTierThreads) {
+        float re = 0.f, im = 0.f;
+        if (n < a.S / 2) {
+            const size_t n0 = (size_t)a.frame_off + (size_t)k * a.S + 2 * n;
+            if (n0 < a.frames) re = __ldg(&h[n0 * a.stride]) * a.scale;
+            if (n0 + 1 < a.frames) im = __ldg(&h[(n0 + 1) * a.stride]) * a.scale;
+        }
+        sm[n] = make_float2(re, im);
+    }
+    __syncthreads();
+    cta_fft_forward(sm, (int)a.S, (int)a.s_log, a.twM);
+    cta_split_r2c(sm, (int)a.S, (int)a.s_log, a.tw2M);
+    float2 *dst = a.H + ((size_t)o * a.P + k) * a.S;
+    for (uint32_t kk = threadIdx.x; kk < a.S; kk += kTierThreads) dst[kk] = sm[zpos((int)kk, (int)a.s_log)];
 }
 
 }  // namespace ca

@@ -20,7 +20,7 @@ CA_MAX_TIERS = 4
 FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE = 1, 2, 4, 8
 
 EXPORTS = [
-    "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_create", "ca_destroy",
+    "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",
     "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
     "ca_host_alloc", "ca_host_free",
@@ -52,9 +52,11 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("periods", C.c_uint64), ("xruns", C.c_uint64), ("mean_us", C.c_double), ("p50_us", C.c_double),
                 ("p99_us", C.c_double), ("max_us", C.c_double), ("fwd_us", C.c_double), ("mac_us", C.c_double),
-                ("inv_us", C.c_double), ("total_us", C.c_double), ("gpu_launches", C.c_uint64),
-                ("mac_bytes", C.c_uint64), ("partitions", C.c_uint32), ("mac_split", C.c_uint32),
-                ("device_bytes", C.c_uint64)]
+                ("inv_us", C.c_double), ("tiers_us", C.c_double), ("total_us", C.c_double), ("gpu_launches", C.c_uint64),
+                ("mac_bytes", C.c_uint64), ("mac_bytes_amortized", C.c_uint64), ("partitions", C.c_uint32),
+                ("mac_split", C.c_uint32), ("device_bytes", C.c_uint64), ("n_tiers", C.c_uint32),
+                ("tier_block", C.c_uint32 * CA_MAX_TIERS), ("tier_parts", C.c_uint32 * CA_MAX_TIERS),
+                ("tier_offset", C.c_uint32 * CA_MAX_TIERS), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -86,6 +88,7 @@ def lib():
         L.ca_strerror.argtypes = [C.c_int]
         L.ca_last_error_string.restype = C.c_char_p
         L.ca_config_init.argtypes = [C.POINTER(Config)]
+        L.ca_config_auto_tiers.argtypes = [C.POINTER(Config), C.c_uint32, C.c_uint32]
         L.ca_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
         L.ca_destroy.argtypes = [vp]
         L.ca_load_ir.argtypes = [vp, C.c_uint32, f32p, f32p, C.c_uint32]
@@ -148,13 +151,16 @@ class Engine:
     """One engine = n_instances batched convolution instances (one reference `Convolution` each)."""
 
     def __init__(self, period=256, max_ir_frames=130048, n_instances=1, n_in=2, n_out=2, n_ir_slots=2, device=0,
-                 flags=0, mac_split=0, part_begin=0, part_count=0, sample_rate=48000.0, tiers=None, max_voices=0):
+                 flags=0, mac_split=0, part_begin=0, part_count=0, sample_rate=48000.0, tiers=None, max_voices=0, tier_growth=0,
+                 tier_max_block=0):
         kw = dict(period=period, max_ir_frames=max_ir_frames, n_instances=n_instances, n_in=n_in, n_out=n_out,
                   n_ir_slots=n_ir_slots, device=device, flags=flags, mac_split=mac_split, part_begin=part_begin,
                   part_count=part_count, sample_rate=sample_rate, max_voices=max_voices)
-        if tiers:
+        if tiers and tiers != "auto":
             kw.update(n_tiers=len(tiers), tier_block=[t[0] for t in tiers], tier_parts=[t[1] for t in tiers])
         self.cfg = default_config(**kw)
+        if tiers == "auto":
+            _check(lib().ca_config_auto_tiers(C.byref(self.cfg), tier_growth, tier_max_block), "ca_config_auto_tiers")
         h = C.c_void_p()
         _check(lib().ca_create(C.byref(self.cfg), C.byref(h)), "ca_create")
         self._h = h

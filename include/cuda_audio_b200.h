@@ -77,9 +77,11 @@ typedef struct ca_config {
      * with partitions [part_begin, part_begin + part_count) of the uniform partitioning only;
      * part_count == 0 means "all". */
     uint32_t part_begin, part_count;
-    /* non-uniform partitioning: tier j uses block size tier_block[j] (multiple of period,
-     * power of two) for tier_parts[j] partitions; tier 0 must equal period; n_tiers <= 1
-     * means uniform.  The last tier's tier_parts may be 0 (= cover the rest). */
+    /* non-uniform partitioning: tier j uses block size tier_block[j] (power of two; tier 0 must
+     * equal period, higher tiers 256..16384 and increasing) for tier_parts[j] partitions
+     * (0 = cover the rest); n_tiers <= 1 means uniform.  Tier j >= 1 must start at an IR offset
+     * >= its block size (sum of the previous tiers' parts*block): its result is then first
+     * needed one period after its block completes, so it runs off the output's critical path. */
     uint32_t n_tiers;
     uint32_t tier_block[CA_MAX_TIERS];
     uint32_t tier_parts[CA_MAX_TIERS];
@@ -101,13 +103,18 @@ typedef struct ca_stats {
     uint64_t periods;       /* ca_process* calls so far                                 */
     uint64_t xruns;         /* calls whose host wall time exceeded period / sample_rate */
     double mean_us, p50_us, p99_us, max_us; /* host wall time per ca_process* call      */
-    /* CA_FLAG_PROFILE: mean device time per period, CUDA events on the engine's stream */
-    double fwd_us, mac_us, inv_us, total_us;
+    /* CA_FLAG_PROFILE: mean device time per period, CUDA events on the engine's stream:
+     * forward R2C, FDL MAC, inverse C2R+mix of tier 0, and the deferred long tiers */
+    double fwd_us, mac_us, inv_us, tiers_us, total_us;
     uint64_t gpu_launches;  /* kernels launched by the engine so far                    */
-    uint64_t mac_bytes;     /* algorithmic bytes the FDL MAC streams per period         */
-    uint32_t partitions;    /* P                                                       */
-    uint32_t mac_split;     /* effective split                                          */
+    uint64_t mac_bytes;     /* algorithmic bytes tier 0's FDL MAC streams per period    */
+    uint64_t mac_bytes_amortized; /* all tiers, per period (tier j fires every block_j/period) */
+    uint32_t partitions;    /* P of tier 0                                             */
+    uint32_t mac_split;     /* effective split of tier 0                                */
     uint64_t device_bytes;  /* device memory held by the engine                         */
+    uint32_t n_tiers;
+    uint32_t tier_block[CA_MAX_TIERS], tier_parts[CA_MAX_TIERS], tier_offset[CA_MAX_TIERS];
+    uint32_t reserved;
 } ca_stats;
 
 int ca_api_version(void);
@@ -115,6 +122,9 @@ const char *ca_strerror(int code);
 const char *ca_last_error_string(void); /* thread-local detail of the last CUDA failure */
 
 void ca_config_init(ca_config *cfg); /* zero + struct_size + reference defaults (2x2, period 256) */
+/* Fill n_tiers / tier_block / tier_parts for cfg->period and cfg->max_ir_frames: every tier's block
+ * is `growth` (power of two, 0 = 8) times the previous one, up to max_block (0 = 16384). */
+int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block);
 
 int ca_create(const ca_config *cfg, ca_engine **out);
 int ca_destroy(ca_engine *e);

@@ -52,3 +52,50 @@ def partner(Zs,R):
             if c==0: Zp[l,d]=Zs[l,(R-d)%R]
             else: Zp[l,d]=Zs[lp,R-1-d]
     return Zp
+
+
+# ---- CTA-level FFT (fft_cta.cuh): s radix-2 DIF stages in "shared memory" + 256-point blocks ----
+def brev(x, bits):
+    return int('{:0{w}b}'.format(x, w=bits)[::-1], 2) if bits else 0
+
+
+def zpos(k, s):
+    return (brev(k & ((1 << s) - 1), s) << 8) | (k >> s)
+
+
+def cta_fwd(z, s):
+    M = 256 << s
+    sm = np.array(z, complex)
+    for st in range(s):
+        half = M >> (st + 1)
+        new = sm.copy()
+        for j in range(M // 2):
+            pos = j & (half - 1)
+            i0 = ((j // half) * 2 * half) | pos
+            i1 = i0 + half
+            a, b = sm[i0], sm[i1]
+            new[i0] = a + b
+            new[i1] = (a - b) * W(M, pos << st)
+        sm = new
+    for blk in range(1 << s):
+        sm[blk * 256:(blk + 1) * 256] = np.fft.fft(sm[blk * 256:(blk + 1) * 256])  # the warp FFT, natural order
+    return sm
+
+
+def cta_inv(sm, s):
+    M = 256 << s
+    sm = np.array(sm, complex)
+    for blk in range(1 << s):
+        sm[blk * 256:(blk + 1) * 256] = np.fft.ifft(sm[blk * 256:(blk + 1) * 256]) * 256
+    for st in range(s - 1, -1, -1):
+        half = M >> (st + 1)
+        new = sm.copy()
+        for j in range(M // 2):
+            pos = j & (half - 1)
+            i0 = ((j // half) * 2 * half) | pos
+            i1 = i0 + half
+            a, b = sm[i0], sm[i1] * np.conj(W(M, pos << st))
+            new[i0] = a + b
+            new[i1] = a - b
+        sm = new
+    return sm

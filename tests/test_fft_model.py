@@ -67,3 +67,18 @@ def test_overlap_save_partitioned_model():
         y.append(np.fft.irfft(full, 2 * B)[B:] * 2 * B)
     y = np.concatenate(y)
     assert np.allclose(y, np.convolve(x, h)[:len(x)])
+
+
+@pytest.mark.parametrize("s", [0, 1, 3, 5])
+def test_cta_fft_layout(s):
+    """fft_cta.cuh: DIF stages + 256-point blocks leave bin k at zpos(k); the inverse undoes it."""
+    M = 256 << s
+    rng = np.random.default_rng(s)
+    z = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    sm = wm.cta_fwd(z, s)
+    ref = np.fft.fft(z)
+    pos = np.array([wm.zpos(k, s) for k in range(M)])
+    assert sorted(pos) == list(range(M))
+    assert np.allclose(sm[pos], ref)
+    back = wm.cta_inv(sm, s)
+    assert np.allclose(back / M, z)

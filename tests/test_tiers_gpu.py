@@ -1,0 +1,129 @@
+"""Non-uniform partitioning (BASELINE configs[2]: low-latency 64-frame period, 10 s IR, small head
+partitions + large tail partitions) against the FP64 oracle and against the uniform engine."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+FS = 48000
+
+
+def ca():
+    import cuda_audio_b200 as m
+    return m
+
+
+def irs2x2(L, seed0=1000):
+    return [[O.synth_ir(L, FS, seed0 + 2 * i + o) for o in range(2)] for i in range(2)]
+
+
+def run(m, B, L, irs, x, pr, predelay=0, **kw):
+    with m.Engine(period=B, max_ir_frames=L, **kw) as e:
+        for i in range(2):
+            e.load_ir(i, irs[i][0], irs[i][1])
+            e.set_params(0, i, select=i, predelay=predelay, **pr[i])
+            e.set_glide(0, i, pr[i]["wet"])
+        y = e.render(x[None])[0]
+        return y, e.stats()
+
+
+@pytest.mark.parametrize("B,L,tiers", [
+    (64, 64 * 8 + 512 * 3 + 100, [(64, 8), (512, 0)]),
+    (64, 20000, [(64, 8), (512, 7), (4096, 0)]),
+    (32, 9000, [(32, 8), (256, 8), (2048, 0)]),
+    (128, 30000, [(128, 4), (512, 3), (2048, 0)]),
+    (256, 70000, "auto"),
+])
+def test_tiers_match_fp64_and_uniform(B, L, tiers):
+    m = ca()
+    irs = irs2x2(L)
+    n = ((L + 6 * 16384) // B) * B
+    x = np.stack([O.synth_audio(n, 2000 + i) for i in range(2)])
+    pr = [dict(wet=0.9, dry=0.2, level=0.8, panWet=0.2, panDry=-0.3), dict(wet=0.7, dry=0.1, level=1.0, panWet=-0.4, panDry=0.1)]
+    yt, st = run(m, B, L, irs, x, pr, predelay=37, tiers=tiers)
+    assert st.n_tiers >= 2
+    yu, su = run(m, B, L, irs, x, pr, predelay=37)
+    truth = O.engine_truth(x, irs, pr, predelay=37)
+    for o in range(2):
+        assert O.rel_l2(yt[o], truth[o]) < 5e-6, (o, O.rel_l2(yt[o], truth[o]))
+        assert O.rel_l2(yt[o], yu[o]) < 2e-6
+    assert st.mac_bytes_amortized < su.mac_bytes_amortized
+
+
+def test_cfg3_full_size_impulse_and_noise():
+    """configs[2] at full size: 64-frame period, 10 s IR (480 000 frames), tiers 64/512/4096/16384.
+    Size-independent property: an impulse returns the IR; plus noise vs the fp64 FFT convolution."""
+    m = ca()
+    B, L = 64, 480000
+    irs = irs2x2(L)
+    n = ((L + 40000) // B) * B
+    x = np.zeros((2, n), np.float32)
+    x[0, 5] = 1.0
+    x[1, 70] = -0.5
+    pr = [dict(wet=1.0, dry=0.0)] * 2
+    y, st = run(m, B, L, irs, x, pr, tiers="auto", flags=m.FLAG_GRAPH)
+    assert list(st.tier_block[:st.n_tiers]) == [64, 512, 4096, 16384]
+    for o in range(2):
+        want = np.zeros(n)
+        want[5:5 + L] += irs[0][o][:n - 5]
+        want[70:70 + L] += -0.5 * irs[1][o][:n - 70]
+        assert O.rel_l2(y[o], want) < 2e-6, (o, O.rel_l2(y[o], want))
+    xn = np.stack([O.synth_audio(n, 2000 + i) for i in range(2)])
+    yn, _ = run(m, B, L, irs, xn, pr, tiers="auto")
+    truth = O.engine_truth(xn, irs, pr)
+    for o in range(2):
+        assert O.rel_l2(yn[o], truth[o]) < 5e-6
+    idx = np.random.default_rng(3).integers(L // 2, n, 128)
+    d = O.direct_conv_at(xn[0], irs[0][0], idx) + O.direct_conv_at(xn[1], irs[1][0], idx)
+    assert O.rel_l2(yn[0][idx], d) < 1e-4
+
+
+def test_tiers_graph_batch_and_crossfade():
+    m = ca()
+    B, L, K = 64, 12000, 3
+    tiers = [(64, 8), (512, 7), (4096, 0)]
+    irs = [irs2x2(L, 1000 + 8 * s) for s in range(K)]
+    n = B * 900
+    x = np.stack([np.stack([O.synth_audio(n, 3000 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(flags, tiers):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, flags=flags, max_voices=3) as e:
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=1.0, dry=0.0)
+                    e.set_glide(s, i, 1.0)
+            out = np.empty((K, 2, n), np.float32)
+            for t in range(n // B):
+                if t == 300:   # instance 1, input 0 switches to the other IR of its pair with a 30-period glide
+                    e.set_params(1, 0, select=3, wet=1.0, dry=0.0, vsteps=30)
+                out[:, :, t * B:(t + 1) * B] = e.process(x[:, :, t * B:(t + 1) * B])
+            return out
+
+    yt = go(0, tiers)
+    yg = go(m.FLAG_GRAPH, tiers)
+    yu = go(0, None)
+    assert np.array_equal(yt, yg)                      # graph replay (per fire-mask graphs) == plain launches
+    assert O.rel_l2(yt, yu) < 2e-6                     # tiers == uniform, including the cross-fade of instance 1
+    truth = O.engine_truth(x[0], irs[0], [dict(wet=1.0)] * 2)
+    assert O.rel_l2(yt[0, 0], truth[0]) < 5e-6
+    # instance 1 really cross-faded: before the switch it equals IR pair (2,3), long after it input 0 uses IR 3
+    t1 = O.engine_truth(x[1], irs[1], [dict(wet=1.0)] * 2)
+    assert O.rel_l2(yt[1, 0][:300 * B], t1[0][:300 * B]) < 5e-6
+    assert O.rel_l2(yt[1, 0][350 * B:], t1[0][350 * B:]) > 1e-2
+
+
+def test_invalid_tier_configs():
+    m = ca()
+    with pytest.raises(m.CaError):
+        m.Engine(period=64, max_ir_frames=5000, tiers=[(64, 4), (512, 0)])      # offset 256 < block 512
+    with pytest.raises(m.CaError):
+        m.Engine(period=64, max_ir_frames=5000, tiers=[(128, 8), (1024, 0)])    # tier 0 != period
+    with pytest.raises(m.CaError):
+        m.Engine(period=64, max_ir_frames=50000, tiers=[(64, 8), (512, 2)])     # does not cover the IR
+    with pytest.raises(m.CaError):
+        m.Engine(period=64, max_ir_frames=5000, tiers=[(64, 8), (512, 0)], part_begin=0, part_count=4)
