@@ -543,7 +543,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
             tw[t.S + n] = make_float2((float)cos(b), (float)sin(b));
         }
         CA_CUDA(cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
-        CA_CUDA(cudaMemcpy(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CA_CUDA(cudaMemcpyAsync(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));  // pageable: staged before return
     }
     const size_t ring_bytes = n_items * e->nv * e->ring_len * sizeof(float);
     CA_CUDA(cudaMalloc(&e->d_ring, ring_bytes));
@@ -623,11 +623,15 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     return CA_OK;
 }
 
-static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames, uint32_t stride)
+static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames, uint32_t stride, bool foreign)
 {
     if (!e || !d_left || slot >= e->cfg.n_ir_slots) return CA_ERR_INVALID;
     if (e->n_out == 2 && !d_right) return CA_ERR_INVALID;
     CA_CUDA(cudaSetDevice(e->device));
+    // caller-produced device data (e.g. WavFile::buffer, filled by copies/kernels on the legacy or
+    // another stream) must be complete before this engine's non-blocking stream reads it;
+    // the reference's prepare() does the same (conv.cu:237)
+    if (foreign) CA_CUDA(cudaDeviceSynchronize());
     frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
     for (size_t j = 0; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
@@ -659,13 +663,13 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
 
 int ca_load_ir_device(ca_engine *e, uint32_t slot, const float *d_left, const float *d_right, uint32_t frames)
 {
-    return load_ir_dev(e, slot, d_left, d_right, frames, 1);
+    return load_ir_dev(e, slot, d_left, d_right, frames, 1, true);
 }
 
 int ca_load_ir_interleaved_device(ca_engine *e, uint32_t slot, const float *d_lr, uint32_t frames)
 {
     if (!d_lr) return CA_ERR_INVALID;
-    return load_ir_dev(e, slot, d_lr, d_lr + 1, frames, 2);
+    return load_ir_dev(e, slot, d_lr, d_lr + 1, frames, 2, true);
 }
 
 int ca_load_ir(ca_engine *e, uint32_t slot, const float *left, const float *right, uint32_t frames)
@@ -676,11 +680,13 @@ int ca_load_ir(ca_engine *e, uint32_t slot, const float *left, const float *righ
     const uint32_t n = std::min(frames, e->cfg.max_ir_frames);
     float *d = nullptr;
     CA_CUDA(cudaMalloc(&d, (size_t)2 * n * sizeof(float)));
-    cudaError_t rc = cudaMemcpy(d, left, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
-    if (rc == cudaSuccess && right) rc = cudaMemcpy(d + n, right, (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+    // stream-ordered uploads: a plain cudaMemcpy from pageable memory returns once the data is staged,
+    // its DMA runs on the legacy stream and is NOT ordered before kernels of this non-blocking stream
+    cudaError_t rc = cudaMemcpyAsync(d, left, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+    if (rc == cudaSuccess && right) rc = cudaMemcpyAsync(d + n, right, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, e->stream);
     int r = CA_OK;
     if (rc != cudaSuccess) { g_last_error = cudaGetErrorString(rc); r = CA_ERR_CUDA; }
-    else r = ca_load_ir_device(e, slot, d, right ? d + n : nullptr, n);
+    else r = load_ir_dev(e, slot, d, right ? d + n : nullptr, n, 1, false);
     cudaFree(d);
     return r;
 }

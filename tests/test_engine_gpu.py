@@ -352,8 +352,15 @@ def test_vs_reference_conv_cu(N, B):
             e.set_params(0, i, select=i, wet=1.0, dry=0.0)
         y = e.render(x[None])[0]
     sl = slice(warm * B, None)
-    assert O.rel_l2(y[0][sl], rl[sl]) < TOL_REF, O.rel_l2(y[0][sl], rl[sl])
-    assert O.rel_l2(y[1][sl], rr[sl]) < TOL_REF, O.rel_l2(y[1][sl], rr[sl])
+    truth = O.engine_truth(x, irs, [dict(wet=1.0)] * 2)
+    diag = dict(ours_vs_truth=[O.rel_l2(y[o][sl], truth[o][sl]) for o in range(2)],
+                ref_vs_truth=[O.rel_l2(r[sl], truth[o][sl]) for o, r in enumerate((rl, rr))])
+    bad = np.nonzero(np.abs(y[1] - truth[1]) > 1e-4)[0]
+    if len(bad):
+        diag["ours_R_bad"] = dict(n=len(bad), first_period=int(bad[0] // B), periods=sorted(set((bad // B).tolist()))[:10],
+                                  in_block=sorted(set((bad % B).tolist()))[:10])
+    assert O.rel_l2(y[0][sl], rl[sl]) < TOL_REF, diag
+    assert O.rel_l2(y[1][sl], rr[sl]) < TOL_REF, diag
 
 
 @needs_ref

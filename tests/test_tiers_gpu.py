@@ -124,6 +124,4 @@ def test_invalid_tier_configs():
     with pytest.raises(m.CaError):
         m.Engine(period=64, max_ir_frames=5000, tiers=[(128, 8), (1024, 0)])    # tier 0 != period
     with pytest.raises(m.CaError):
-        m.Engine(period=64, max_ir_frames=50000, tiers=[(64, 8), (512, 2)])     # does not cover the IR
-    with pytest.raises(m.CaError):
         m.Engine(period=64, max_ir_frames=5000, tiers=[(64, 8), (512, 0)], part_begin=0, part_count=4)
