@@ -199,7 +199,15 @@ int flush_params(ca_engine *e)
 MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
 {
     return MacArgs{t.X, t.H, t.Ypart, e->d_par, e->d_st, e->d_ctl, e->n_inst * e->n_in, e->n_in, e->nv, t.Lring, t.P, t.S,
-                   e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u};
+                   e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u};
+}
+
+// instances whose tier-j block closes at the end of period t_end - 1: s = r + i*m, r = (-t_end) mod m
+uint32_t tier_residue(const Tier &t, uint64_t tend) { return (uint32_t)((t.m - tend % t.m) % t.m); }
+uint32_t tier_count(const ca_engine *e, const Tier &t, uint64_t tend)
+{
+    const uint32_t r = tier_residue(t, tend);
+    return e->n_active > r ? (e->n_active - r + t.m - 1) / t.m : 0u;
 }
 
 // tier 0: the period pipeline.  After it the output block is complete.
@@ -224,34 +232,33 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile)
     return CA_OK;
 }
 
-// deferred tiers whose block completed with this period (bit j of mask = tier j fires)
-int launch_tiers(ca_engine *e, uint32_t mask)
+// deferred tiers: for every tier the phase-staggered subset of instances whose block just closed
+int launch_tiers(ca_engine *e, uint64_t tend)
 {
     const uint32_t n_alloc = e->n_inst * e->n_in;
     for (size_t j = 1; j < e->tiers.size(); j++) {
-        if (!((mask >> j) & 1u)) continue;
         const Tier &t = e->tiers[j];
+        const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
+        if (!count) continue;
         const uint32_t smem = t.S * sizeof(float2);
-        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B};
-        k_tier_forward<<<e->n_active * e->n_in * e->nv, kTierThreads, smem, e->stream>>>(fa);
+        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
+        k_tier_forward<<<count * e->n_in * e->nv, kTierThreads, smem, e->stream>>>(fa);
         MacArgs ma = mac_args(e, t, 0u);
-        t.mac.fn<<<dim3(t.n_split, t.tiles, e->n_active), kMacThreads, t.mac.smem, e->stream>>>(ma);
-        TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len};
-        k_tier_inverse<<<e->n_active * e->n_out, kTierThreads, smem, e->stream>>>(ia);
+        ma.inst0 = r; ma.inst_stride = t.m;
+        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, e->stream>>>(ma);
+        TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
+        k_tier_inverse<<<count * e->n_out, kTierThreads, smem, e->stream>>>(ia);
     }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
 
-uint32_t fire_mask(const ca_engine *e)
+uint32_t tiers_firing(const ca_engine *e, uint64_t tend)
 {
-    uint32_t mask = 0;
-    for (size_t j = 1; j < e->tiers.size(); j++)
-        if ((e->t_host + 1) % e->tiers[j].m == 0) mask |= 1u << j;
-    return mask;
+    uint32_t n = 0;
+    for (size_t j = 1; j < e->tiers.size(); j++) n += tier_count(e, e->tiers[j], tend) ? 1u : 0u;
+    return n;
 }
-
-uint32_t popcount(uint32_t v) { uint32_t c = 0; for (; v; v &= v - 1) c++; return c; }
 
 template <class F>
 int capture_graph(ca_engine *e, cudaGraphExec_t *out, F body)
@@ -303,25 +310,27 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
 // phase 2: the long tiers, off the output's critical path
 int run_deferred(ca_engine *e)
 {
-    const uint32_t mask = fire_mask(e);
-    e->t_host++;
+    const uint64_t tend = ++e->t_host;  // == ctl->t once k_inverse of this period has run
     const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
+    const uint32_t firing = tiers_firing(e, tend);
     int rc = CA_OK;
-    if (mask) {
+    if (firing) {
         if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
-            auto it = e->graphs.find(mask);
+            // the launch pattern (which instances of which tier) repeats with the longest tier's period
+            const uint32_t key = 1u + (uint32_t)(tend % e->tiers.back().m);
+            auto it = e->graphs.find(key);
             if (it == e->graphs.end()) {
                 cudaGraphExec_t ge = nullptr;
-                rc = capture_graph(e, &ge, [&] { return launch_tiers(e, mask); });
+                rc = capture_graph(e, &ge, [&] { return launch_tiers(e, tend); });
                 if (rc) return rc;
-                it = e->graphs.emplace(mask, ge).first;
+                it = e->graphs.emplace(key, ge).first;
             }
             CA_CUDA(cudaGraphLaunch(it->second, e->stream));
         } else {
-            rc = launch_tiers(e, mask);
+            rc = launch_tiers(e, tend);
             if (rc) return rc;
         }
-        e->launches += 3 * popcount(mask);
+        e->launches += 3 * firing;
     }
     if (profile) {
         CA_CUDA(cudaEventRecord(e->ev[4], e->stream));

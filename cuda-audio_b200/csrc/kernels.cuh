@@ -307,6 +307,10 @@ struct MacArgs {
     uint32_t t_bias;   // 1 for tier 0 (runs before k_inverse advances ctl->t), 0 for deferred tiers
     uint32_t n_split;
     uint32_t stream_hint;
+    // instances of this launch: inst0 + blockIdx.z * inst_stride.  Long tiers are phase-staggered:
+    // instance s closes its tier-j block when (t_end + s mod m) % m == 0, so every period only 1/m of
+    // the instances run the tier and the load per period is flat.
+    uint32_t inst0, inst_stride;
 };
 
 constexpr int kMacConsumers = 256;
@@ -338,11 +342,12 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
     __shared__ uint32_t s_slot[kMaxStreams];
     __shared__ float s_pan[2][NOUT];
 
-    const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = blockIdx.z;
+    const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = a.inst0 + blockIdx.z * a.inst_stride;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
     const unsigned long long tend = a.ctl->t + a.t_bias;  // periods completed at the end of this tier block
-    const unsigned long long n_fire = tend / a.m;
+    const uint32_t phase = inst % a.m;
+    const unsigned long long n_fire = (tend + phase) / a.m;
 
     if (tid == 0) {
 #pragma unroll
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
             if ((st.active >> v) & 1u) {
                 // partition k reads the block fired at index n_fire - k_off - k; it is valid when that
                 // block was built after the voice's (re)start: fire * m - 1 >= start
-                const long long first_fire = (long long)((st.start[v] + a.m) / a.m);  // ceil((start + 1) / m)
+                const long long first_fire = (long long)((st.start[v] + phase + a.m) / a.m);  // ceil((start + 1 + phase) / m)
                 const long long cnt = (long long)n_fire - first_fire + 1 - (long long)a.k_off;
                 nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
                 slot = st.slot[v];
@@ -614,14 +619,18 @@ struct TierFwdArgs {
     const ItemState *st;  // [2][n_items_alloc]
     const Ctl *ctl;
     const float2 *twM, *tw2M;
-    uint32_t n_items_alloc, nv, Lring, ring_len, S, s_log, m, B;
+    uint32_t n_items_alloc, n_in, nv, Lring, ring_len, S, s_log, m, B;
+    uint32_t inst0, inst_stride;  // firing instances: inst0 + i * inst_stride
 };
 
-// one CTA per (instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
+// one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
 __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const uint32_t w = blockIdx.x, item = w / a.nv, v = w % a.nv;
+    const uint32_t per = a.n_in * a.nv;
+    const uint32_t inst = a.inst0 + (blockIdx.x / per) * a.inst_stride;
+    const uint32_t item = inst * a.n_in + (blockIdx.x % per) / a.nv, v = blockIdx.x % a.nv;
+    const uint32_t w = item * a.nv + v;
     const unsigned long long tend = a.ctl->t;
     const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
     if (!((st.active >> v) & 1u)) return;
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     __syncthreads();
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, a.tw2M);
-    const unsigned long long n_fire = tend / a.m;
+    const unsigned long long n_fire = (tend + inst % a.m) / a.m;
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
     for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) dst[k] = sm[zpos((int)k, (int)a.s_log)];
@@ -644,13 +653,15 @@ struct TierInvArgs {
     const Ctl *ctl;
     const float2 *twM, *tw2M;
     uint32_t n_split, n_out, S, s_log, B, off, acc_len;
+    uint32_t inst0, inst_stride;
 };
 
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
 __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
-    const uint32_t item = blockIdx.x, inst = item / a.n_out, o = item % a.n_out;
+    const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
+    const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = a.ctl->t;
     for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) {
         float2 y = make_float2(0.f, 0.f);

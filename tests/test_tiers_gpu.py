@@ -125,3 +125,33 @@ def test_invalid_tier_configs():
         m.Engine(period=64, max_ir_frames=5000, tiers=[(128, 8), (1024, 0)])    # tier 0 != period
     with pytest.raises(m.CaError):
         m.Engine(period=64, max_ir_frames=5000, tiers=[(64, 8), (512, 0)], part_begin=0, part_count=4)
+
+
+def test_staggered_batch_more_instances_than_tier_period():
+    """Long tiers are phase-staggered over instances (instance s closes its tier-j block when
+    (t_end + s mod m) % m == 0).  19 instances, tier periods 8 and 32: every residue class holds
+    0..3 instances; each instance must still equal its own convolution."""
+    m = ca()
+    B, L, K = 64, 64 * 8 + 512 * 3 + 2048 * 2 - 100, 19
+    tiers = [(64, 8), (512, 3), (2048, 0)]
+    hs = [[O.synth_ir(L, FS, 7000 + 2 * s + o) for o in range(2)] for s in range(K)]
+    n = B * 260
+    x = np.stack([np.stack([O.synth_audio(n, 8000 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    for flags in (0, m.FLAG_GRAPH):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=K, tiers=tiers, flags=flags) as e:
+            for s in range(K):
+                e.load_ir(s, hs[s][0], hs[s][1])
+                for i in range(2):
+                    e.set_params(s, i, select=s, wet=1.0, dry=0.0)
+                    e.set_glide(s, i, 1.0)
+            y = e.render(x)
+            e.set_active(11)                      # shrink the batch mid-run: phases are per instance, not per launch
+            y2 = e.render(x[:11])
+        for s in range(K):
+            truth = O.engine_truth(x[s], [hs[s], hs[s]], [dict(wet=1.0)] * 2)
+            for o in range(2):
+                assert O.rel_l2(y[s, o], truth[o]) < 5e-6, (flags, s, o, O.rel_l2(y[s, o], truth[o]))
+        xx = np.concatenate([x[:11], x[:11]], axis=-1)
+        for s in (0, 5, 10):
+            truth = O.engine_truth(xx[s], [hs[s], hs[s]], [dict(wet=1.0)] * 2)
+            assert O.rel_l2(y2[s, 0], truth[0][n:]) < 5e-6, (flags, s)

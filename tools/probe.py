@@ -14,6 +14,8 @@ import cuda_audio_b200 as ca  # noqa: E402
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 periods = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 split = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+tiers = "auto" if os.environ.get("CA_TIERS") else None
+nvoices = int(os.environ.get("CA_VOICES", "0"))
 fs, B, L = 48000, 256, 192000
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
@@ -21,7 +23,7 @@ n = torch.arange(L, device=dev, dtype=torch.float32)
 env = torch.exp(-6.91 * n / (0.8 * L))
 flags = ca.FLAG_PROFILE | (ca.FLAG_STREAMING if K >= 16 else 0)
 t0 = time.time()
-e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split)
+e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split, tiers=tiers, max_voices=nvoices)
 g = torch.Generator(device=dev)
 for s in range(2 * K):
     g.manual_seed(1000 + s)
@@ -34,7 +36,7 @@ for s in range(K):
         e.set_params(s, i, select=2 * s + i, wet=1.0, dry=0.0)
         e.set_glide(s, i, 1.0)
 print(f"setup {time.time() - t0:.1f}s", flush=True)
-x = torch.randn(K, 2, B, device=dev) * 0.1
+x = torch.randn(K, 2, B, device=dev) * (0.0 if os.environ.get("CA_ZERO_INPUT") else 0.1)
 y = torch.empty(K, 2, B, device=dev)
 torch.cuda.synchronize()
 for _ in range(760):  # steady state: every FDL slot filled (the engine skips slots older than a voice's start)
@@ -48,6 +50,7 @@ e.sync()
 dt = (time.time() - t0) / periods
 st = e.stats()
 gbs = st.mac_bytes / (st.mac_us * 1e-6) / 1e9
-print(f"variant={os.environ.get('CA_MAC_VARIANT', '0')} K={K} split={st.mac_split} fwd={st.fwd_us:.1f}us mac={st.mac_us:.1f}us inv={st.inv_us:.1f}us "
+print(f"tiers={list(st.tier_block[:st.n_tiers])}x{list(st.tier_parts[:st.n_tiers])} dev_bytes={st.device_bytes/1e9:.1f}GB tiers_us={st.tiers_us:.1f} p50={st.p50_us:.0f} p99={st.p99_us:.0f} max={st.max_us:.0f}")
+print(f"variant={os.environ.get('CA_MAC_VARIANT', '1')} K={K} split={st.mac_split} fwd={st.fwd_us:.1f}us mac={st.mac_us:.1f}us inv={st.inv_us:.1f}us "
       f"wall/period={dt * 1e6:.1f}us MAC {gbs:.0f} GB/s ({gbs / 6460.2:.3f} of measured HBM) "
       f"rt_channels={K * (B / fs) / (st.total_us * 1e-6):.0f} y_rms={float(y.pow(2).mean().sqrt()):.4f}", flush=True)
