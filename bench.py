@@ -104,9 +104,9 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_engine(ca, torch, dev, K, flags, mac_split=0):
+def build_engine(ca, torch, dev, K, flags, tiers=None, mac_split=0):
     e = ca.Engine(period=B, max_ir_frames=IR_FRAMES, n_instances=K, n_ir_slots=2 * K, device=dev.index,
-                  flags=flags, mac_split=mac_split, sample_rate=FS)
+                  flags=flags, mac_split=mac_split, sample_rate=FS, tiers=tiers)
     n = torch.arange(IR_FRAMES, device=dev, dtype=torch.float32)
     env = torch.exp(-6.91 * n / (0.8 * IR_FRAMES))       # T60 = 0.8 x IR length
     g = torch.Generator(device=dev)
@@ -114,8 +114,7 @@ def build_engine(ca, torch, dev, K, flags, mac_split=0):
         g.manual_seed(1000 + s)
         h = torch.randn(2, IR_FRAMES, device=dev, generator=g) * env
         h = h / h.pow(2).sum(dim=1, keepdim=True).sqrt()  # unit energy per channel
-        torch.cuda.current_stream().synchronize()
-        e.load_ir_device(s, h[0].data_ptr(), h[1].data_ptr(), IR_FRAMES)
+        e.load_ir_device(s, h[0].data_ptr(), h[1].data_ptr(), IR_FRAMES)   # synchronises the device itself
     for s in range(K):
         for i in range(2):
             e.set_params(s, i, select=2 * s + i)          # reference defaults: wet = dry = 0.5
@@ -123,9 +122,8 @@ def build_engine(ca, torch, dev, K, flags, mac_split=0):
     return e
 
 
-def percentile(v, q):
-    v = sorted(v)
-    return v[min(len(v) - 1, int(q * len(v)))]
+def tier_desc(st):
+    return [{"block": int(st.tier_block[j]), "partitions": int(st.tier_parts[j]), "ir_offset": int(st.tier_offset[j])} for j in range(st.n_tiers)]
 
 
 def run_ours(args):
@@ -155,8 +153,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    deadline_s = B / FS
+    tiers = None if args.uniform else "auto"
     K = args.instances
-    e = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING)
+    e = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING, tiers=tiers)
+    st0 = e.stats()
+    cycle = max(int(st0.tier_block[j]) for j in range(st0.n_tiers)) // B      # periods until the launch pattern repeats
     gin = torch.Generator(device=dev)
     gin.manual_seed(2000 + rank)
     x_dev = (torch.randn(K, 2, B, device=dev, generator=gin) * 0.1).clamp_(-0.9, 0.9)   # RMS 0.1 noise
@@ -166,24 +168,24 @@ def run_ours(args):
 
     # ---- device-resident throughput: `value` ----
     # Steady state only: the engine skips delay-line slots that are older than a voice's start, so
-    # the first P = 750 periods after start-up do LESS work than a running system.  Warm up past that.
-    warm = max(args.warmup, 3) + STEADY
+    # the first IR-length worth of periods after start-up does LESS work than a running system.
+    warm = max(args.warmup, 3) + STEADY + cycle
     for _ in range(warm):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
     e.sync()
+    steps = ((args.steps + cycle - 1) // cycle) * cycle if args.round_to_cycle else args.steps
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = e.stats().gpu_launches
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
     ev1.record(stream)
     e.sync()
     barrier()
-    ms_dev = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
-    launches = e.stats().gpu_launches - launches0
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1)) / steps
 
     # ---- end to end through ca_process with pinned host buffers: `e2e` ----
     pin, pout = ca.PinnedArray((K, 2, B)), ca.PinnedArray((K, 2, B))
@@ -192,87 +194,37 @@ def run_ours(args):
         e.process_raw(pin.ptr, pout.ptr)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e.process_raw(pin.ptr, pout.ptr)
+    e.sync()
     barrier()
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    launches += 3 * args.steps
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    launches = e.stats().gpu_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     y_rms = float(np.sqrt((pout.array.astype(np.float64) ** 2).mean()))
+    st_main = e.stats()
 
-    # ---- roofline of the dominant kernel (FDL MAC), CUDA events around each kernel ----
-    roof = None
     extras = {}
-    e_prof = None
-    if rank == 0 and not args.no_roofline:
-        e.close()
-        e = None
-        torch.cuda.empty_cache()
-        e_prof = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING | ca.FLAG_PROFILE)
-        for _ in range(STEADY):
-            e_prof.process_device(x_dev.data_ptr(), y_dev.data_ptr())
-        e_prof.sync()
-        e_prof.reset_stats()
-        for _ in range(min(args.steps, 50)):
-            e_prof.process_device(x_dev.data_ptr(), y_dev.data_ptr())
-        e_prof.sync()
-        st = e_prof.stats()
-        peak, peak_src = measured_peak_hbm()
-        achieved = st.mac_bytes / (st.mac_us * 1e-6) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "mac_traffic.json")) as f:
-                traffic = int(json.load(f)["dram_bytes_per_instance"] * K)  # ncu --set full capture, scaled per instance
-        except Exception:
-            pass
-        roof = {"kernel": "k_mac (FDL complex MAC, TMA-staged)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(st.mac_bytes), "kernel_us": round(st.mac_us, 2),
-                "step_us": {"forward_r2c": round(st.fwd_us, 2), "fdl_mac": round(st.mac_us, 2), "inverse_c2r_mix": round(st.inv_us, 2)}}
-        e_prof.close()
-        e_prof = None
-        torch.cuda.empty_cache()
-
-    # ---- latency of ONE instance through the public call (p50/p99), and the sustained search ----
-    if rank == 0 and world == 1 and not args.no_latency:
-        e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH)
-        a, b = ca.PinnedArray((1, 2, B)), ca.PinnedArray((1, 2, B))
-        a.array[...] = 0.05
-        for _ in range(STEADY + 200):
-            e1.process_raw(a.ptr, b.ptr)
-        e1.reset_stats()
-        for _ in range(args.latency_periods):
-            e1.process_raw(a.ptr, b.ptr)
-        s1 = e1.stats()
-        extras["latency_1_instance"] = {"periods": int(s1.periods), "p50_us": round(s1.p50_us, 1), "p99_us": round(s1.p99_us, 1),
-                                        "max_us": round(s1.max_us, 1), "deadline_us": round(DEADLINE_MS * 1e3, 1),
-                                        "p99_frac_of_deadline": round(s1.p99_us / (DEADLINE_MS * 1e3), 4), "mac_split": int(s1.mac_split)}
-        e1.close()
+    # ---- sustained real-time channels through ca_process: largest K whose p99 per-period wall time
+    #      over >= 2000 consecutive periods stays below the deadline / 25 % of it ----
     if rank == 0 and world == 1 and not args.no_sustained:
-        Kmax = args.sustain_instances
-        es = build_engine(ca, torch, dev, Kmax, ca.FLAG_STREAMING)
-        a, b = ca.PinnedArray((Kmax, 2, B)), ca.PinnedArray((Kmax, 2, B))
-        a.array[...] = pin.array[np.arange(Kmax) % K]
-        for _ in range(STEADY):       # fill every instance's delay lines before searching
-            es.process_raw(a.ptr, b.ptr)
-
         def p99_at(k, periods):
-            es.set_active(k)
-            for _ in range(20):
-                es.process_raw(a.ptr, b.ptr)
-            es.reset_stats()
+            e.set_active(k)
+            for _ in range(2 * cycle):
+                e.process_raw(pin.ptr, pout.ptr)
+            e.reset_stats()
             for _ in range(periods):
-                es.process_raw(a.ptr, b.ptr)
-            s = es.stats()
-            return s.p99_us, s.p50_us
+                e.process_raw(pin.ptr, pout.ptr)
+            s = e.stats()
+            return s.p99_us, s.p50_us, s.max_us
 
         def search(limit_us):
-            lo, hi = 1, Kmax
-            if p99_at(hi, 100)[0] < limit_us:
+            lo, hi = 1, K
+            if p99_at(hi, 128)[0] < limit_us:
                 return hi
-            while hi - lo > max(8, Kmax // 128):
+            while hi - lo > max(8, K // 128):
                 mid = (lo + hi) // 2
-                if p99_at(mid, 100)[0] < limit_us:
+                if p99_at(mid, 128)[0] < limit_us:
                     lo = mid
                 else:
                     hi = mid
@@ -281,15 +233,95 @@ def run_ours(args):
         res = {}
         for name, frac in (("p99_lt_deadline", 1.0), ("p99_lt_25pct_deadline", 0.25)):
             k = search(frac * DEADLINE_MS * 1e3)
-            periods = args.sustain_periods
-            p99, p50 = p99_at(k, periods)           # confirmation over >= 2000 consecutive periods
+            p99, p50, mx = p99_at(k, args.sustain_periods)   # confirmation over >= 2000 consecutive periods
             while p99 >= frac * DEADLINE_MS * 1e3 and k > 8:
                 k = int(k * 0.97)
-                p99, p50 = p99_at(k, periods)
-            res[name] = {"channels": int(k), "p50_us": round(p50, 1), "p99_us": round(p99, 1), "periods": periods,
-                         "capped_by_allocation": bool(k >= Kmax)}
+                p99, p50, mx = p99_at(k, args.sustain_periods)
+            res[name] = {"channels": int(k), "p50_us": round(p50, 1), "p99_us": round(p99, 1), "max_us": round(mx, 1),
+                         "periods": args.sustain_periods, "capped_by_allocation": bool(k >= K)}
+        res["note"] = (f"{K} instances hold {st_main.device_bytes / 1e9:.0f} GB of distinct IR spectra + delay lines; "
+                       "'capped_by_allocation' means HBM capacity, not time, limits the count")
         extras["sustained_through_ca_process"] = res
-        es.close()
+        e.set_active(K)
+    e.close()
+    e = None
+    pin.free()
+    pout.free()
+    torch.cuda.empty_cache()
+
+    # ---- per-kernel device times (CUDA events around every kernel) and the MAC's roofline ----
+    roof = None
+    if rank == 0 and not args.no_roofline:
+        peak, peak_src = measured_peak_hbm()
+        Kp = min(K, args.profile_instances)
+        ep = build_engine(ca, torch, dev, Kp, ca.FLAG_STREAMING | ca.FLAG_PROFILE, tiers=tiers)
+        for _ in range(STEADY + cycle):
+            ep.process_device(x_dev.data_ptr(), y_dev.data_ptr())
+        ep.sync()
+        ep.reset_stats()
+        for _ in range(max(cycle, 32)):
+            ep.process_device(x_dev.data_ptr(), y_dev.data_ptr())
+        ep.sync()
+        sp = ep.stats()
+        mac_us = sp.mac_us + sp.tier_mac_us
+        achieved = sp.mac_bytes_amortized / (mac_us * 1e-6) / 1e9
+        roof = {"kernel": "k_mac (FDL complex MAC, TMA-staged; all tiers of one period)", "bound": "hbm", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "instances": Kp, "algorithmic_bytes_per_period": int(sp.mac_bytes_amortized), "kernel_us_per_period": round(mac_us, 2),
+                "share_of_step": round(mac_us / sp.total_us, 3),
+                "step_us": {"forward_r2c": round(sp.fwd_us, 2), "fdl_mac_tier0": round(sp.mac_us, 2), "inverse_c2r_mix": round(sp.inv_us, 2),
+                            "long_tiers_forward_fft": round(sp.tier_fwd_us, 2), "long_tiers_mac": round(sp.tier_mac_us, 2),
+                            "long_tiers_inverse_fft": round(sp.tier_inv_us, 2), "total": round(sp.total_us, 2)}}
+        ep.close()
+        torch.cuda.empty_cache()
+        if not args.uniform:
+            # the same FDL MAC on the uniform partitioning: one pure HBM stream of K x 9.2 MB per launch
+            Ku = min(K, args.uniform_instances)
+            eu = build_engine(ca, torch, dev, Ku, ca.FLAG_STREAMING | ca.FLAG_PROFILE, tiers=None)
+            for _ in range(STEADY):
+                eu.process_device(x_dev.data_ptr(), y_dev.data_ptr())
+            eu.sync()
+            eu.reset_stats()
+            for _ in range(32):
+                eu.process_device(x_dev.data_ptr(), y_dev.data_ptr())
+            eu.sync()
+            su = eu.stats()
+            ach_u = su.mac_bytes / (su.mac_us * 1e-6) / 1e9
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "mac_traffic.json")) as f:
+                    traffic = int(json.load(f)["dram_bytes_per_instance"] * Ku)   # ncu --set full capture, per instance
+            except Exception:
+                pass
+            extras["uniform_partitioning"] = {
+                "instances": Ku, "partitions": int(su.partitions), "rt_channels": round(Ku * deadline_s / (su.total_us * 1e-6), 1),
+                "roofline": {"kernel": "k_mac, uniform P=750: one HBM stream", "bound": "hbm", "achieved": round(ach_u, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(ach_u / peak, 4), "traffic": traffic, "algorithmic_bytes_per_launch": int(su.mac_bytes),
+                             "kernel_us": round(su.mac_us, 2), "share_of_step": round(su.mac_us / su.total_us, 3)},
+                "step_us": {"forward_r2c": round(su.fwd_us, 2), "fdl_mac": round(su.mac_us, 2), "inverse_c2r_mix": round(su.inv_us, 2)}}
+            eu.close()
+            torch.cuda.empty_cache()
+
+    # ---- latency of ONE instance through the public call (p50/p99) ----
+    if rank == 0 and world == 1 and not args.no_latency:
+        lat = {}
+        for name, tr in (("non_uniform", "auto"), ("uniform", None)):
+            e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH, tiers=tr)
+            a, b = ca.PinnedArray((1, 2, B)), ca.PinnedArray((1, 2, B))
+            a.array[...] = 0.05
+            for _ in range(STEADY + 200):
+                e1.process_raw(a.ptr, b.ptr)
+            e1.reset_stats()
+            for _ in range(args.latency_periods):
+                e1.process_raw(a.ptr, b.ptr)
+            s1 = e1.stats()
+            lat[name] = {"periods": int(s1.periods), "p50_us": round(s1.p50_us, 1), "p99_us": round(s1.p99_us, 1), "max_us": round(s1.max_us, 1),
+                         "p99_frac_of_deadline": round(s1.p99_us / (DEADLINE_MS * 1e3), 4), "mac_split": int(s1.mac_split)}
+            e1.close()
+            a.free()
+            b.free()
+        lat["deadline_us"] = round(DEADLINE_MS * 1e3, 1)
+        extras["latency_1_instance"] = lat
 
     # ---- CPU baseline (oracle port) on the host cores, rank 0, N = 1 only ----
     cpu = None
@@ -297,15 +329,16 @@ def run_ours(args):
         cpu = cpu_port_baseline(args.cpu_seconds)
 
     if rank == 0:
-        deadline_s = B / FS
         out = {
             "metric": METRIC, "value": round(world * K * deadline_s / (ms_dev * 1e-3), 1), "unit": "rt_channels",
-            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_dev, 4),
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(ms_dev, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample_rate": FS, "period": B, "ir_frames": IR_FRAMES, "partitions": 750,
-                       "instances_per_gpu": K, "sharding": "independent instances per GPU, no collective",
-                       "l2": f"inputs larger than L2: {K * 9.224e6 / 1e9:.1f} GB of spectra streamed per step per GPU",
-                       "value_definition": "instances x periods/s x (256/48000): real-time channel equivalents"},
+            "config": {"workload": WORKLOAD, "sample_rate": FS, "period": B, "ir_frames": IR_FRAMES,
+                       "partitioning": "uniform" if args.uniform else "non-uniform (tiers phase-staggered over instances)",
+                       "tiers": tier_desc(st_main), "instances_per_gpu": K, "device_bytes_per_gpu": int(st_main.device_bytes),
+                       "sharding": "independent instances per GPU, no collective",
+                       "l2": f"inputs larger than L2: {st_main.mac_bytes_amortized / 1e9:.2f} GB of spectra streamed per step per GPU out of a {st_main.device_bytes / 1e9:.0f} GB working set",
+                       "value_definition": "instances x periods/s x (256/48000): real-time channel equivalents; every instance is a distinct 4-path true-stereo convolution"},
             "clocks": clocks,
             "e2e": {"value": round(world * K * deadline_s / (ms_e2e * 1e-3), 1), "unit": "rt_channels", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": K * 2 * B * 4, "d2h_bytes_per_step": K * 2 * B * 4, "api": "ca_process (C ABI), pinned host buffers"},
@@ -434,8 +467,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--instances", type=int, default=3072, help="instances per GPU in the throughput run")
-    ap.add_argument("--sustain-instances", type=int, default=4096)
+    ap.add_argument("--instances", type=int, default=10240, help="instances per GPU in the throughput run")
+    ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
+    ap.add_argument("--uniform-instances", type=int, default=2048)
+    ap.add_argument("--profile-instances", type=int, default=4096)
+    ap.add_argument("--round-to-cycle", action="store_true", help="round --steps up to a multiple of the tier launch-pattern period")
     ap.add_argument("--sustain-periods", type=int, default=2000)
     ap.add_argument("--latency-periods", type=int, default=2000)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

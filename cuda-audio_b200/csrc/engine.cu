@@ -145,7 +145,10 @@ struct ca_engine {
     uint32_t g_active = 0;
     // profiling
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t tev[CA_MAX_TIERS][4] = {};
+    bool tev_used[CA_MAX_TIERS] = {};
     double prof_us[4] = {0, 0, 0, 0};
+    double tier_prof_us[3] = {0, 0, 0};  // long tiers: forward FFT, MAC, inverse FFT
     uint64_t prof_n = 0;
     // stats
     std::vector<float> wall;  // ring of host wall times (us)
@@ -233,21 +236,26 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile)
 }
 
 // deferred tiers: for every tier the phase-staggered subset of instances whose block just closed
-int launch_tiers(ca_engine *e, uint64_t tend)
+int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
 {
     const uint32_t n_alloc = e->n_inst * e->n_in;
     for (size_t j = 1; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
         const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
+        e->tev_used[j] = profile && count;
         if (!count) continue;
         const uint32_t smem = t.S * sizeof(float2);
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], e->stream));
         k_tier_forward<<<count * e->n_in * e->nv, kTierThreads, smem, e->stream>>>(fa);
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], e->stream));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
         t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, e->stream>>>(ma);
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], e->stream));
         TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
         k_tier_inverse<<<count * e->n_out, kTierThreads, smem, e->stream>>>(ia);
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], e->stream));
     }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -321,13 +329,13 @@ int run_deferred(ca_engine *e)
             auto it = e->graphs.find(key);
             if (it == e->graphs.end()) {
                 cudaGraphExec_t ge = nullptr;
-                rc = capture_graph(e, &ge, [&] { return launch_tiers(e, tend); });
+                rc = capture_graph(e, &ge, [&] { return launch_tiers(e, tend, false); });
                 if (rc) return rc;
                 it = e->graphs.emplace(key, ge).first;
             }
             CA_CUDA(cudaGraphLaunch(it->second, e->stream));
         } else {
-            rc = launch_tiers(e, tend);
+            rc = launch_tiers(e, tend, profile);
             if (rc) return rc;
         }
         e->launches += 3 * firing;
@@ -340,6 +348,13 @@ int run_deferred(ca_engine *e)
             CA_CUDA(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
             e->prof_us[i] += 1e3 * ms;
         }
+        for (size_t j = 1; j < e->tiers.size(); j++)
+            if (e->tev_used[j])
+                for (int i = 0; i < 3; i++) {
+                    float ms = 0;
+                    CA_CUDA(cudaEventElapsedTime(&ms, e->tev[j][i], e->tev[j][i + 1]));
+                    e->tier_prof_us[i] += 1e3 * ms;
+                }
         e->prof_n++;
     }
     return CA_OK;
@@ -424,6 +439,7 @@ int ca_destroy(ca_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graphs(e);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &row : e->tev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->upload_done) if (ev) cudaEventDestroy(ev);
     if (e->out_ready) cudaEventDestroy(e->out_ready);
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.tw); }
@@ -489,6 +505,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
 
     CA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto &ev : e->ev) CA_CUDA(cudaEventCreate(&ev));
+    for (auto &row : e->tev) for (auto &ev : row) CA_CUDA(cudaEventCreate(&ev));
     for (auto &ev : e->upload_done) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
 
@@ -806,6 +823,9 @@ int ca_get_stats(ca_engine *e, ca_stats *s)
         s->mac_us = e->prof_us[1] / (double)e->prof_n;
         s->inv_us = e->prof_us[2] / (double)e->prof_n;
         s->tiers_us = e->prof_us[3] / (double)e->prof_n;
+        s->tier_fwd_us = e->tier_prof_us[0] / (double)e->prof_n;
+        s->tier_mac_us = e->tier_prof_us[1] / (double)e->prof_n;
+        s->tier_inv_us = e->tier_prof_us[2] / (double)e->prof_n;
         s->total_us = s->fwd_us + s->mac_us + s->inv_us + s->tiers_us;
     }
     s->gpu_launches = e->launches;
@@ -826,6 +846,7 @@ int ca_reset_stats(ca_engine *e)
     if (!e) return CA_ERR_INVALID;
     e->periods = e->xruns = 0; e->wall_sum = e->wall_max = 0;
     for (auto &p : e->prof_us) p = 0;
+    for (auto &p : e->tier_prof_us) p = 0;
     e->prof_n = 0;
     return CA_OK;
 }

@@ -52,7 +52,8 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("periods", C.c_uint64), ("xruns", C.c_uint64), ("mean_us", C.c_double), ("p50_us", C.c_double),
                 ("p99_us", C.c_double), ("max_us", C.c_double), ("fwd_us", C.c_double), ("mac_us", C.c_double),
-                ("inv_us", C.c_double), ("tiers_us", C.c_double), ("total_us", C.c_double), ("gpu_launches", C.c_uint64),
+                ("inv_us", C.c_double), ("tiers_us", C.c_double), ("total_us", C.c_double), ("tier_fwd_us", C.c_double),
+                ("tier_mac_us", C.c_double), ("tier_inv_us", C.c_double), ("gpu_launches", C.c_uint64),
                 ("mac_bytes", C.c_uint64), ("mac_bytes_amortized", C.c_uint64), ("partitions", C.c_uint32),
                 ("mac_split", C.c_uint32), ("device_bytes", C.c_uint64), ("n_tiers", C.c_uint32),
                 ("tier_block", C.c_uint32 * CA_MAX_TIERS), ("tier_parts", C.c_uint32 * CA_MAX_TIERS),

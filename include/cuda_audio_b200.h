@@ -106,6 +106,7 @@ typedef struct ca_stats {
     /* CA_FLAG_PROFILE: mean device time per period, CUDA events on the engine's stream:
      * forward R2C, FDL MAC, inverse C2R+mix of tier 0, and the deferred long tiers */
     double fwd_us, mac_us, inv_us, tiers_us, total_us;
+    double tier_fwd_us, tier_mac_us, tier_inv_us; /* the long tiers' share of tiers_us by kernel */
     uint64_t gpu_launches;  /* kernels launched by the engine so far                    */
     uint64_t mac_bytes;     /* algorithmic bytes tier 0's FDL MAC streams per period    */
     uint64_t mac_bytes_amortized; /* all tiers, per period (tier j fires every block_j/period) */
