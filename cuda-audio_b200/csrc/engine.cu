@@ -75,17 +75,17 @@ MacVariant mac_pick(int bt, int n_out, int variant)
     }
 }
 
-struct FftFns { fwd_fn fwd; ir_fn ir; inv_fn inv; };
+struct FftFns { fwd_fn fwd; ir_fn ir; inv_fn inv, inv_packed; };
 FftFns fft_pick(int R)
 {
     switch (R) {
-    case 1: return {k_forward<1>, k_ir_fft<1>, k_inverse<1>};
-    case 2: return {k_forward<2>, k_ir_fft<2>, k_inverse<2>};
-    case 4: return {k_forward<4>, k_ir_fft<4>, k_inverse<4>};
-    case 8: return {k_forward<8>, k_ir_fft<8>, k_inverse<8>};
-    case 16: return {k_forward<16>, k_ir_fft<16>, k_inverse<16>};
-    case 32: return {k_forward<32>, k_ir_fft<32>, k_inverse<32>};
-    default: return {nullptr, nullptr, nullptr};
+    case 1: return {k_forward<1>, k_ir_fft<1>, k_inverse<1, false>, k_inverse<1, true>};
+    case 2: return {k_forward<2>, k_ir_fft<2>, k_inverse<2, false>, k_inverse<2, true>};
+    case 4: return {k_forward<4>, k_ir_fft<4>, k_inverse<4, false>, k_inverse<4, true>};
+    case 8: return {k_forward<8>, k_ir_fft<8>, k_inverse<8, false>, k_inverse<8, true>};
+    case 16: return {k_forward<16>, k_ir_fft<16>, k_inverse<16, false>, k_inverse<16, true>};
+    case 32: return {k_forward<32>, k_ir_fft<32>, k_inverse<32, false>, k_inverse<32, true>};
+    default: return {nullptr, nullptr, nullptr, nullptr};
     }
 }
 
@@ -223,13 +223,14 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile)
                n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out};
     MacArgs ma = mac_args(e, t0, 1u);
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
-               t0.n_split, e->n_in, e->n_out, e->acc_len};
+               t0.n_split, e->n_in, e->n_out, e->acc_len, e->n_active * e->n_out};
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     e->fft.fwd<<<(n_items * e->nv + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
     t0.mac.fn<<<dim3(t0.n_split, t0.tiles, e->n_active), kMacThreads, t0.mac.smem, e->stream>>>(ma);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    e->fft.inv<<<e->n_active * e->n_out, kInvThreads, 0, e->stream>>>(ia);
+    if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
+    else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
     CA_CUDA(cudaGetLastError());
     return CA_OK;

@@ -1,11 +1,15 @@
 // fft_cta.cuh -- CTA-level complex FFT of M = 256 * 2^s points (s = 0..6) in shared memory, for the
 // long tiers of the non-uniform partitioning (block sizes 256 .. 16384).
 //
-//   forward : s radix-2 DIF stages in shared memory (span M -> 512), then one 256-point warp FFT
+//   forward : radix-4 DIF passes in shared memory (two fused radix-2 stages each, plus one radix-2
+//             pass when s is odd) bring the span from M down to 512, then one 256-point warp FFT
 //             (fft_warp.cuh, R = 8) per contiguous 256-element block.
-//   inverse : the transposed flow graph (warp inverse FFTs, then radix-2 DIT stages).
+//   inverse : the transposed flow graph (warp inverse FFTs, then DIT passes).
 // After `forward` bin k lives at shared index zpos(k) = (bitrev_s(k mod 2^s) << 8) | (k >> s);
 // `inverse` expects its input in that layout and leaves time samples in natural order.
+// Twiddles come from two 128-entry shared-memory tables per transform (W^n = hi[n >> 7] * lo[n & 127],
+// filled from the fp64-accurate global table): no dependent global loads inside the passes.
+// Layout checked against numpy in tests/test_fft_model.py (cta_fwd / cta_inv / zpos).
 #pragma once
 #include "fft_warp.cuh"
 
@@ -19,31 +23,113 @@ __device__ __forceinline__ int zpos(int k, int s)
     return (b << 8) | (k >> s);
 }
 
-// twM: W_M^n, n < M.  All threads of the CTA must call; ends with __syncthreads().
-__device__ __forceinline__ void cta_fft_forward(float2 *sm, int M, int s, const float2 *__restrict__ twM)
+struct CtaTw {
+    float2 hi[128], lo[128];    // W_M^(128 a), W_M^b
+    float2 hi2[128], lo2[128];  // W_2M^(128 a), W_2M^b   (real-FFT split)
+};
+
+// all threads; twM = W_M^n (n < M), tw2M = W_2M^k (k < M); ends with __syncthreads()
+__device__ __forceinline__ void cta_tw_init(CtaTw &t, int M, const float2 *__restrict__ twM, const float2 *__restrict__ tw2M)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x;
-    for (int st = 0; st < s; st++) {
-        const int lh = 31 - __clz(M) - 1 - st;  // log2(half)
-        const int half = 1 << lh;
-        for (int j = tid; j < M / 2; j += nthreads) {
-            const int pos = j & (half - 1);
-            const int i0 = ((j >> lh) << (lh + 1)) | pos, i1 = i0 + half;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
+        const int a = (128 * i < M) ? 128 * i : 0;
+        t.hi[i] = __ldg(&twM[a]);
+        t.lo[i] = __ldg(&twM[i]);
+        t.hi2[i] = __ldg(&tw2M[a]);
+        t.lo2[i] = __ldg(&tw2M[i]);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float2 tw_m(const CtaTw &t, int n) { return cmul(t.hi[n >> 7], t.lo[n & 127]); }
+__device__ __forceinline__ float2 tw_2m(const CtaTw &t, int k) { return cmul(t.hi2[k >> 7], t.lo2[k & 127]); }
+
+__device__ __forceinline__ float2 mul_mj(float2 v) { return make_float2(v.y, -v.x); }  // v * (-j)
+__device__ __forceinline__ float2 mul_pj(float2 v) { return make_float2(-v.y, v.x); }  // v * (+j)
+
+// two fused radix-2 DIF stages (st, st+1): span N = M >> st, quarter q = N / 4
+__device__ __forceinline__ void dif_radix4_pass(float2 *sm, int M, int st, const CtaTw &t)
+{
+    const int lq = 31 - __clz(M) - st - 2;
+    const int q = 1 << lq;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < M / 4; j += blockDim.x) {
+        const int pos = j & (q - 1);
+        const int base = ((j >> lq) << (lq + 2)) | pos;
+        const float2 a0 = sm[base], a1 = sm[base + q], a2 = sm[base + 2 * q], a3 = sm[base + 3 * q];
+        const float2 wA = tw_m(t, pos << st);  // W_N^pos ; W_N^(pos+q) = -j W_N^pos ; W_(N/2)^pos = (W_N^pos)^2
+        const float2 wB = cmul(wA, wA);
+        const float2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), wA);
+        const float2 b1 = cadd(a1, a3), b3 = mul_mj(cmul(csub(a1, a3), wA));
+        sm[base] = cadd(b0, b1);
+        sm[base + q] = cmul(csub(b0, b1), wB);
+        sm[base + 2 * q] = cadd(b2, b3);
+        sm[base + 3 * q] = cmul(csub(b2, b3), wB);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void dit_radix4_pass(float2 *sm, int M, int st, const CtaTw &t)
+{
+    const int lq = 31 - __clz(M) - st - 2;
+    const int q = 1 << lq;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < M / 4; j += blockDim.x) {
+        const int pos = j & (q - 1);
+        const int base = ((j >> lq) << (lq + 2)) | pos;
+        const float2 c0 = sm[base], c1 = sm[base + q], c2 = sm[base + 2 * q], c3 = sm[base + 3 * q];
+        const float2 wA = tw_m(t, pos << st);
+        const float2 wB = cmul(wA, wA);
+        const float2 t1 = cmulc(c1, wB), t3 = cmulc(c3, wB);
+        const float2 b0 = cadd(c0, t1), b1 = csub(c0, t1), b2 = cadd(c2, t3), b3 = csub(c2, t3);
+        const float2 u2 = cmulc(b2, wA), u3 = mul_pj(cmulc(b3, wA));
+        sm[base] = cadd(b0, u2);
+        sm[base + 2 * q] = csub(b0, u2);
+        sm[base + q] = cadd(b1, u3);
+        sm[base + 3 * q] = csub(b1, u3);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void radix2_pass(float2 *sm, int M, int st, const CtaTw &t, bool inverse)
+{
+    const int lh = 31 - __clz(M) - 1 - st;
+    const int half = 1 << lh;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < M / 2; j += blockDim.x) {
+        const int pos = j & (half - 1);
+        const int i0 = ((j >> lh) << (lh + 1)) | pos, i1 = i0 + half;
+        const float2 w = tw_m(t, pos << st);  // W_{2 half}^pos
+        if (!inverse) {
             const float2 a = sm[i0], b = sm[i1];
-            const float2 w = __ldg(&twM[pos << st]);  // W_{2 half}^pos
             sm[i0] = cadd(a, b);
             sm[i1] = cmul(csub(a, b), w);
+        } else {
+            const float2 a = sm[i0], b = cmulc(sm[i1], w);
+            sm[i0] = cadd(a, b);
+            sm[i1] = csub(a, b);
         }
-        __syncthreads();
     }
+    __syncthreads();
+}
+
+// twM: W_M^n, n < M.  All threads of the CTA must call; ends with __syncthreads().
+__device__ __forceinline__ void cta_fft_forward(float2 *sm, int M, int s, const CtaTw &t, const float2 *__restrict__ twM)
+{
+    int st = 0;
+    for (; s - st >= 2; st += 2) dif_radix4_pass(sm, M, st, t);
+    if (s - st == 1) radix2_pass(sm, M, st, t, false);
     WarpFft<8> f;
     f.init(twM, M >> 8);
-    const int warp = tid >> 5, nwarps = nthreads >> 5;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int blk = warp; blk < (1 << s); blk += nwarps) {
         float2 *base = sm + (blk << 8);
         float2 v[8];
 #pragma unroll
-        for (int b = 0; b < 8; b++) v[b] = base[8 * f.lane + b];
+        for (int b = 0; b < 4; b++) {
+            const float4 q = *reinterpret_cast<const float4 *>(base + 8 * f.lane + 2 * b);
+            v[2 * b] = make_float2(q.x, q.y);
+            v[2 * b + 1] = make_float2(q.z, q.w);
+        }
         f.forward(v);
         __syncwarp();
 #pragma unroll
@@ -52,12 +138,11 @@ __device__ __forceinline__ void cta_fft_forward(float2 *sm, int M, int s, const 
     __syncthreads();
 }
 
-__device__ __forceinline__ void cta_fft_inverse(float2 *sm, int M, int s, const float2 *__restrict__ twM)
+__device__ __forceinline__ void cta_fft_inverse(float2 *sm, int M, int s, const CtaTw &t, const float2 *__restrict__ twM)
 {
-    const int tid = threadIdx.x, nthreads = blockDim.x;
     WarpFft<8> f;
     f.init(twM, M >> 8);
-    const int warp = tid >> 5, nwarps = nthreads >> 5;
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int blk = warp; blk < (1 << s); blk += nwarps) {
         float2 *base = sm + (blk << 8);
         float2 v[8];
@@ -66,22 +151,13 @@ __device__ __forceinline__ void cta_fft_inverse(float2 *sm, int M, int s, const 
         f.inverse(v);
         __syncwarp();
 #pragma unroll
-        for (int b = 0; b < 8; b++) base[8 * f.lane + b] = v[b];
+        for (int b = 0; b < 4; b++)
+            *reinterpret_cast<float4 *>(base + 8 * f.lane + 2 * b) = make_float4(v[2 * b].x, v[2 * b].y, v[2 * b + 1].x, v[2 * b + 1].y);
     }
     __syncthreads();
-    for (int st = s - 1; st >= 0; st--) {
-        const int lh = 31 - __clz(M) - 1 - st;
-        const int half = 1 << lh;
-        for (int j = tid; j < M / 2; j += nthreads) {
-            const int pos = j & (half - 1);
-            const int i0 = ((j >> lh) << (lh + 1)) | pos, i1 = i0 + half;
-            const float2 a = sm[i0];
-            const float2 b = cmulc(sm[i1], __ldg(&twM[pos << st]));
-            sm[i0] = cadd(a, b);
-            sm[i1] = csub(a, b);
-        }
-        __syncthreads();
-    }
+    int st = s;
+    if (s & 1) { st = s - 1; radix2_pass(sm, M, st, t, true); }
+    for (st -= 2; st >= 0; st -= 2) dit_radix4_pass(sm, M, st, t);
 }
 
 // real-FFT split of one bin (see WarpFft::split_r2c): z = Z[k], zp = Z[M-k], w = W_2M^k
@@ -99,8 +175,9 @@ __device__ __forceinline__ float2 c2r_bin(float2 y, float2 yp, float2 w)
 }
 
 // in place over the zpos layout: Z (M-point FFT of z[n] = w[2n] + j w[2n+1]) -> packed real spectrum
-__device__ __forceinline__ void cta_split_r2c(float2 *sm, int M, int s, const float2 *__restrict__ tw2M)
+__device__ __forceinline__ void cta_split_r2c(float2 *sm, int M, int s, const CtaTw &t)
 {
+#pragma unroll 2
     for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
         if (k == 0) {
             const float2 z = sm[0];
@@ -108,15 +185,17 @@ __device__ __forceinline__ void cta_split_r2c(float2 *sm, int M, int s, const fl
         } else {
             const int p0 = zpos(k, s), p1 = zpos(M - k, s);
             const float2 z = sm[p0], zp = sm[p1];
-            sm[p0] = r2c_bin(z, zp, __ldg(&tw2M[k]));
-            if (p1 != p0) sm[p1] = r2c_bin(zp, z, __ldg(&tw2M[M - k]));
+            const float2 w = tw_2m(t, k);
+            sm[p0] = r2c_bin(z, zp, w);
+            if (p1 != p0) sm[p1] = r2c_bin(zp, z, make_float2(-w.x, w.y));  // W_2M^(M-k) = -conj(W_2M^k)
         }
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void cta_split_c2r(float2 *sm, int M, int s, const float2 *__restrict__ tw2M)
+__device__ __forceinline__ void cta_split_c2r(float2 *sm, int M, int s, const CtaTw &t)
 {
+#pragma unroll 2
     for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
         if (k == 0) {
             const float2 y = sm[0];
@@ -124,8 +203,9 @@ __device__ __forceinline__ void cta_split_c2r(float2 *sm, int M, int s, const fl
         } else {
             const int p0 = zpos(k, s), p1 = zpos(M - k, s);
             const float2 y = sm[p0], yp = sm[p1];
-            sm[p0] = c2r_bin(y, yp, __ldg(&tw2M[k]));
-            if (p1 != p0) sm[p1] = c2r_bin(yp, y, __ldg(&tw2M[M - k]));
+            const float2 w = tw_2m(t, k);
+            sm[p0] = c2r_bin(y, yp, w);
+            if (p1 != p0) sm[p1] = c2r_bin(yp, y, make_float2(-w.x, w.y));
         }
     }
     __syncthreads();

@@ -516,41 +516,59 @@ struct InvArgs {
     Ctl *ctl;
     const float2 *twM, *tw2M;
     uint32_t n_split, n_in, n_out, acc_len;
+    uint32_t n_items;  // active instances * n_out
 };
 
 constexpr int kInvThreads = 128;
 
-template <int R>
+// PACKED: one warp per (instance, output), the warp sums the (few) partial spectra itself -- the
+// throughput schedule.  !PACKED: one CTA per item, all 128 threads sum the n_split partials through
+// shared memory before warp 0 transforms -- the latency schedule (n_split up to 32).
+template <int R, bool PACKED>
 __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
 {
     constexpr int B = 32 * R;
-    __shared__ __align__(16) float2 Ys[B];
-    const uint32_t item = blockIdx.x;
-    const uint32_t inst = item / a.n_out, o = item % a.n_out;
+    __shared__ __align__(16) float2 Ys[PACKED ? 2 : B];
     const int tid = threadIdx.x;
+    const uint32_t item = PACKED ? blockIdx.x * (kInvThreads / 32) + (tid >> 5) : blockIdx.x;
+    if (PACKED && item >= a.n_items) return;
+    const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const unsigned long long t = a.ctl->t_next - 1ull;
 
-    // --- sum the partial spectra of the MAC splits (fixed order) ---
-    for (int f4 = tid; f4 < B / 2; f4 += kInvThreads) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * B) + f4;
-        const size_t stride = (size_t)a.n_out * B / 2;
+    if constexpr (!PACKED) {
+        // --- sum the partial spectra of the MAC splits (fixed order) ---
+        for (int f4 = tid; f4 < B / 2; f4 += kInvThreads) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * B) + f4;
+            const size_t stride = (size_t)a.n_out * B / 2;
 #pragma unroll 4
-        for (uint32_t sp = 0; sp < a.n_split; sp++) {
-            const float4 v = src[sp * stride];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            for (uint32_t sp = 0; sp < a.n_split; sp++) {
+                const float4 v = src[sp * stride];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            reinterpret_cast<float4 *>(Ys)[f4] = s;
         }
-        reinterpret_cast<float4 *>(Ys)[f4] = s;
+        __syncthreads();
     }
-    __syncthreads();
 
-    if (tid < 32) {
-        const int lane = tid;
+    if (PACKED || tid < 32) {
+        const int lane = tid & 31;
         WarpFft<R> f;
         f.init(a.twM);
         float2 v[R];
+        if constexpr (PACKED) {
+            const float2 *src = a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * B;
 #pragma unroll
-        for (int d = 0; d < R; d++) v[d] = Ys[f.c + 32 * d];
+            for (int d = 0; d < R; d++) v[d] = src[f.c + 32 * d];
+            for (uint32_t sp = 1; sp < a.n_split; sp++) {
+                src += (size_t)a.n_out * B;
+#pragma unroll
+                for (int d = 0; d < R; d++) { const float2 q = src[f.c + 32 * d]; v[d].x += q.x; v[d].y += q.y; }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < R; d++) v[d] = Ys[f.c + 32 * d];
+        }
         f.split_c2r(v, a.tw2M);
         f.inverse(v);
         // overlap discard: keep time samples [B, 2B) = lanes 16..31; lane a holds output
@@ -604,14 +622,14 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             }
         }
     }
-    if (item == 0 && tid == 0) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
+    if (item == 0 && (tid & 31) == 0 && tid < 32) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
 }
 
 // ------------------------------------------------------------------------------------------
 // long tiers of the non-uniform partitioning (block S = 256 * 2^s_log, fired every m periods,
 // AFTER the period's output has been produced: k_inverse has already advanced ctl->t)
 // ------------------------------------------------------------------------------------------
-constexpr int kTierThreads = 256;
+constexpr int kTierThreads = 512;
 
 struct TierFwdArgs {
     const float *ring;    // [(item*nv + v)][ring_len]
@@ -627,6 +645,7 @@ struct TierFwdArgs {
 __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
+    __shared__ CtaTw tw;
     const uint32_t per = a.n_in * a.nv;
     const uint32_t inst = a.inst0 + (blockIdx.x / per) * a.inst_stride;
     const uint32_t item = inst * a.n_in + (blockIdx.x % per) / a.nv, v = blockIdx.x % a.nv;
@@ -637,10 +656,11 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const uint32_t mask = a.ring_len - 1;
     const float *ring = a.ring + (size_t)w * a.ring_len;
     const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
-    for (uint32_t n = threadIdx.x; n < a.S; n += kTierThreads) sm[n] = *reinterpret_cast<const float2 *>(ring + ((start + 2 * n) & mask));
-    __syncthreads();
-    cta_fft_forward(sm, (int)a.S, (int)a.s_log, a.twM);
-    cta_split_r2c(sm, (int)a.S, (int)a.s_log, a.tw2M);
+    for (uint32_t n = threadIdx.x; n < a.S / 2; n += kTierThreads)
+        *reinterpret_cast<float4 *>(sm + 2 * n) = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
+    cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
+    cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
+    cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     const unsigned long long n_fire = (tend + inst % a.m) / a.m;
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
@@ -660,6 +680,7 @@ struct TierInvArgs {
 __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
+    __shared__ CtaTw tw;
     const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
     const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = a.ctl->t;
@@ -670,9 +691,9 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
         for (uint32_t sp = 0; sp < a.n_split; sp++) { const float2 q = src[sp * stride]; y.x += q.x; y.y += q.y; }
         sm[zpos((int)k, (int)a.s_log)] = y;
     }
-    __syncthreads();
-    cta_split_c2r(sm, (int)a.S, (int)a.s_log, a.tw2M);
-    cta_fft_inverse(sm, (int)a.S, (int)a.s_log, a.twM);
+    cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
+    cta_split_c2r(sm, (int)a.S, (int)a.s_log, tw);
+    cta_fft_inverse(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     // z[n] = y[2n] + j y[2n+1]; keep y[S, 2S) = z[S/2, S): they belong to output times
     // [t_end*B - S + off, t_end*B + off)
     const uint32_t amask = a.acc_len - 1;
@@ -699,6 +720,7 @@ struct TierIrArgs {
 __global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
+    __shared__ CtaTw tw;
     const uint32_t o = blockIdx.x / a.P, k = blockIdx.x % a.P;
     const float *h = o == 0 ? a.h[0] : a.h[1];
     for (uint32_t n = threadIdx.x; n < a.S; n += kTierThreads) {
@@ -710,9 +732,9 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
         }
         sm[n] = make_float2(re, im);
     }
-    __syncthreads();
-    cta_fft_forward(sm, (int)a.S, (int)a.s_log, a.twM);
-    cta_split_r2c(sm, (int)a.S, (int)a.s_log, a.tw2M);
+    cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
+    cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
+    cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     float2 *dst = a.H + ((size_t)o * a.P + k) * a.S;
     for (uint32_t kk = threadIdx.x; kk < a.S; kk += kTierThreads) dst[kk] = sm[zpos((int)kk, (int)a.s_log)];
 }
