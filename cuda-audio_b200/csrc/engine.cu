@@ -101,6 +101,8 @@ uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l
 // period; tier j >= 1 has block S_j = m * period, covers IR frames [off, off + P*S) and runs after
 // the output of every m-th period has been produced (its result is first needed one period later
 // because off >= S).
+constexpr uint32_t kIoChunks = 4;
+
 struct Tier {
     uint32_t S = 0, m = 1, P = 0, off = 0, s_log = 0, bt = 0, tiles = 1, n_split = 1, Lring = 0;
     float2 *H = nullptr, *X = nullptr, *Ypart = nullptr, *tw = nullptr;
@@ -130,6 +132,8 @@ struct ca_engine {
     InParamDev *h_upload[2] = {nullptr, nullptr};
     cudaEvent_t upload_done[2] = {nullptr, nullptr};
     cudaEvent_t out_ready = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the chunked host pipeline
+    cudaEvent_t io_ev[2][kIoChunks + 1] = {};
     int upload_idx = 0;
     // parameters (host shadow)
     std::mutex par_mutex;
@@ -213,21 +217,23 @@ uint32_t tier_count(const ca_engine *e, const Tier &t, uint64_t tend)
     return e->n_active > r ? (e->n_active - r + t.m - 1) / t.m : 0u;
 }
 
-// tier 0: the period pipeline.  After it the output block is complete.
-int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile)
+// tier 0: the period pipeline for instances [i0, i1).  After the launch that covers the last
+// instance (last == true) the output block is complete and the device period counter advances.
+int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, uint32_t i0, uint32_t i1, bool last)
 {
     const Tier &t0 = e->tiers[0];
-    const uint32_t n_items = e->n_active * e->n_in;
+    const uint32_t n_items = (i1 - i0) * e->n_in;
     const uint32_t n_alloc = e->n_inst * e->n_in;
     FwdArgs fa{d_in, e->d_ring, t0.X, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
-               n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out};
+               n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in};
     MacArgs ma = mac_args(e, t0, 1u);
+    ma.inst0 = i0;
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
-               t0.n_split, e->n_in, e->n_out, e->acc_len, e->n_active * e->n_out};
+               t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u};
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     e->fft.fwd<<<(n_items * e->nv + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    t0.mac.fn<<<dim3(t0.n_split, t0.tiles, e->n_active), kMacThreads, t0.mac.smem, e->stream>>>(ma);
+    t0.mac.fn<<<dim3(t0.n_split, t0.tiles, i1 - i0), kMacThreads, t0.mac.smem, e->stream>>>(ma);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
     if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
     else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
@@ -303,13 +309,13 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
         auto it = e->graphs.find(0u);
         if (it == e->graphs.end()) {
             cudaGraphExec_t ge = nullptr;
-            rc = capture_graph(e, &ge, [&] { return launch_period(e, d_in, d_out, false); });
+            rc = capture_graph(e, &ge, [&] { return launch_period(e, d_in, d_out, false, 0, e->n_active, true); });
             if (rc) return rc;
             it = e->graphs.emplace(0u, ge).first;
         }
         CA_CUDA(cudaGraphLaunch(it->second, e->stream));
     } else {
-        rc = launch_period(e, d_in, d_out, profile);
+        rc = launch_period(e, d_in, d_out, profile, 0, e->n_active, true);
         if (rc) return rc;
     }
     e->launches += 3;
@@ -438,11 +444,15 @@ int ca_destroy(ca_engine *e)
     if (!e) return CA_OK;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->s_out) cudaStreamSynchronize(e->s_out);
     drop_graphs(e);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &row : e->tev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->upload_done) if (ev) cudaEventDestroy(ev);
     if (e->out_ready) cudaEventDestroy(e->out_ready);
+    for (auto &row : e->io_ev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+    if (e->s_in) cudaStreamDestroy(e->s_in);
+    if (e->s_out) cudaStreamDestroy(e->s_out);
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.tw); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl);
@@ -509,6 +519,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     for (auto &row : e->tev) for (auto &ev : row) CA_CUDA(cudaEventCreate(&ev));
     for (auto &ev : e->upload_done) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
+    CA_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CA_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (auto &row : e->io_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
     uint32_t s_max = e->B, reach = e->B;
@@ -778,16 +791,44 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     if (!e || !in || !out) return CA_ERR_INVALID;  // the reference silently returns on null ports (conv.cu:297)
     if (nframes != e->B) return CA_ERR_PERIOD;
     const double t0 = now_us();
-    const size_t in_bytes = (size_t)e->n_active * e->n_in * e->B * sizeof(float);
-    const size_t out_bytes = (size_t)e->n_active * e->n_out * e->B * sizeof(float);
+    const size_t in_stride = (size_t)e->n_in * e->B, out_stride = (size_t)e->n_out * e->B;  // floats per instance
+    const size_t in_bytes = e->n_active * in_stride * sizeof(float), out_bytes = e->n_active * out_stride * sizeof(float);
     const float *src = in;
     if (!is_pinned(e, in)) { memcpy(e->h_in, in, in_bytes); src = e->h_in; }
     float *dst = is_pinned(e, out) ? out : e->h_out;
-    CA_CUDA(cudaMemcpyAsync(e->d_in, src, in_bytes, cudaMemcpyHostToDevice, e->stream));
-    int rc = run_period(e, e->d_in, e->d_out);
-    if (rc) return rc;
-    CA_CUDA(cudaMemcpyAsync(dst, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
-    CA_CUDA(cudaEventRecord(e->out_ready, e->stream));
+    const bool graph = (e->cfg.flags & CA_FLAG_GRAPH) != 0, profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
+    // Large batches: cut the instances into chunks and pipeline H2D | kernels | D2H on three streams so
+    // the PCIe copies (2 KB per instance and direction) hide behind the kernels of the other chunks.
+    const uint32_t chunks = (graph || profile || e->n_active < 512) ? 1u : std::min<uint32_t>(kIoChunks, e->n_active / 256);
+    int rc = CA_OK;
+    if (chunks <= 1) {
+        CA_CUDA(cudaMemcpyAsync(e->d_in, src, in_bytes, cudaMemcpyHostToDevice, e->stream));
+        rc = run_period(e, e->d_in, e->d_out);
+        if (rc) return rc;
+        CA_CUDA(cudaMemcpyAsync(dst, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+        CA_CUDA(cudaEventRecord(e->out_ready, e->stream));
+    } else {
+        rc = flush_params(e);
+        if (rc) return rc;
+        // d_in / d_out are free: the previous call returned only after its D2H (hence every kernel of its
+        // period pipeline) had completed; the deferred tiers still running on e->stream touch neither.
+        for (uint32_t c = 0; c < chunks; c++) {
+            const uint32_t i0 = (uint32_t)((uint64_t)e->n_active * c / chunks), i1 = (uint32_t)((uint64_t)e->n_active * (c + 1) / chunks);
+            CA_CUDA(cudaMemcpyAsync(e->d_in + i0 * in_stride, src + i0 * in_stride, (i1 - i0) * in_stride * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
+            CA_CUDA(cudaEventRecord(e->io_ev[0][c], e->s_in));
+        }
+        for (uint32_t c = 0; c < chunks; c++) {
+            const uint32_t i0 = (uint32_t)((uint64_t)e->n_active * c / chunks), i1 = (uint32_t)((uint64_t)e->n_active * (c + 1) / chunks);
+            CA_CUDA(cudaStreamWaitEvent(e->stream, e->io_ev[0][c], 0));
+            rc = launch_period(e, e->d_in, e->d_out, false, i0, i1, c + 1 == chunks);
+            if (rc) return rc;
+            CA_CUDA(cudaEventRecord(e->io_ev[1][c], e->stream));
+            CA_CUDA(cudaStreamWaitEvent(e->s_out, e->io_ev[1][c], 0));
+            CA_CUDA(cudaMemcpyAsync(dst + i0 * out_stride, e->d_out + i0 * out_stride, (i1 - i0) * out_stride * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+        }
+        e->launches += 3 * chunks;
+        CA_CUDA(cudaEventRecord(e->out_ready, e->s_out));
+    }
     rc = run_deferred(e);  // long tiers keep the GPU busy while the host already has its output
     if (rc) return rc;
     CA_CUDA(cudaEventSynchronize(e->out_ready));

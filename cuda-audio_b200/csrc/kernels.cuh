@@ -121,6 +121,7 @@ struct FwdArgs {
     uint32_t n_items;  // active instances * n_in
     uint32_t n_items_alloc;  // stride between the two state buffers
     uint32_t n_in, nv, Lring, ring_len, ring_out;
+    uint32_t item0;    // first (instance, input) item of this launch (chunked host pipeline)
 };
 
 template <int R>
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
     const int lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
     if (w >= a.n_items * a.nv) return;
-    const uint32_t item = w / a.nv, v = w % a.nv;
+    const uint32_t item = a.item0 + w / a.nv, v = w % a.nv;
     const unsigned long long t = a.ctl->t;
     if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
 
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
 
     const uint32_t mask = a.ring_len - 1;
-    float *ring = a.ring + (size_t)w * a.ring_len;
+    float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
     if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
         for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
 
     const unsigned long long n_fire = t + 1ull;  // tier 0 fires every period
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);  // ring runs backwards
-    float2 *dst = a.X + ((size_t)w * a.Lring + slot) * B;
+    float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot) * B;
 #pragma unroll
     for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
 }
@@ -516,7 +517,9 @@ struct InvArgs {
     Ctl *ctl;
     const float2 *twM, *tw2M;
     uint32_t n_split, n_in, n_out, acc_len;
-    uint32_t n_items;  // active instances * n_out
+    uint32_t n_items;  // (instance, output) items of this launch
+    uint32_t item0;    // first item of this launch
+    uint32_t advance;  // 1: this launch completes the period (advances ctl->t)
 };
 
 constexpr int kInvThreads = 128;
@@ -530,8 +533,9 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
     constexpr int B = 32 * R;
     __shared__ __align__(16) float2 Ys[PACKED ? 2 : B];
     const int tid = threadIdx.x;
-    const uint32_t item = PACKED ? blockIdx.x * (kInvThreads / 32) + (tid >> 5) : blockIdx.x;
-    if (PACKED && item >= a.n_items) return;
+    const uint32_t local = PACKED ? blockIdx.x * (kInvThreads / 32) + (tid >> 5) : blockIdx.x;
+    if (PACKED && local >= a.n_items) return;
+    const uint32_t item = a.item0 + local;
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const unsigned long long t = a.ctl->t_next - 1ull;
 
@@ -622,7 +626,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             }
         }
     }
-    if (item == 0 && (tid & 31) == 0 && tid < 32) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
+    if (a.advance && local == 0 && tid == 0) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
 }
 
 // ------------------------------------------------------------------------------------------
