@@ -520,6 +520,7 @@ struct InvArgs {
     uint32_t n_items;  // (instance, output) items of this launch
     uint32_t item0;    // first item of this launch
     uint32_t advance;  // 1: this launch completes the period (advances ctl->t)
+    uint32_t raw_wet;  // 1: store the unclamped wet block only (partition-range shards: clamp + dry after the reduce)
 };
 
 constexpr int kInvThreads = 128;
@@ -591,7 +592,9 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             const float *x1 = x0 + B;
             float *accp = nullptr;
             if (a.accring) accp = a.accring + (size_t)item * a.acc_len + (uint32_t)((t * (unsigned long long)B) & (a.acc_len - 1)) + n0;
-            auto clampf = [](float w) { return fminf(fmaxf(w, -1.0f), 1.0f); };  // conv.cu:98
+            const bool raw = a.raw_wet != 0;
+            if (raw) { dg[0] = 0.f; dg[1] = 0.f; }
+            auto clampf = [raw](float w) { return raw ? w : fminf(fmaxf(w, -1.0f), 1.0f); };  // conv.cu:98
             if constexpr (R == 1) {
                 float2 w = v[0];
                 if (accp) { const float2 q = *reinterpret_cast<const float2 *>(accp); w.x += q.x; w.y += q.y; *reinterpret_cast<float2 *>(accp) = make_float2(0.f, 0.f); }

@@ -17,7 +17,7 @@ ROOT = os.path.normpath(os.path.join(_PKG, "..", ".."))          # cuda-audio_b2
 LIB_PATH = os.path.join(ROOT, "libcuda_audio_b200.so")
 
 CA_MAX_TIERS = 4
-FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE = 1, 2, 4, 8
+FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",

@@ -56,7 +56,9 @@ enum ca_flags {
     CA_FLAG_GRAPH = 1u << 0,      /* replay one CUDA graph per period instead of 3 launches   */
     CA_FLAG_STREAMING = 1u << 1,  /* working set >> L2: evict-first hints on spectra loads     */
     CA_FLAG_L2_PERSIST = 1u << 2, /* pin IR spectra + FDL in L2 (access-policy window)         */
-    CA_FLAG_PROFILE = 1u << 3     /* record CUDA events around every kernel (ca_get_stats)     */
+    CA_FLAG_PROFILE = 1u << 3,    /* record CUDA events around every kernel (ca_get_stats)     */
+    CA_FLAG_RAW_WET = 1u << 4     /* output the unclamped wet signal only: for partition-range
+                                   * shards whose partial outputs are summed before clamp + dry */
 };
 
 typedef struct ca_engine ca_engine;

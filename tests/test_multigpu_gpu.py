@@ -1,0 +1,70 @@
+"""Multi-GPU paths on real GPUs (skipped unless the box has >= 2): IR partition-range split with an
+NCCL reduce of the partial outputs (BASELINE configs[4]), one process per GPU via torchrun."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.skipif(n_gpus() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ir_split_nccl_reduce(world):
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                          "--master-port", str(free_port()), os.path.join(ROOT, "tests", "mp_irsplit_worker.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("IRSPLIT_RESULT ")][-1]
+    res = json.loads(line.split(" ", 1)[1])
+    assert res["world"] == world
+    assert res["err_fp64"] < 5e-6, res
+    assert res["err_single_gpu"] < 1e-6, res      # different summation order only
+    assert res["clipped"] > 0                      # clamp acts on the reduced sum
+
+
+def test_raw_wet_shards_on_one_gpu_clamp_after_sum():
+    """Collective-free check of the same math on one GPU: shards output raw wet blocks
+    (CA_FLAG_RAW_WET), the clamp is applied to their sum."""
+    import numpy as np
+
+    import cuda_audio_b200 as m
+    from oracle import oracle as O
+    fs, B, L = 48000, 128, 128 * 30
+    irs = [[3.0 * O.synth_ir(L, fs, 20 + 2 * i + o) for o in range(2)] for i in range(2)]
+    x = np.stack([O.synth_audio(B * 80, 30 + i, rms=0.3) for i in range(2)])
+    total = np.zeros((2, B * 80))
+    for pb, pc in ((0, 9), (9, 11), (20, 10)):
+        with m.Engine(period=B, max_ir_frames=L, part_begin=pb, part_count=pc, flags=m.FLAG_RAW_WET) as e:
+            for i in range(2):
+                e.load_ir(i, irs[i][0], irs[i][1])
+                e.set_params(0, i, select=i, wet=1.0, dry=0.7)     # dry must NOT appear in a raw-wet shard
+                e.set_glide(0, i, 1.0)
+            total += e.render(x[None])[0]
+    truth = O.engine_truth(x, irs, [dict(wet=1.0, dry=0.0)] * 2)
+    wet = np.stack([O.fft_conv(x[0], irs[0][o]) + O.fft_conv(x[1], irs[1][o]) for o in range(2)])
+    assert (np.abs(wet) > 1.0).sum() > 100
+    assert O.rel_l2(np.clip(total, -1, 1), truth) < 5e-6
+    assert O.rel_l2(total, wet) < 5e-6                                 # unclamped, no dry
