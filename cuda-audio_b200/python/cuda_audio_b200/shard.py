@@ -134,8 +134,11 @@ class TorchEngine:
         self.e.set_glide(instance, inp, g)
 
     def process_tensor(self, x):
+        # x was produced, and the previous block's y is still being consumed (reduce, clamp, dry mix),
+        # on torch's streams; the engine runs on its own non-blocking stream: order the two explicitly.
+        self.torch.cuda.current_stream(self.dev).synchronize()
         self.e.process_device(x.data_ptr(), self.y.data_ptr())
-        self.e.sync()          # the reduce runs on torch's stream
+        self.e.sync()
         return self.y
 
     def close(self):
