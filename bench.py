@@ -353,6 +353,64 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# configs[4]: one 60 s IR split by partition range across the GPUs, NCCL reduce per period
+# ------------------------------------------------------------------------------------------------
+def run_irsplit(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cuda_audio_b200 as ca
+    from cuda_audio_b200 import shard
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = int(args.irsplit_seconds * FS)
+    cfg = shard.IrSplitConfig(period=B, ir_frames=L, sample_rate=FS)
+    grp = shard.IrSplitGroup(cfg, lambda pb, pc: shard.TorchEngine(cfg, local_rank, pb, pc, flags=ca.FLAG_GRAPH), dist=dist, rank=rank, world=world)
+    rng = np.random.default_rng(1000)
+    env = np.exp(-6.91 * np.arange(L) / (0.8 * L)).astype(np.float32)
+    for i in range(2):
+        h = rng.standard_normal((2, L)).astype(np.float32) * env
+        h /= np.sqrt((h ** 2).sum(axis=1, keepdims=True))
+        grp.load_ir(i, h[0], h[1])
+        grp.set_params(i, select=i)
+        grp.set_glide(i, 0.5)
+    g = torch.Generator(device=dev)
+    g.manual_seed(2000)
+    x = (torch.randn(1, 2, B, device=dev, generator=g) * 0.1).clamp_(-0.9, 0.9)
+    zeros = lambda a: torch.zeros(1, 2, B, device=dev)  # noqa: E731
+    P = (L + B - 1) // B
+    for _ in range(P + 50):                     # steady state: every FDL slot of every shard filled
+        grp.process(x, zeros_like=zeros)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        y = grp.process(x, zeros_like=zeros)
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e6)
+    wall.sort()
+    if rank == 0:
+        st = grp.engine.e.stats()
+        print(json.dumps({"mode": "irsplit", "metric": "per-period latency (us), one IR split by partition range + NCCL reduce", "unit": "us",
+                          "value": round(wall[len(wall) // 2], 1), "p99_us": round(wall[min(len(wall) - 1, int(0.99 * len(wall)))], 1),
+                          "higher_is_better": False, "n_gpus": world, "steps": args.steps, "deadline_us": round(DEADLINE_MS * 1e3, 1),
+                          "config": {"workload": f"true-stereo 48 kHz, 256-frame period, {args.irsplit_seconds:g} s IR (P={P}) split by partition range",
+                                     "partitions_per_rank": [c for _, c in grp.plan], "collective": "reduce(sum) of 2 x 256 fp32 per period" if world > 1 else "none",
+                                     "rank0_mac_bytes": int(st.mac_bytes)},
+                          "output_rms": float(y.pow(2).mean().sqrt())}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port (fp32 partitioned overlap-save, OpenMP over instances)
 # ------------------------------------------------------------------------------------------------
 def cpu_port_baseline(seconds=10.0, inst_per_thread=4):
@@ -467,6 +525,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="channels", choices=["channels", "irsplit"],
+                    help="channels: the headline (independent instances, no collective); irsplit: configs[4], one long IR split across the GPUs")
+    ap.add_argument("--irsplit-seconds", type=float, default=60.0)
     ap.add_argument("--instances", type=int, default=10240, help="instances per GPU in the throughput run")
     ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
     ap.add_argument("--uniform-instances", type=int, default=2048)
@@ -483,6 +544,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "irsplit":
+        run_irsplit(args)
     else:
         run_ours(args)
 
