@@ -537,8 +537,11 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         // (latency schedule), 1 when the batch alone fills the machine.
         uint32_t split = j == 0 ? cfg->mac_split : 0;
         if (!split) {
+            // few instances: cut the row list so that ~2 CTAs per SM each stream >= 256 KB
             const uint64_t ctas = (uint64_t)e->n_inst * t.tiles;
-            split = ctas >= (uint64_t)2 * sms ? 1u : (uint32_t)std::min<uint64_t>(32, (2 * (uint64_t)sms + ctas - 1) / ctas);
+            const uint64_t bytes = (uint64_t)8 * t.S * t.P * (e->n_in * e->n_out + e->n_in) * e->n_inst;
+            const uint64_t want = std::min<uint64_t>(2 * (uint64_t)sms, std::max<uint64_t>(1, bytes / (256u << 10)));
+            split = ctas >= want ? 1u : (uint32_t)std::min<uint64_t>(256, (want + ctas - 1) / ctas);
         }
         const uint32_t rows = t.P * e->n_in;  // steady state: one voice per input
         t.n_split = std::max<uint32_t>(1, std::min(split, std::max<uint32_t>(1, rows / (uint32_t)t.mac.kc)));
