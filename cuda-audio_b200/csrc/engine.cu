@@ -143,7 +143,7 @@ struct ca_engine {
     std::vector<uint8_t> ir_loaded;
     FftFns fft{};
     // graphs: [0] = the period pipeline (tier 0), [mask] = the deferred tiers that fire together
-    std::map<uint32_t, cudaGraphExec_t> graphs;
+    std::map<uint64_t, cudaGraphExec_t> graphs;
     const float *g_in = nullptr;
     float *g_out = nullptr;
     uint32_t g_active = 0;
@@ -275,6 +275,18 @@ uint32_t tiers_firing(const ca_engine *e, uint64_t tend)
     return n;
 }
 
+// graph key of the deferred launch pattern at t_end: which tiers fire and for which residue class
+// (key 0 is the period pipeline)
+uint64_t tiers_key(const ca_engine *e, uint64_t tend)
+{
+    uint64_t key = 1;
+    for (size_t j = 1; j < e->tiers.size(); j++) {
+        const Tier &t = e->tiers[j];
+        key = key * (t.m + 1) + (tier_count(e, t, tend) ? tier_residue(t, tend) + 1 : 0);
+    }
+    return key;
+}
+
 template <class F>
 int capture_graph(ca_engine *e, cudaGraphExec_t *out, F body)
 {
@@ -306,12 +318,12 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
             drop_graphs(e);
             e->g_in = d_in; e->g_out = d_out; e->g_active = e->n_active;
         }
-        auto it = e->graphs.find(0u);
+        auto it = e->graphs.find((uint64_t)0);
         if (it == e->graphs.end()) {
             cudaGraphExec_t ge = nullptr;
             rc = capture_graph(e, &ge, [&] { return launch_period(e, d_in, d_out, false, 0, e->n_active, true); });
             if (rc) return rc;
-            it = e->graphs.emplace(0u, ge).first;
+            it = e->graphs.emplace((uint64_t)0, ge).first;
         }
         CA_CUDA(cudaGraphLaunch(it->second, e->stream));
     } else {
@@ -331,8 +343,7 @@ int run_deferred(ca_engine *e)
     int rc = CA_OK;
     if (firing) {
         if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
-            // the launch pattern (which instances of which tier) repeats with the longest tier's period
-            const uint32_t key = 1u + (uint32_t)(tend % e->tiers.back().m);
+            const uint64_t key = tiers_key(e, tend);
             auto it = e->graphs.find(key);
             if (it == e->graphs.end()) {
                 cudaGraphExec_t ge = nullptr;
@@ -364,6 +375,33 @@ int run_deferred(ca_engine *e)
                 }
         e->prof_n++;
     }
+    return CA_OK;
+}
+
+// Capture + instantiate every graph ca_process() will need (period pipeline over the engine's own
+// staging buffers, and one graph per deferred-tier launch pattern) so that no capture or
+// instantiation ever happens inside a real-time period.
+int prewarm_graphs(ca_engine *e)
+{
+    if (!(e->cfg.flags & CA_FLAG_GRAPH) || (e->cfg.flags & CA_FLAG_PROFILE)) return CA_OK;
+    drop_graphs(e);
+    e->g_in = e->d_in; e->g_out = e->d_out; e->g_active = e->n_active;
+    cudaGraphExec_t ge = nullptr;
+    int rc = capture_graph(e, &ge, [&] { return launch_period(e, e->d_in, e->d_out, false, 0, e->n_active, true); });
+    if (rc) return rc;
+    e->graphs.emplace((uint64_t)0, ge);
+    const uint64_t cycle = e->tiers.back().m;
+    for (uint64_t tend = 1; tend <= cycle && e->tiers.size() > 1; tend++) {
+        if (!tiers_firing(e, tend)) continue;
+        const uint64_t key = tiers_key(e, tend);
+        if (e->graphs.count(key)) continue;
+        ge = nullptr;
+        rc = capture_graph(e, &ge, [&] { return launch_tiers(e, tend, false); });
+        if (rc) return rc;
+        e->graphs.emplace(key, ge);
+    }
+    for (auto &kv : e->graphs) cudaGraphUpload(kv.second, e->stream);
+    CA_CUDA(cudaStreamSynchronize(e->stream));
     return CA_OK;
 }
 
@@ -640,7 +678,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         }
     }
     CA_CUDA(cudaStreamSynchronize(e->stream));
-    return CA_OK;
+    return prewarm_graphs(e);
 }
 
 int ca_create(const ca_config *cfg, ca_engine **out)
@@ -772,8 +810,10 @@ int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g)
 int ca_set_active(ca_engine *e, uint32_t n)
 {
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
+    if (n == e->n_active) return CA_OK;
+    CA_CUDA(cudaStreamSynchronize(e->stream));
     e->n_active = n;
-    return CA_OK;
+    return prewarm_graphs(e);  // not a real-time call: rebuild the graphs for the new batch size now
 }
 
 int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nframes)
