@@ -61,6 +61,8 @@ MacVariant mac_pick_v(int variant)
     case 3: return mac_variant<BT, NOUT, 4, 2>();   //  96 KB, longer stages
     case 4: return mac_variant<BT, NOUT, 1, 4>();   //  48 KB: 4 CTAs / SM
     case 5: return mac_variant<BT, NOUT, 2, 6>();   // 144 KB: 1 CTA / SM, deep
+    case 6: return mac_variant<BT, NOUT, 1, 3>();   //  36 KB: 6 CTAs / SM
+    case 7: return mac_variant<BT, NOUT, 1, 2>();   //  24 KB: 9 CTAs / SM
     default: return mac_variant<BT, NOUT, 2, 4>();  //  96 KB: 2 CTAs / SM (measured best)
     }
 }

@@ -350,16 +350,17 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
     const uint32_t phase = inst % a.m;
     const unsigned long long n_fire = (tend + phase) / a.m;
 
-    if (tid == 0) {
+    // --- set-up, spread over three warps so the dependent global loads overlap ---
+    if (tid == 32) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMacConsumers / 32); }
         mbar_fence_init();
-        uint32_t acc = 0;
-        for (uint32_t s = 0; s < ns; s++) {
-            const uint32_t i = s / a.nv, v = s % a.nv;
+    } else if (warp == 0) {
+        // lane s: rows of stream s = (input s / nv, voice s % nv); exclusive prefix sum by shuffles
+        uint32_t nk = 0, slot = 0;
+        if ((uint32_t)lane < ns) {
+            const uint32_t i = lane / a.nv, v = lane % a.nv;
             const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + inst * a.n_in + i];
-            s_rowstart[s] = acc;
-            uint32_t nk = 0, slot = 0;
             if ((st.active >> v) & 1u) {
                 // partition k reads the block fired at index n_fire - k_off - k; it is valid when that
                 // block was built after the voice's (re)start: fire * m - 1 >= start
@@ -368,12 +369,22 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
                 nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
                 slot = st.slot[v];
             }
-            s_slot[s] = slot;
-            acc += nk;
         }
-        for (uint32_t s = ns; s <= kMaxStreams; s++) s_rowstart[s] = acc;
-        for (uint32_t i = 0; i < 2; i++)
-            for (int o = 0; o < NOUT; o++) s_pan[i][o] = pan_gain(a.par[inst * a.n_in + min(i, a.n_in - 1)].panWet, o, NOUT);
+        uint32_t incl = nk;
+#pragma unroll
+        for (int d = 1; d < kMaxStreams; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane <= kMaxStreams) {
+            const uint32_t total_rows = __shfl_sync(kFull, incl, kMaxStreams - 1);
+            if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; }
+            else s_rowstart[kMaxStreams] = total_rows;
+        }
+    } else if (warp == 2 && lane < 2 * NOUT) {
+        const uint32_t i = lane / NOUT;
+        const int o = lane % NOUT;
+        s_pan[i][o] = pan_gain(a.par[inst * a.n_in + min(i, a.n_in - 1)].panWet, o, NOUT);
     }
     __syncthreads();
 
