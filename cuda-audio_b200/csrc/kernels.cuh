@@ -376,11 +376,9 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
             const uint32_t up = __shfl_up_sync(kFull, incl, d);
             if (lane >= d) incl += up;
         }
-        if (lane <= kMaxStreams) {
-            const uint32_t total_rows = __shfl_sync(kFull, incl, kMaxStreams - 1);
-            if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; }
-            else s_rowstart[kMaxStreams] = total_rows;
-        }
+        const uint32_t total_rows = __shfl_sync(kFull, incl, kMaxStreams - 1);  // all 32 lanes take part
+        if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; }
+        else if (lane == kMaxStreams) s_rowstart[kMaxStreams] = total_rows;
     } else if (warp == 2 && lane < 2 * NOUT) {
         const uint32_t i = lane / NOUT;
         const int o = lane % NOUT;
