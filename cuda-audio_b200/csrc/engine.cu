@@ -549,7 +549,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     int rc = plan_tiers(cfg, e);
     if (rc) return rc;
     e->fft = fft_pick((int)e->R);
-    int variant = 1;
+    int variant = -1;  // -1: per tier by rows per CTA (measured: short row lists want many small CTAs per SM)
     if (const char *v = getenv("CA_MAC_VARIANT")) variant = atoi(v);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -571,7 +571,10 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
         t.bt = std::min<uint32_t>(t.S, 256);
         t.tiles = t.S / t.bt;
-        t.mac = mac_pick((int)t.bt, (int)e->n_out, variant);
+        // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /
+        // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 48 KB / 4 CTAs per SM
+        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 4 : 1);
+        t.mac = mac_pick((int)t.bt, (int)e->n_out, tier_variant);
         CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
         // split of the row list per instance: enough CTAs to cover the SMs when few instances run
         // (latency schedule), 1 when the batch alone fills the machine.
