@@ -23,7 +23,8 @@ n = torch.arange(L, device=dev, dtype=torch.float32)
 env = torch.exp(-6.91 * n / (0.8 * L))
 flags = ca.FLAG_PROFILE | (ca.FLAG_STREAMING if K >= 16 else 0)
 t0 = time.time()
-e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split, tiers=tiers, max_voices=nvoices)
+e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split, tiers=tiers, max_voices=nvoices,
+              tier_growth=int(os.environ.get('CA_TIER_GROWTH', '0')), tier_max_block=int(os.environ.get('CA_TIER_MAXBLOCK', '0')))
 g = torch.Generator(device=dev)
 for s in range(2 * K):
     g.manual_seed(1000 + s)
@@ -50,7 +51,7 @@ e.sync()
 dt = (time.time() - t0) / periods
 st = e.stats()
 gbs = st.mac_bytes / (st.mac_us * 1e-6) / 1e9
-print(f"tiers={list(st.tier_block[:st.n_tiers])}x{list(st.tier_parts[:st.n_tiers])} dev_bytes={st.device_bytes/1e9:.1f}GB tiers_us={st.tiers_us:.1f} p50={st.p50_us:.0f} p99={st.p99_us:.0f} max={st.max_us:.0f}")
+print(f"tiers={list(st.tier_block[:st.n_tiers])}x{list(st.tier_parts[:st.n_tiers])} dev_bytes={st.device_bytes/1e9:.1f}GB total={st.total_us:.1f} fwd0={st.fwd_us:.1f} mac0={st.mac_us:.1f} inv0={st.inv_us:.1f} tfwd={st.tier_fwd_us:.1f} tmac={st.tier_mac_us:.1f} tinv={st.tier_inv_us:.1f} bytes/period={st.mac_bytes_amortized/1e9:.2f}GB")
 print(f"variant={os.environ.get('CA_MAC_VARIANT', '1')} K={K} split={st.mac_split} fwd={st.fwd_us:.1f}us mac={st.mac_us:.1f}us inv={st.inv_us:.1f}us "
       f"wall/period={dt * 1e6:.1f}us MAC {gbs:.0f} GB/s ({gbs / 6460.2:.3f} of measured HBM) "
       f"rt_channels={K * (B / fs) / (st.total_us * 1e-6):.0f} y_rms={float(y.pow(2).mean().sqrt()):.4f}", flush=True)
