@@ -254,16 +254,17 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         e->tev_used[j] = profile && count;
         if (!count) continue;
         const uint32_t smem = t.S * sizeof(float2);
+        const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], e->stream));
-        k_tier_forward<<<count * e->n_in * e->nv, kTierThreads, smem, e->stream>>>(fa);
+        k_tier_forward<<<count * e->n_in * e->nv, threads, smem, e->stream>>>(fa);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], e->stream));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
         t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, e->stream>>>(ma);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], e->stream));
         TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-        k_tier_inverse<<<count * e->n_out, kTierThreads, smem, e->stream>>>(ia);
+        k_tier_inverse<<<count * e->n_out, threads, smem, e->stream>>>(ia);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], e->stream));
     }
     CA_CUDA(cudaGetLastError());
@@ -737,7 +738,7 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
             a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
             a.H = H; a.twM = t.tw; a.tw2M = t.tw + t.S;
             a.frames = frames; a.P = t.P; a.n_out = e->n_out; a.frame_off = t.off; a.S = t.S; a.s_log = t.s_log; a.scale = scale;
-            k_tier_ir<<<e->n_out * t.P, kTierThreads, t.S * sizeof(float2), e->stream>>>(a);
+            k_tier_ir<<<e->n_out * t.P, std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8)), t.S * sizeof(float2), e->stream>>>(a);
         }
         e->launches += 1;
     }

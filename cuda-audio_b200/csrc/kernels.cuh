@@ -583,57 +583,63 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
 #pragma unroll
             for (int d = 0; d < R; d++) v[d] = Ys[f.c + 32 * d];
         }
-        f.split_c2r(v, a.tw2M);
-        f.inverse(v);
-        // overlap discard: keep time samples [B, 2B) = lanes 16..31; lane a holds output
-        // samples [2R (a-16), 2R (a-16) + 2R)
+        // overlap discard: only time samples [B, 2B) are kept = lanes 16..31; lane a holds output samples
+        // [2R (a-16), 2R (a-16) + 2R).  Everything the epilogue needs is fetched BEFORE the transform so
+        // the loads overlap the FFT's shuffle chain.
+        constexpr int NV4 = R >= 2 ? R / 2 : 1;
+        float4 accv[NV4], xa[NV4], xb[NV4];
+        float dg[2] = {0.f, 0.f};
+        const int n0 = 2 * R * ((lane & 15));
+        float *dst = a.out + ((size_t)inst * a.n_out + o) * B + n0;
+        float *accp = nullptr;
+        const bool raw = a.raw_wet != 0;
         if (lane >= 16) {
-            float dg[2];
-            {   // dry gain per input: dry * panDry * level, conv.cu:418-427
+            if (!raw) {  // dry gain per input: dry * panDry * level, conv.cu:418-427
                 const InParamDev p0 = a.par[inst * a.n_in];
                 const InParamDev p1 = a.par[inst * a.n_in + (a.n_in - 1)];
                 dg[0] = p0.dry * pan_gain(p0.panDry, (int)o, (int)a.n_out) * p0.level;
-                dg[1] = p1.dry * pan_gain(p1.panDry, (int)o, (int)a.n_out) * p1.level;
+                dg[1] = a.n_in > 1 ? p1.dry * pan_gain(p1.panDry, (int)o, (int)a.n_out) * p1.level : 0.f;
             }
-            const int n0 = 2 * R * (lane - 16);
-            float *dst = a.out + ((size_t)inst * a.n_out + o) * B + n0;
             const float *x0 = a.in + ((size_t)inst * a.n_in) * B + n0;
-            const float *x1 = x0 + B;
-            float *accp = nullptr;
+            const float *x1 = x0 + (a.n_in > 1 ? B : 0);
             if (a.accring) accp = a.accring + (size_t)item * a.acc_len + (uint32_t)((t * (unsigned long long)B) & (a.acc_len - 1)) + n0;
-            const bool raw = a.raw_wet != 0;
-            if (raw) { dg[0] = 0.f; dg[1] = 0.f; }
-            auto clampf = [raw](float w) { return raw ? w : fminf(fmaxf(w, -1.0f), 1.0f); };  // conv.cu:98
             if constexpr (R == 1) {
-                float2 w = v[0];
-                if (accp) { const float2 q = *reinterpret_cast<const float2 *>(accp); w.x += q.x; w.y += q.y; *reinterpret_cast<float2 *>(accp) = make_float2(0.f, 0.f); }
-                float2 y = make_float2(clampf(w.x), clampf(w.y));
-                const float2 xa = *reinterpret_cast<const float2 *>(x0);
-                y.x = fmaf(dg[0], xa.x, y.x); y.y = fmaf(dg[0], xa.y, y.y);
-                if (a.n_in > 1) {
-                    const float2 xb = *reinterpret_cast<const float2 *>(x1);
-                    y.x = fmaf(dg[1], xb.x, y.x); y.y = fmaf(dg[1], xb.y, y.y);
-                }
-                *reinterpret_cast<float2 *>(dst) = y;
+                const float2 q0 = *reinterpret_cast<const float2 *>(x0), q1 = *reinterpret_cast<const float2 *>(x1);
+                xa[0] = make_float4(q0.x, q0.y, 0.f, 0.f);
+                xb[0] = make_float4(q1.x, q1.y, 0.f, 0.f);
+                accv[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (accp) { const float2 q = *reinterpret_cast<const float2 *>(accp); accv[0].x = q.x; accv[0].y = q.y; }
             } else {
 #pragma unroll
-                for (int j = 0; j < R / 2; j++) {
-                    float4 w = make_float4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
-                    if (accp) {  // contributions of the long (deferred) tiers to this block; consume and clear
-                        const float4 q = *reinterpret_cast<const float4 *>(accp + 4 * j);
-                        w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w;
-                        *reinterpret_cast<float4 *>(accp + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    float4 y = make_float4(clampf(w.x), clampf(w.y), clampf(w.z), clampf(w.w));
-                    const float4 xa = *reinterpret_cast<const float4 *>(x0 + 4 * j);
-                    y.x = fmaf(dg[0], xa.x, y.x); y.y = fmaf(dg[0], xa.y, y.y);
-                    y.z = fmaf(dg[0], xa.z, y.z); y.w = fmaf(dg[0], xa.w, y.w);
-                    if (a.n_in > 1) {
-                        const float4 xb = *reinterpret_cast<const float4 *>(x1 + 4 * j);
-                        y.x = fmaf(dg[1], xb.x, y.x); y.y = fmaf(dg[1], xb.y, y.y);
-                        y.z = fmaf(dg[1], xb.z, y.z); y.w = fmaf(dg[1], xb.w, y.w);
-                    }
+                for (int j = 0; j < NV4; j++) {
+                    xa[j] = *reinterpret_cast<const float4 *>(x0 + 4 * j);
+                    xb[j] = *reinterpret_cast<const float4 *>(x1 + 4 * j);
+                    accv[j] = accp ? *reinterpret_cast<const float4 *>(accp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        f.split_c2r(v, a.tw2M);
+        f.inverse(v);
+        if (lane >= 16) {
+            auto clampf = [raw](float w) { return raw ? w : fminf(fmaxf(w, -1.0f), 1.0f); };  // conv.cu:98
+            if constexpr (R == 1) {
+                float2 y = make_float2(clampf(v[0].x + accv[0].x), clampf(v[0].y + accv[0].y));
+                y.x = fmaf(dg[0], xa[0].x, fmaf(dg[1], xb[0].x, y.x));
+                y.y = fmaf(dg[0], xa[0].y, fmaf(dg[1], xb[0].y, y.y));
+                *reinterpret_cast<float2 *>(dst) = y;
+                if (accp) *reinterpret_cast<float2 *>(accp) = make_float2(0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV4; j++) {
+                    // wet = this period's tier-0 block + what the long (deferred) tiers left for it
+                    float4 y = make_float4(clampf(v[2 * j].x + accv[j].x), clampf(v[2 * j].y + accv[j].y),
+                                           clampf(v[2 * j + 1].x + accv[j].z), clampf(v[2 * j + 1].y + accv[j].w));
+                    y.x = fmaf(dg[0], xa[j].x, fmaf(dg[1], xb[j].x, y.x));
+                    y.y = fmaf(dg[0], xa[j].y, fmaf(dg[1], xb[j].y, y.y));
+                    y.z = fmaf(dg[0], xa[j].z, fmaf(dg[1], xb[j].z, y.z));
+                    y.w = fmaf(dg[0], xa[j].w, fmaf(dg[1], xb[j].w, y.w));
                     *reinterpret_cast<float4 *>(dst + 4 * j) = y;
+                    if (accp) *reinterpret_cast<float4 *>(accp + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);  // consumed
                 }
             }
         }
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
 // long tiers of the non-uniform partitioning (block S = 256 * 2^s_log, fired every m periods,
 // AFTER the period's output has been produced: k_inverse has already advanced ctl->t)
 // ------------------------------------------------------------------------------------------
-constexpr int kTierThreads = 512;
+constexpr int kTierThreads = 512;  // launch bound; the host launches M/8 threads clamped to [128, 512]
 
 struct TierFwdArgs {
     const float *ring;    // [(item*nv + v)][ring_len]
@@ -672,7 +678,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const uint32_t mask = a.ring_len - 1;
     const float *ring = a.ring + (size_t)w * a.ring_len;
     const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
-    for (uint32_t n = threadIdx.x; n < a.S / 2; n += kTierThreads)
+    for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x)
         *reinterpret_cast<float4 *>(sm + 2 * n) = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const unsigned long long n_fire = (tend + inst % a.m) / a.m;
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
-    for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) dst[k] = sm[zpos((int)k, (int)a.s_log)];
+    for (uint32_t k = threadIdx.x; k < a.S; k += blockDim.x) dst[k] = sm[zpos((int)k, (int)a.s_log)];
 }
 
 struct TierInvArgs {
@@ -700,7 +706,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
     const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = a.ctl->t;
-    for (uint32_t k = threadIdx.x; k < a.S; k += kTierThreads) {
+    for (uint32_t k = threadIdx.x; k < a.S; k += blockDim.x) {
         float2 y = make_float2(0.f, 0.f);
         const float2 *src = a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * a.S + k;
         const size_t stride = (size_t)a.n_out * a.S;
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const uint32_t amask = a.acc_len - 1;
     const uint32_t pos0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask);
     float *acc = a.accring + (size_t)item * a.acc_len;
-    for (uint32_t n = threadIdx.x; n < a.S / 2; n += kTierThreads) {
+    for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x) {
         const float2 z = sm[a.S / 2 + n];
         float2 *p = reinterpret_cast<float2 *>(acc + ((pos0 + 2 * n) & amask));
         float2 q = *p;
@@ -739,7 +745,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
     __shared__ CtaTw tw;
     const uint32_t o = blockIdx.x / a.P, k = blockIdx.x % a.P;
     const float *h = o == 0 ? a.h[0] : a.h[1];
-    for (uint32_t n = threadIdx.x; n < a.S; n += kTierThreads) {
+    for (uint32_t n = threadIdx.x; n < a.S; n += blockDim.x) {
         float re = 0.f, im = 0.f;
         if (n < a.S / 2) {
             const size_t n0 = (size_t)a.frame_off + (size_t)k * a.S + 2 * n;
@@ -752,7 +758,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     float2 *dst = a.H + ((size_t)o * a.P + k) * a.S;
-    for (uint32_t kk = threadIdx.x; kk < a.S; kk += kTierThreads) dst[kk] = sm[zpos((int)kk, (int)a.s_log)];
+    for (uint32_t kk = threadIdx.x; kk < a.S; kk += blockDim.x) dst[kk] = sm[zpos((int)kk, (int)a.s_log)];
 }
 
 }  // namespace ca
