@@ -679,14 +679,14 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const float *ring = a.ring + (size_t)w * a.ring_len;
     const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
     for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x)
-        *reinterpret_cast<float4 *>(sm + 2 * n) = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
+        *reinterpret_cast<float4 *>(sm + swz(2 * (int)n)) = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     const unsigned long long n_fire = (tend + inst % a.m) / a.m;
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
-    for (uint32_t k = threadIdx.x; k < a.S; k += blockDim.x) dst[k] = sm[zpos((int)k, (int)a.s_log)];
+    for (uint32_t p = threadIdx.x; p < a.S; p += blockDim.x) dst[p] = sm[swz((int)p)];  // position order (fft_cta.cuh)
 }
 
 struct TierInvArgs {
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
         const float2 *src = a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * a.S + k;
         const size_t stride = (size_t)a.n_out * a.S;
         for (uint32_t sp = 0; sp < a.n_split; sp++) { const float2 q = src[sp * stride]; y.x += q.x; y.y += q.y; }
-        sm[zpos((int)k, (int)a.s_log)] = y;
+        sm[swz((int)k)] = y;  // spectra of the long tiers are stored in position order
     }
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_split_c2r(sm, (int)a.S, (int)a.s_log, tw);
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const uint32_t pos0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask);
     float *acc = a.accring + (size_t)item * a.acc_len;
     for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x) {
-        const float2 z = sm[a.S / 2 + n];
+        const float2 z = sm[swz((int)(a.S / 2 + n))];
         float2 *p = reinterpret_cast<float2 *>(acc + ((pos0 + 2 * n) & amask));
         float2 q = *p;
         q.x += z.x; q.y += z.y;
@@ -752,13 +752,13 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_ir(const TierIrArgs a)
             if (n0 < a.frames) re = __ldg(&h[n0 * a.stride]) * a.scale;
             if (n0 + 1 < a.frames) im = __ldg(&h[(n0 + 1) * a.stride]) * a.scale;
         }
-        sm[n] = make_float2(re, im);
+        sm[swz((int)n)] = make_float2(re, im);
     }
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     float2 *dst = a.H + ((size_t)o * a.P + k) * a.S;
-    for (uint32_t kk = threadIdx.x; kk < a.S; kk += blockDim.x) dst[kk] = sm[zpos((int)kk, (int)a.s_log)];
+    for (uint32_t p = threadIdx.x; p < a.S; p += blockDim.x) dst[p] = sm[swz((int)p)];
 }
 
 }  // namespace ca
