@@ -475,6 +475,11 @@ def run_reference(args):
         print(json.dumps(base), flush=True)
         return
 
+    # the reference logs every IR load to stdout (log.cu); keep stdout clean for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
     N = 262144  # reference fftSize for a 4 s IR at 48 kHz: pow2 >= L + nframes
     ncores = os.cpu_count() or 8
     cand = [k for k in (1, 2, 4, 8, 16, 32, 64) if k <= max(1, args.ref_max_instances)]
@@ -503,6 +508,8 @@ def run_reference(args):
         if best is None or res["rt_channels"] > best[1]["rt_channels"]:
             best = (k, res)
     clocks = sampler.stop()
+    os.dup2(saved_stdout, 1)
+    os.close(devnull)
     k, res = best
     base.update({
         "value": res["rt_channels"], "ms_per_step": res["ms_per_step"],
