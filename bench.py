@@ -122,6 +122,17 @@ def build_engine(ca, torch, dev, K, flags, tiers=None, mac_split=0):
     return e
 
 
+def mac_traffic(kind, instances):
+    """DRAM bytes (read + write) of the MAC launches of one period, from the committed ncu --set full
+    captures (profiles/mac_traffic.json), scaled per instance."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "mac_traffic.json")) as f:
+            j = json.load(f)[kind]
+        return int(j["dram_bytes_per_instance_period" if kind == "tiered" else "dram_bytes_per_instance"] * instances)
+    except Exception:
+        return None
+
+
 def tier_desc(st):
     return [{"block": int(st.tier_block[j]), "partitions": int(st.tier_parts[j]), "ir_offset": int(st.tier_offset[j])} for j in range(st.n_tiers)]
 
@@ -266,7 +277,7 @@ def run_ours(args):
         mac_us = sp.mac_us + sp.tier_mac_us
         achieved = sp.mac_bytes_amortized / (mac_us * 1e-6) / 1e9
         roof = {"kernel": "k_mac (FDL complex MAC, TMA-staged; all tiers of one period)", "bound": "hbm", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": mac_traffic("tiered" if not args.uniform else "uniform", Kp), "peak_source": peak_src,
                 "instances": Kp, "algorithmic_bytes_per_period": int(sp.mac_bytes_amortized), "kernel_us_per_period": round(mac_us, 2),
                 "share_of_step": round(mac_us / sp.total_us, 3),
                 "step_us": {"forward_r2c": round(sp.fwd_us, 2), "fdl_mac_tier0": round(sp.mac_us, 2), "inverse_c2r_mix": round(sp.inv_us, 2),
@@ -287,12 +298,7 @@ def run_ours(args):
             eu.sync()
             su = eu.stats()
             ach_u = su.mac_bytes / (su.mac_us * 1e-6) / 1e9
-            traffic = None
-            try:
-                with open(os.path.join(ROOT, "profiles", "mac_traffic.json")) as f:
-                    traffic = int(json.load(f)["dram_bytes_per_instance"] * Ku)   # ncu --set full capture, per instance
-            except Exception:
-                pass
+            traffic = mac_traffic("uniform", Ku)
             extras["uniform_partitioning"] = {
                 "instances": Ku, "partitions": int(su.partitions), "rt_channels": round(Ku * deadline_s / (su.total_us * 1e-6), 1),
                 "roofline": {"kernel": "k_mac, uniform P=750: one HBM stream", "bound": "hbm", "achieved": round(ach_u, 1), "peak": peak, "unit": "GB/s",
