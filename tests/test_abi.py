@@ -64,3 +64,30 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f == "Makefile" and "oracle" not in txt, os.path.join(dp, f)
+
+
+def test_auto_tiers_plan_is_valid():
+    """ca_config_auto_tiers (host logic, no GPU): tier 0 == period, blocks grow by `growth`, every
+    tier >= 1 starts at an IR offset >= its block size, the last tier covers the rest."""
+    import cuda_audio_b200 as m
+    for B, L, growth, maxb in [(64, 480000, 0, 0), (256, 192000, 0, 0), (32, 5000, 0, 0), (1024, 200000, 0, 0), (64, 700, 0, 0),
+                               (256, 2880000, 0, 0), (256, 192000, 4, 4096), (64, 480000, 16, 16384), (128, 300, 0, 0)]:
+        cfg = m.default_config(period=B, max_ir_frames=L)
+        assert m.lib().ca_config_auto_tiers(ctypes.byref(cfg), growth, maxb) == 0
+        off = 0
+        assert cfg.tier_block[0] == B and 1 <= cfg.n_tiers <= 4
+        for j in range(cfg.n_tiers):
+            S, P = cfg.tier_block[j], cfg.tier_parts[j]
+            assert S & (S - 1) == 0
+            if j:
+                assert off >= S and S > cfg.tier_block[j - 1] and 256 <= S <= (maxb or 16384)
+            if j + 1 < cfg.n_tiers:
+                assert P > 0
+                off += S * P
+            else:
+                assert P == 0          # the engine extends the last tier to cover max_ir_frames
+        assert off < L or cfg.n_tiers == 1
+    cfg = m.default_config(period=100)
+    assert m.lib().ca_config_auto_tiers(ctypes.byref(cfg), 0, 0) == -1
+    cfg = m.default_config(period=64)
+    assert m.lib().ca_config_auto_tiers(ctypes.byref(cfg), 3, 0) == -1
