@@ -942,6 +942,52 @@ int ca_reset_stats(ca_engine *e)
     return CA_OK;
 }
 
+// ---- diagnostics: read-only bandwidth sweep (L2-resident vs HBM), the denominator for the
+//      single-instance (L2-resident) MAC that MEASURED_PEAKS.json does not contain ----
+namespace {
+__global__ void __launch_bounds__(256) k_read_sweep(const float4 *__restrict__ p, size_t n4, float *sink)
+{
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = p[i], b = p[i + stride], c = p[i + 2 * stride], d = p[i + 3 * stride];
+        acc.x += a.x + b.x + c.x + d.x; acc.y += a.y + b.y + c.y + d.y;
+        acc.z += a.z + b.z + c.z + d.z; acc.w += a.w + b.w + c.w + d.w;
+    }
+    for (; i < n4; i += stride) { const float4 a = p[i]; acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+    if (acc.x + acc.y + acc.z + acc.w == 12345.678f) *sink = acc.x;  // keep the loads alive
+}
+}  // namespace
+
+int ca_measure_read_gbs(int device, size_t bytes, int iters, double *gbs)
+{
+    if (!gbs || bytes < 4096 || iters < 1) return CA_ERR_INVALID;
+    CA_CUDA(cudaSetDevice(device));
+    float4 *buf = nullptr;
+    float *sink = nullptr;
+    CA_CUDA(cudaMalloc(&buf, bytes));
+    CA_CUDA(cudaMalloc(&sink, sizeof(float)));
+    CA_CUDA(cudaMemset(buf, 0, bytes));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaEvent_t e0, e1;
+    CA_CUDA(cudaEventCreate(&e0));
+    CA_CUDA(cudaEventCreate(&e1));
+    const size_t n4 = bytes / sizeof(float4);
+    for (int w = 0; w < 3; w++) k_read_sweep<<<sms * 8, 256>>>(buf, n4, sink);
+    CA_CUDA(cudaEventRecord(e0));
+    for (int it = 0; it < iters; it++) k_read_sweep<<<sms * 8, 256>>>(buf, n4, sink);
+    CA_CUDA(cudaEventRecord(e1));
+    CA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    CA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    return CA_OK;
+}
+
 int ca_host_alloc(void **p, size_t bytes)
 {
     if (!p) return CA_ERR_INVALID;

@@ -23,7 +23,7 @@ EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",
     "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
-    "ca_host_alloc", "ca_host_free",
+    "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.ca_reset_stats.argtypes = [vp]
         L.ca_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.ca_host_free.argtypes = [vp]
+        L.ca_measure_read_gbs.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -128,6 +129,12 @@ def default_config(**kw) -> Config:
         else:
             setattr(cfg, k, v)
     return cfg
+
+
+def measure_read_gbs(nbytes: int, iters: int = 20, device: int = 0) -> float:
+    g = C.c_double()
+    _check(lib().ca_measure_read_gbs(device, nbytes, iters, C.byref(g)), "ca_measure_read_gbs")
+    return g.value
 
 
 class PinnedArray:

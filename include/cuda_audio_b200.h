@@ -166,6 +166,10 @@ void *ca_stream(ca_engine *e);
 int ca_get_stats(ca_engine *e, ca_stats *s);
 int ca_reset_stats(ca_engine *e);
 
+/* Diagnostics: read-only bandwidth (GB/s) of a `bytes`-sized device buffer swept `iters` times --
+ * L2-resident for small sizes, HBM for large ones; the roofline denominator of the single-instance MAC. */
+int ca_measure_read_gbs(int device, size_t bytes, int iters, double *gbs);
+
 /* Pinned host memory helpers for callers that want zero staging copies. */
 int ca_host_alloc(void **p, size_t bytes);
 int ca_host_free(void *p);
