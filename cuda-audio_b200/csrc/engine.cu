@@ -233,7 +233,7 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
                t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    e->fft.fwd<<<(n_items * e->nv + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
+    e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
     t0.mac.fn<<<dim3(t0.n_split, t0.tiles, i1 - i0), kMacThreads, t0.mac.smem, e->stream>>>(ma);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));

@@ -124,73 +124,105 @@ struct FwdArgs {
     uint32_t item0;    // first (instance, input) item of this launch (chunked host pipeline)
 };
 
+// One warp per (instance, input); it steps the voice state once and then runs every audible voice
+// (one in steady state, two or three during an IR cross-fade).
 template <int R>
 __global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
 {
     constexpr int B = 32 * R;
     const int lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
-    if (w >= a.n_items * a.nv) return;
-    const uint32_t item = a.item0 + w / a.nv, v = w % a.nv;
+    if (w >= a.n_items) return;
+    const uint32_t item = a.item0 + w;
     const unsigned long long t = a.ctl->t;
     if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
 
-    // --- parameters: every warp of the item recomputes the same state step; voice 0 stores it ---
     const InParamDev p = a.par[item];
-    const ItemState s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
-    if (v == 0 && lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
-    if (!((s.active >> v) & 1u)) return;
-    float cv = 0.f;
-#pragma unroll
-    for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
-    const float gain = cv * p.level;
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
+    const ItemState s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
+    if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
 
+    WarpFft<R> f;
+    f.init(a.twM);
     const uint32_t mask = a.ring_len - 1;
-    float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
-    if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
-        for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-    }
-    // --- predelay ring: the whole response of this block is delayed by pd (conv.cu:97) ---
     const float *x = a.in + (size_t)item * B;
     const uint32_t base = (uint32_t)((t * (unsigned long long)B) & mask);
     const uint32_t prev = (base - B) & mask;
-#pragma unroll
-    for (int j = 0; j < R; j++)  // clear the block that becomes reachable by the scatter in this period
-        ring[(base + kMaxPredelay + lane + 32 * j) & mask] = 0.f;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-        const int n = lane + 32 * j;
-        const uint32_t idx = (base + pd + n) & mask;
-        ring[idx] += gain * __ldg(&x[n]);
-    }
-    __syncwarp();
+    const uint32_t off = ((lane < 16) ? prev : base) + 2 * R * (lane & 15);  // time layout: lane a holds floats [2R a, 2R a + 2R)
+    const unsigned long long n_fire = t + 1ull;                               // tier 0 fires every period
+    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);      // the FDL ring runs backwards
 
-    // --- window [x'(t-1) | x'(t)] in time layout: lane a holds floats [2R a, 2R a + 2R) ---
-    WarpFft<R> f;
-    f.init(a.twM);
-    const uint32_t off = ((lane < 16) ? prev : base) + 2 * R * (lane & 15);
-    float2 z[R];
-    if constexpr (R == 1) {
-        z[0] = *reinterpret_cast<const float2 *>(ring + off);
-    } else {
+#pragma unroll 1
+    for (uint32_t v = 0; v < a.nv; v++) {
+        if (!((s.active >> v) & 1u)) continue;
+        float cv = 0.f;
 #pragma unroll
-        for (int j = 0; j < R / 2; j++) {
-            const float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
-            z[2 * j] = make_float2(q.x, q.y);
-            z[2 * j + 1] = make_float2(q.z, q.w);
+        for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
+        const float gain = cv * p.level;
+        float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
+        if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
+            for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
         }
-    }
-    f.forward(z);
-    f.split_r2c(z, a.tw2M);
-
-    const unsigned long long n_fire = t + 1ull;  // tier 0 fires every period
-    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);  // ring runs backwards
-    float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot) * B;
 #pragma unroll
-    for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
+        for (int j = 0; j < R; j++)  // clear the block that becomes reachable by the predelay scatter in this period
+            ring[(base + kMaxPredelay + lane + 32 * j) & mask] = 0.f;
+
+        float2 z[R];
+        if (pd == 0) {
+            // no predelay: the block lands exactly on the current ring block.  One round trip: read the
+            // window (previous block | what earlier, delayed blocks left in the current one) and the
+            // input in window layout, add, keep the sum in registers and write the current block back.
+            if constexpr (R == 1) {
+                float2 q = *reinterpret_cast<const float2 *>(ring + off);
+                if (lane >= 16) {
+                    const float2 xi = *reinterpret_cast<const float2 *>(x + 2 * (lane & 15));
+                    q.x = fmaf(gain, xi.x, q.x); q.y = fmaf(gain, xi.y, q.y);
+                    *reinterpret_cast<float2 *>(ring + off) = q;
+                }
+                z[0] = q;
+            } else {
+#pragma unroll
+                for (int j = 0; j < R / 2; j++) {
+                    float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
+                    if (lane >= 16) {
+                        const float4 xi = *reinterpret_cast<const float4 *>(x + 2 * R * (lane & 15) + 4 * j);
+                        q.x = fmaf(gain, xi.x, q.x); q.y = fmaf(gain, xi.y, q.y);
+                        q.z = fmaf(gain, xi.z, q.z); q.w = fmaf(gain, xi.w, q.w);
+                        *reinterpret_cast<float4 *>(ring + off + 4 * j) = q;
+                    }
+                    z[2 * j] = make_float2(q.x, q.y);
+                    z[2 * j + 1] = make_float2(q.z, q.w);
+                }
+            }
+        } else {
+            // predelay ring: the whole response of this block is delayed by pd samples (conv.cu:97):
+            // scatter-add the scaled block at +pd, then read the window back
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const int n = lane + 32 * j;
+                const uint32_t idx = (base + pd + n) & mask;
+                ring[idx] += gain * __ldg(&x[n]);
+            }
+            __syncwarp();
+            if constexpr (R == 1) {
+                z[0] = *reinterpret_cast<const float2 *>(ring + off);
+            } else {
+#pragma unroll
+                for (int j = 0; j < R / 2; j++) {
+                    const float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
+                    z[2 * j] = make_float2(q.x, q.y);
+                    z[2 * j + 1] = make_float2(q.z, q.w);
+                }
+            }
+        }
+        f.forward(z);
+        f.split_r2c(z, a.tw2M);
+        float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot) * B;
+#pragma unroll
+        for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

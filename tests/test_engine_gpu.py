@@ -443,3 +443,23 @@ def test_chunked_host_pipeline_matches_single_stream():
     truth = O.engine_truth(np.concatenate(list(x[:, s]), axis=-1), [[h[2 * ((s + i) % 2)], h[2 * ((s + i) % 2) + 1]] for i in range(2)],
                            [dict(wet=1.0, dry=0.3, panWet=0.01 * (s % 50))] * 2)
     assert O.rel_l2(np.concatenate(list(ya[:, s, 0]), axis=-1), truth[0]) < 5e-6
+
+
+@pytest.mark.parametrize("n_in,n_out", [(1, 2), (2, 1), (1, 1)])
+@pytest.mark.parametrize("tiers", [None, [(64, 8), (512, 0)]])
+def test_channel_layouts(n_in, n_out, tiers):
+    """mono-in / stereo-out, stereo-in / mono-out and mono: uniform and tiered."""
+    m = ca()
+    fs, B, L = 48000, 64, 64 * 8 + 512 * 2 + 31
+    irs = [[O.synth_ir(L, fs, 500 + 2 * i + o) for o in range(n_out)] for i in range(n_in)]
+    x = np.stack([O.synth_audio(B * 70, 600 + i) for i in range(n_in)])
+    pr = [dict(wet=0.9, dry=0.25, level=0.7, panWet=0.3, panDry=-0.6), dict(wet=0.4, dry=0.5, level=1.0, panWet=-0.2, panDry=0.1)][:n_in]
+    with m.Engine(period=B, max_ir_frames=L, n_in=n_in, n_out=n_out, n_ir_slots=n_in, tiers=tiers) as e:
+        for i in range(n_in):
+            e.load_ir(i, irs[i][0], irs[i][1] if n_out == 2 else None)
+            e.set_params(0, i, select=i, predelay=9, **pr[i])
+            e.set_glide(0, i, pr[i]["wet"])
+        y = e.render(x[None])[0]
+    truth = O.engine_truth(x, irs, pr, predelay=9)
+    for o in range(n_out):
+        assert O.rel_l2(y[o], truth[o]) < 5e-6, (n_in, n_out, o, O.rel_l2(y[o], truth[o]))
