@@ -135,6 +135,8 @@ struct ca_engine {
     cudaEvent_t upload_done[2] = {nullptr, nullptr};
     cudaEvent_t out_ready = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the chunked host pipeline
+    cudaStream_t s_tier[CA_MAX_TIERS] = {};         // side streams: forward FFT + MAC of concurrently firing tiers
+    cudaEvent_t fork_ev = nullptr, join_ev[CA_MAX_TIERS] = {};
     cudaEvent_t io_ev[2][kIoChunks + 1] = {};
     int upload_idx = 0;
     // parameters (host shadow)
@@ -248,25 +250,48 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
 int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
 {
     const uint32_t n_alloc = e->n_inst * e->n_in;
+    uint32_t firing = 0;
+    for (size_t j = 1; j < e->tiers.size(); j++) firing += tier_count(e, e->tiers[j], tend) ? 1u : 0u;
+    // Different tiers work on disjoint buffers until their inverse adds into the shared output ring:
+    // with >= 2 tiers firing, each tier's forward FFT + MAC runs on its own side stream (the 16 K tier
+    // launches too few CTAs to fill the GPU alone), then the inverse kernels run in tier order on the
+    // main stream so the output-ring accumulation stays race-free and deterministic.
+    const bool fork = firing >= 2 && !profile;
+    if (fork) CA_CUDA(cudaEventRecord(e->fork_ev, e->stream));
     for (size_t j = 1; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
         const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
         e->tev_used[j] = profile && count;
         if (!count) continue;
+        cudaStream_t st = fork ? e->s_tier[j] : e->stream;
+        if (fork) CA_CUDA(cudaStreamWaitEvent(st, e->fork_ev, 0));
         const uint32_t smem = t.S * sizeof(float2);
         const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
-        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], e->stream));
-        k_tier_forward<<<count * e->n_in * e->nv, threads, smem, e->stream>>>(fa);
-        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], e->stream));
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
+        k_tier_forward<<<count * e->n_in * e->nv, threads, smem, st>>>(fa);
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
-        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, e->stream>>>(ma);
-        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], e->stream));
-        TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-        k_tier_inverse<<<count * e->n_out, threads, smem, e->stream>>>(ia);
-        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], e->stream));
+        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, st>>>(ma);
+        if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], st));
+        if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
+        else {
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
+            k_tier_inverse<<<count * e->n_out, threads, smem, st>>>(ia);
+            if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
+        }
     }
+    if (fork)
+        for (size_t j = 1; j < e->tiers.size(); j++) {
+            const Tier &t = e->tiers[j];
+            const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
+            if (!count) continue;
+            CA_CUDA(cudaStreamWaitEvent(e->stream, e->join_ev[j], 0));
+            const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
+            k_tier_inverse<<<count * e->n_out, threads, t.S * sizeof(float2), e->stream>>>(ia);
+        }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -492,6 +517,9 @@ int ca_destroy(ca_engine *e)
     for (auto &ev : e->upload_done) if (ev) cudaEventDestroy(ev);
     if (e->out_ready) cudaEventDestroy(e->out_ready);
     for (auto &row : e->io_ev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+    for (auto &st : e->s_tier) if (st) cudaStreamDestroy(st);
+    if (e->fork_ev) cudaEventDestroy(e->fork_ev);
+    for (auto &ev : e->join_ev) if (ev) cudaEventDestroy(ev);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.tw); }
@@ -562,6 +590,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+    for (auto &st : e->s_tier) CA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CA_CUDA(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
+    for (auto &ev : e->join_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &row : e->io_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
