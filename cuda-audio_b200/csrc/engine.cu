@@ -73,6 +73,7 @@ MacVariant mac_pick(int bt, int n_out, int variant)
     case 32: return n_out == 1 ? mac_pick_v<32, 1>(variant) : mac_pick_v<32, 2>(variant);
     case 64: return n_out == 1 ? mac_pick_v<64, 1>(variant) : mac_pick_v<64, 2>(variant);
     case 128: return n_out == 1 ? mac_pick_v<128, 1>(variant) : mac_pick_v<128, 2>(variant);
+    case 512: return n_out == 1 ? mac_pick_v<512, 1>(variant) : mac_pick_v<512, 2>(variant);
     default: return n_out == 1 ? mac_pick_v<256, 1>(variant) : mac_pick_v<256, 2>(variant);
     }
 }
@@ -601,7 +602,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     for (size_t j = 0; j < e->tiers.size(); j++) {
         Tier &t = e->tiers[j];
         t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
-        t.bt = std::min<uint32_t>(t.S, 256);
+        const uint32_t bt_max = getenv("CA_MAC_BT") ? (uint32_t)atoi(getenv("CA_MAC_BT")) : 256u;
+        t.bt = std::min<uint32_t>(t.S, j == 0 ? 256u : bt_max);
         t.tiles = t.S / t.bt;
         // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /
         // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 48 KB / 4 CTAs per SM
