@@ -602,7 +602,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     for (size_t j = 0; j < e->tiers.size(); j++) {
         Tier &t = e->tiers[j];
         t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
-        const uint32_t bt_max = getenv("CA_MAC_BT") ? (uint32_t)atoi(getenv("CA_MAC_BT")) : 256u;
+        // bin tile of the long tiers: 512 complex (4 KB arrays) halves the CTA count per byte (+6 % measured)
+        const uint32_t bt_max = getenv("CA_MAC_BT") ? (uint32_t)atoi(getenv("CA_MAC_BT")) : 512u;
         t.bt = std::min<uint32_t>(t.S, j == 0 ? 256u : bt_max);
         t.tiles = t.S / t.bt;
         // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /

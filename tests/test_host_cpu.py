@@ -144,3 +144,22 @@ def test_render_fails_loudly_without_gpu(tmp_path):
         pytest.skip("GPU present")
     r = subprocess.run([RENDER, "--synthetic-ir", "0.05", "--synthetic-in", "0.1", "--out", str(tmp_path / "o.wav")], capture_output=True, text=True)
     assert r.returncode != 0 and not (tmp_path / "o.wav").exists()
+
+
+def test_live_executable_fails_cleanly_without_libjack(tmp_path):
+    """ca_live = the reference's main.cu flow with libjack resolved at run time: without libjack /
+    jackd it must report the problem and exit non-zero (the reference asserts)."""
+    live = os.path.join(ROOT, "cuda-audio_b200", "host", "ca_live")
+    assert os.path.exists(live)
+    lines = ["conv.count 2"]
+    for i in range(2):
+        lines += [f"conv[{i}].fftSize 8192", f"conv[{i}].index {tmp_path}/none.index", f"conv[{i}].input system:capture_{i + 1}",
+                  f"conv[{i}].output system:playback_{i + 1}"]
+        lines += [f"conv[{i}].value.{k} 0" for k in ("select", "predelay", "speed")]
+        lines += [f"conv[{i}].value.{k} 0.5" for k in ("dry", "wet", "panDry", "panWet", "level")]
+    (tmp_path / "settings.txt").write_text("\n".join(lines) + "\n")
+    r = subprocess.run([live, str(tmp_path / "settings.txt")], capture_output=True, text=True, stdin=subprocess.DEVNULL)
+    assert r.returncode == 1
+    assert "cannot start JACK client" in r.stderr or "cannot open JACK client" in r.stderr
+    r = subprocess.run([live, str(tmp_path / "missing.txt")], capture_output=True, text=True, stdin=subprocess.DEVNULL)
+    assert r.returncode == 1 and "cannot open settings file" in r.stderr
