@@ -167,7 +167,27 @@ def run_ours(args):
     deadline_s = B / FS
     tiers = None if args.uniform else "auto"
     K = args.instances
-    e = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING, tiers=tiers)
+    if K <= 0:
+        # as many instances as this GPU's HBM holds: the channel count is capacity-bound, not time-bound
+        with ca.Engine(period=B, max_ir_frames=IR_FRAMES, n_instances=256, n_ir_slots=512, device=dev.index, tiers=tiers) as probe:
+            per_inst = probe.stats().device_bytes / 256.0
+        free, _total = torch.cuda.mem_get_info(dev)
+        K = int((free - args.reserve_gb * 1e9) / per_inst) // 256 * 256
+        if args.uniform:
+            K = min(K, 4096)
+        if world > 1:
+            tk = torch.tensor([K], device=dev, dtype=torch.int64)
+            dist.all_reduce(tk, op=dist.ReduceOp.MIN)
+            K = int(tk.item())
+    e = None
+    while e is None:
+        try:
+            e = build_engine(ca, torch, dev, K, ca.FLAG_STREAMING, tiers=tiers)
+        except ca.CaError as ex:
+            if ex.code != -3 or K <= 1024 or world > 1:
+                raise
+            K = int(K * 0.9) // 256 * 256      # cudaMalloc said no: back off (nothing was left allocated)
+            torch.cuda.empty_cache()
     st0 = e.stats()
     cycle = max(int(st0.tier_block[j]) for j in range(st0.n_tiers)) // B      # periods until the launch pattern repeats
     gin = torch.Generator(device=dev)
@@ -541,7 +561,8 @@ def main():
     ap.add_argument("--mode", default="channels", choices=["channels", "irsplit"],
                     help="channels: the headline (independent instances, no collective); irsplit: configs[4], one long IR split across the GPUs")
     ap.add_argument("--irsplit-seconds", type=float, default=60.0)
-    ap.add_argument("--instances", type=int, default=10240, help="instances per GPU in the throughput run")
+    ap.add_argument("--instances", type=int, default=0, help="instances per GPU in the throughput run (0 = as many as the GPU's HBM holds)")
+    ap.add_argument("--reserve-gb", type=float, default=10.0, help="HBM left free when --instances 0 sizes the batch")
     ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
     ap.add_argument("--uniform-instances", type=int, default=2048)
     ap.add_argument("--profile-instances", type=int, default=4096)

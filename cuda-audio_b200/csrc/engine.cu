@@ -211,7 +211,7 @@ int flush_params(ca_engine *e)
 MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
 {
     return MacArgs{t.X, t.H, t.Ypart, e->d_par, e->d_st, e->d_ctl, e->n_inst * e->n_in, e->n_in, e->nv, t.Lring, t.P, t.S,
-                   e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u};
+                   e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u, t.m > 1 ? 1u : 0u};
 }
 
 // instances whose tier-j block closes at the end of period t_end - 1: s = r + i*m, r = (-t_end) mod m
@@ -652,7 +652,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         for (auto &t : e->tiers) { t.X = reinterpret_cast<float2 *>(p); p += t.x_bytes; }
     }
     for (auto &t : e->tiers) {
-        const size_t yp_bytes = (size_t)e->n_inst * t.n_split * e->n_out * t.S * sizeof(float2);
+        // long tiers are phase-staggered: at most ceil(n_inst / m) instances fire per period
+        const size_t yp_inst = t.m > 1 ? (e->n_inst + t.m - 1) / t.m : e->n_inst;
+        const size_t yp_bytes = yp_inst * t.n_split * e->n_out * t.S * sizeof(float2);
         CA_CUDA(cudaMalloc(&t.Ypart, yp_bytes));
         CA_CUDA(cudaMemsetAsync(t.Ypart, 0, yp_bytes, e->stream));
         e->device_bytes += yp_bytes;

@@ -344,6 +344,7 @@ struct MacArgs {
     // instance s closes its tier-j block when (t_end + s mod m) % m == 0, so every period only 1/m of
     // the instances run the tier and the load per period is flat.
     uint32_t inst0, inst_stride;
+    uint32_t yp_local;  // 1: Ypart is indexed by the launch's instance index (long tiers: only 1/m of the instances fire)
 };
 
 constexpr int kMacConsumers = 256;
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
             s0.x += u.x; s0.y += u.y;
         }
         if (q == 0 && tile == 0) { sum.x = s0.x; sum.y = s0.y; }
-        float2 *dst = a.Ypart + (((size_t)inst * a.n_split + split) * NOUT + o) * a.S + tile * BT + 2 * q;
+        float2 *dst = a.Ypart + (((size_t)(a.yp_local ? blockIdx.z : inst) * a.n_split + split) * NOUT + o) * a.S + tile * BT + 2 * q;
         *reinterpret_cast<float4 *>(dst) = sum;
     }
 }
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
 }
 
 struct TierInvArgs {
-    const float2 *Ypart;  // [inst][n_split][n_out][S]
+    const float2 *Ypart;  // [firing instance of this launch][n_split][n_out][S]
     float *accring;       // [inst*n_out + o][acc_len]
     const Ctl *ctl;
     const float2 *twM, *tw2M;
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const unsigned long long tend = a.ctl->t;
     for (uint32_t k = threadIdx.x; k < a.S; k += blockDim.x) {
         float2 y = make_float2(0.f, 0.f);
-        const float2 *src = a.Ypart + (((size_t)inst * a.n_split) * a.n_out + o) * a.S + k;
+        const float2 *src = a.Ypart + (((size_t)(blockIdx.x / a.n_out) * a.n_split) * a.n_out + o) * a.S + k;
         const size_t stride = (size_t)a.n_out * a.S;
         for (uint32_t sp = 0; sp < a.n_split; sp++) { const float2 q = src[sp * stride]; y.x += q.x; y.y += q.y; }
         sm[swz((int)k)] = y;  // spectra of the long tiers are stored in position order
