@@ -104,7 +104,7 @@ uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l
 // period; tier j >= 1 has block S_j = m * period, covers IR frames [off, off + P*S) and runs after
 // the output of every m-th period has been produced (its result is first needed one period later
 // because off >= S).
-constexpr uint32_t kIoChunks = 4;
+constexpr uint32_t kIoChunks = 16;  // upper bound; the count used is io_chunks (default 8, env CA_IO_CHUNKS)
 
 struct Tier {
     uint32_t S = 0, m = 1, P = 0, off = 0, s_log = 0, bt = 0, tiles = 1, n_split = 1, Lring = 0;
@@ -139,6 +139,7 @@ struct ca_engine {
     cudaStream_t s_tier[CA_MAX_TIERS] = {};         // side streams: forward FFT + MAC of concurrently firing tiers
     cudaEvent_t fork_ev = nullptr, join_ev[CA_MAX_TIERS] = {};
     cudaEvent_t io_ev[2][kIoChunks + 1] = {};
+    uint32_t io_chunks = 8;
     int upload_idx = 0;
     // parameters (host shadow)
     std::mutex par_mutex;
@@ -576,6 +577,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     e->B = cfg->period; e->R = cfg->period / 32;
     e->n_inst = e->n_active = cfg->n_instances; e->n_in = cfg->n_in; e->n_out = cfg->n_out;
     e->nv = cfg->max_voices ? cfg->max_voices : 2u;
+    if (const char *c = getenv("CA_IO_CHUNKS")) e->io_chunks = std::max(1, std::min<int>(kIoChunks, atoi(c)));
     int rc = plan_tiers(cfg, e);
     if (rc) return rc;
     e->fft = fft_pick((int)e->R);
@@ -884,7 +886,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     const bool graph = (e->cfg.flags & CA_FLAG_GRAPH) != 0, profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
     // Large batches: cut the instances into chunks and pipeline H2D | kernels | D2H on three streams so
     // the PCIe copies (2 KB per instance and direction) hide behind the kernels of the other chunks.
-    const uint32_t chunks = (graph || profile || e->n_active < 512) ? 1u : std::min<uint32_t>(kIoChunks, e->n_active / 256);
+    const uint32_t chunks = (graph || profile || e->n_active < 512) ? 1u : std::min<uint32_t>(e->io_chunks, e->n_active / 256);
     int rc = CA_OK;
     if (chunks <= 1) {
         CA_CUDA(cudaMemcpyAsync(e->d_in, src, in_bytes, cudaMemcpyHostToDevice, e->stream));
