@@ -78,17 +78,18 @@ MacVariant mac_pick(int bt, int n_out, int variant)
     }
 }
 
-struct FftFns { fwd_fn fwd; ir_fn ir; inv_fn inv, inv_packed; };
+typedef void (*fused_fn)(const FusedArgs);
+struct FftFns { fwd_fn fwd; ir_fn ir; inv_fn inv, inv_packed; fused_fn fused1, fused2; };
 FftFns fft_pick(int R)
 {
     switch (R) {
-    case 1: return {k_forward<1>, k_ir_fft<1>, k_inverse<1, false>, k_inverse<1, true>};
-    case 2: return {k_forward<2>, k_ir_fft<2>, k_inverse<2, false>, k_inverse<2, true>};
-    case 4: return {k_forward<4>, k_ir_fft<4>, k_inverse<4, false>, k_inverse<4, true>};
-    case 8: return {k_forward<8>, k_ir_fft<8>, k_inverse<8, false>, k_inverse<8, true>};
-    case 16: return {k_forward<16>, k_ir_fft<16>, k_inverse<16, false>, k_inverse<16, true>};
-    case 32: return {k_forward<32>, k_ir_fft<32>, k_inverse<32, false>, k_inverse<32, true>};
-    default: return {nullptr, nullptr, nullptr, nullptr};
+    case 1: return {k_forward<1>, k_ir_fft<1>, k_inverse<1, false>, k_inverse<1, true>, k_fused0<1, 1>, k_fused0<1, 2>};
+    case 2: return {k_forward<2>, k_ir_fft<2>, k_inverse<2, false>, k_inverse<2, true>, k_fused0<2, 1>, k_fused0<2, 2>};
+    case 4: return {k_forward<4>, k_ir_fft<4>, k_inverse<4, false>, k_inverse<4, true>, k_fused0<4, 1>, k_fused0<4, 2>};
+    case 8: return {k_forward<8>, k_ir_fft<8>, k_inverse<8, false>, k_inverse<8, true>, k_fused0<8, 1>, k_fused0<8, 2>};
+    case 16: return {k_forward<16>, k_ir_fft<16>, k_inverse<16, false>, k_inverse<16, true>, nullptr, nullptr};
+    case 32: return {k_forward<32>, k_ir_fft<32>, k_inverse<32, false>, k_inverse<32, true>, nullptr, nullptr};
+    default: return {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     }
 }
 
@@ -148,6 +149,8 @@ struct ca_engine {
     std::atomic<bool> par_dirty{true};
     std::vector<uint8_t> ir_loaded;
     FftFns fft{};
+    bool fused = false;       // tier 0 runs as one fused kernel (k_fused0)
+    uint32_t fused_smem = 0;
     // graphs: [0] = the period pipeline (tier 0), [mask] = the deferred tiers that fire together
     std::map<uint64_t, cudaGraphExec_t> graphs;
     const float *g_in = nullptr;
@@ -236,6 +239,19 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     ma.inst0 = i0;
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
                t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
+    if (e->fused) {
+        // tiered throughput schedule: forward + MAC + inverse of tier 0 in one CTA per instance
+        fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
+        FusedArgs ga{d_in, d_out, e->d_ring, t0.X, t0.H, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
+                     n_alloc, e->n_in, e->nv, t0.Lring, t0.P, e->ring_len, e->ring_out, e->acc_len, i0,
+                     (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
+        if (profile) { CA_CUDA(cudaEventRecord(e->ev[0], e->stream)); CA_CUDA(cudaEventRecord(e->ev[1], e->stream)); }
+        fn<<<i1 - i0, kFusedThreads, e->fused_smem, e->stream>>>(ga);
+        if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl);
+        if (profile) { CA_CUDA(cudaEventRecord(e->ev[2], e->stream)); CA_CUDA(cudaEventRecord(e->ev[3], e->stream)); }
+        CA_CUDA(cudaGetLastError());
+        return CA_OK;
+    }
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
@@ -360,7 +376,7 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
         rc = launch_period(e, d_in, d_out, profile, 0, e->n_active, true);
         if (rc) return rc;
     }
-    e->launches += 3;
+    e->launches += e->fused ? 2 : 3;
     return CA_OK;
 }
 
@@ -630,6 +646,16 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         e->arena_bytes += t.h_bytes + t.x_bytes;
         s_max = std::max(s_max, t.S);
         reach = std::max(reach, t.off + t.S);
+    }
+    {
+        const char *fz = getenv("CA_FUSE");
+        fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
+        e->fused = e->tiers.size() > 1 && fn && e->tiers[0].n_split == 1 && e->tiers[0].tiles == 1 && e->n_in * e->nv <= 4 && !(fz && fz[0] == '0');
+        if (e->fused) {
+            e->fused_smem = e->n_out == 1 ? (e->R == 8 ? FusedCfg<8, 1>::SMEM_BYTES : e->R == 4 ? FusedCfg<4, 1>::SMEM_BYTES : e->R == 2 ? FusedCfg<2, 1>::SMEM_BYTES : FusedCfg<1, 1>::SMEM_BYTES)
+                                          : (e->R == 8 ? FusedCfg<8, 2>::SMEM_BYTES : e->R == 4 ? FusedCfg<4, 2>::SMEM_BYTES : e->R == 2 ? FusedCfg<2, 2>::SMEM_BYTES : FusedCfg<1, 2>::SMEM_BYTES);
+            CA_CUDA(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->fused_smem));
+        }
     }
     if (e->tiers.size() > 1) {
         CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
@@ -913,7 +939,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
             CA_CUDA(cudaStreamWaitEvent(e->s_out, e->io_ev[1][c], 0));
             CA_CUDA(cudaMemcpyAsync(dst + i0 * out_stride, e->d_out + i0 * out_stride, (i1 - i0) * out_stride * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
         }
-        e->launches += 3 * chunks;
+        e->launches += e->fused ? chunks + 1 : 3 * chunks;
         CA_CUDA(cudaEventRecord(e->out_ready, e->s_out));
     }
     rc = run_deferred(e);  // long tiers keep the GPU busy while the host already has its output
@@ -966,6 +992,7 @@ int ca_get_stats(ca_engine *e, ca_stats *s)
     s->mac_bytes_amortized = (uint64_t)(amort * e->n_active);
     s->partitions = t0.P; s->mac_split = t0.n_split; s->device_bytes = e->device_bytes;
     s->n_tiers = (uint32_t)e->tiers.size();
+    s->tier0_fused = e->fused ? 1u : 0u;
     for (size_t j = 0; j < e->tiers.size() && j < CA_MAX_TIERS; j++) { s->tier_block[j] = e->tiers[j].S; s->tier_parts[j] = e->tiers[j].P; s->tier_offset[j] = e->tiers[j].off; }
     return CA_OK;
 }

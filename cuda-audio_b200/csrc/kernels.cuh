@@ -681,6 +681,383 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// fused tier 0 (throughput schedule of the tiered engine): one CTA per instance does
+//   forward R2C (FFT warps)  ||  TMA streaming of the IR + FDL rows (producer warp)
+//   -> MAC (8 consumer warps) -> inverse C2R + ring + clamp + dry (FFT warps)
+// With P_0 = 8 partitions the whole working set of an instance (16 rows x 6 KB) is in flight at once,
+// the newest spectrum goes from the FFT warps to the consumers through shared memory (rows are
+// ordered newest-last), and the partial-spectrum round trip through global memory disappears.
+// ------------------------------------------------------------------------------------------
+struct FusedArgs {
+    const float *in;      // [inst][n_in][B]
+    float *out;           // [inst][n_out][B]
+    float *ring;          // time rings
+    float2 *X;            // tier-0 FDL
+    const float2 *H;      // tier-0 IR bank [slot][n_out][P][B]
+    float *accring;       // output ring of the long tiers (may be nullptr)
+    const InParamDev *par;
+    ItemState *st;
+    Ctl *ctl;
+    const float2 *twM, *tw2M;
+    uint32_t n_items_alloc, n_in, nv, Lring, P, ring_len, ring_out, acc_len;
+    uint32_t inst0, stream_hint, raw_wet;
+};
+
+constexpr int kFusedThreads = kMacConsumers + 32 + 64;  // 8 consumer warps, 1 producer warp, 2 FFT warps
+constexpr int kFusedStages = 7;
+
+template <int R, int NOUT>
+struct FusedCfg {
+    static constexpr int B = 32 * R, LR = B / 2, G = kMacConsumers / LR, KC = G, NARR = 1 + NOUT;
+    static constexpr uint32_t ARR_BYTES = B * 8;
+    static constexpr uint32_t STAGE_BYTES = KC * NARR * ARR_BYTES;                 // 12 KB at NOUT = 2
+    static constexpr uint32_t XNEW_BYTES = 4 * ARR_BYTES;                          // newest spectrum per (input, voice), <= 4 streams
+    static constexpr uint32_t YS_BYTES = NOUT * ARR_BYTES;
+    static constexpr uint32_t SMEM_BYTES = kFusedStages * STAGE_BYTES + XNEW_BYTES + YS_BYTES + (2 * kFusedStages + 1) * 8 + 16;
+};
+
+__global__ void k_tick(Ctl *ctl) { ctl->t = ctl->t_next; }  // the fused kernel reads ctl->t in every CTA: advance afterwards
+
+template <int R, int NOUT>
+__global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
+{
+    using Cfg = FusedCfg<R, NOUT>;
+    constexpr int B = Cfg::B, LR = Cfg::LR, G = Cfg::G, KC = Cfg::KC, NARR = Cfg::NARR, NSTAGE = kFusedStages;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *stage = reinterpret_cast<float4 *>(smem);
+    float2 *xnew = reinterpret_cast<float2 *>(smem + NSTAGE * Cfg::STAGE_BYTES);   // [stream][B]
+    float2 *Ys = xnew + 4 * B;                                                     // [NOUT][B]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::XNEW_BYTES + Cfg::YS_BYTES);
+    uint64_t *empty = full + NSTAGE;
+    uint64_t *xready = empty + NSTAGE;
+    __shared__ uint32_t s_nk[4], s_slot[4], s_rowstart[5];
+    __shared__ float s_pan[2][NOUT];
+
+    const uint32_t inst = a.inst0 + blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fw = warp - (kMacConsumers / 32 + 1);  // FFT warp index (0, 1) or negative
+    const uint32_t ns = a.n_in * a.nv;
+    const unsigned long long t = a.ctl->t;
+    const uint32_t slot_new = (a.Lring - 1u) - (uint32_t)((t + 1ull) % a.Lring);
+
+    ItemState s{};
+    InParamDev p{};
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < NSTAGE; q++) { mbar_init(&full[q], 1); mbar_init(&empty[q], kMacConsumers / 32); }
+        mbar_init(xready, 2);
+        mbar_fence_init();
+        if (blockIdx.x == 0) a.ctl->t_next = t + 1ull;
+    }
+    if (fw >= 0) {
+        // --- voice state of item (inst, fw); rows each voice contributes ---
+        if ((uint32_t)fw < a.n_in) {
+            const uint32_t item = inst * a.n_in + fw;
+            p = a.par[item];
+            s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
+            if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+            if ((uint32_t)lane < a.nv) {
+                uint32_t nk = 0, sl = 0;
+                if ((s.active >> lane) & 1u) {
+                    unsigned long long st0 = 0;
+#pragma unroll
+                    for (int q = 0; q < kMaxVoices; q++) { if (q == lane) { st0 = s.start[q]; sl = s.slot[q]; } }
+                    const long long cnt = (long long)(t + 1ull) - (long long)(st0 + 1ull) + 1;
+                    nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
+                }
+                s_nk[fw * a.nv + lane] = nk;
+                s_slot[fw * a.nv + lane] = sl;
+            }
+            if (lane < NOUT) s_pan[fw][lane] = pan_gain(p.panWet, lane, NOUT);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (uint32_t q = 0; q < 4; q++) { s_rowstart[q] = acc; acc += q < ns ? s_nk[q] : 0u; }
+        s_rowstart[4] = acc;
+    }
+    __syncthreads();
+    const uint32_t total = s_rowstart[4];
+    const uint32_t boundary = a.n_in > 1 ? s_rowstart[a.nv] : total;
+    const int n_iter = (int)((total + KC - 1) / KC);
+
+    if (fw >= 0) {
+        // ===== FFT warps: forward transform of every audible voice of input fw =====
+        if ((uint32_t)fw < a.n_in) {
+            const uint32_t item = inst * a.n_in + fw;
+            const uint32_t pd = a.par[inst * a.n_in].predelay;  // input 0's, conv.cu:412,415
+            WarpFft<R> f;
+            f.init(a.twM);
+            const uint32_t mask = a.ring_len - 1;
+            const float *x = a.in + (size_t)item * B;
+            const uint32_t base = (uint32_t)((t * (unsigned long long)B) & mask);
+            const uint32_t prev = (base - B) & mask;
+            const uint32_t off = ((lane < 16) ? prev : base) + 2 * R * (lane & 15);
+#pragma unroll 1
+            for (uint32_t v = 0; v < a.nv; v++) {
+                if (!((s.active >> v) & 1u)) continue;
+                float cv = 0.f;
+#pragma unroll
+                for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
+                const float gain = cv * p.level;
+                float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
+                if ((s.fresh >> v) & 1u) {
+                    for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < R; j++) ring[(base + kMaxPredelay + lane + 32 * j) & mask] = 0.f;
+                float2 z[R];
+                if (pd == 0) {
+                    if constexpr (R == 1) {
+                        float2 q = *reinterpret_cast<const float2 *>(ring + off);
+                        if (lane >= 16) {
+                            const float2 xi = *reinterpret_cast<const float2 *>(x + 2 * (lane & 15));
+                            q.x = fmaf(gain, xi.x, q.x); q.y = fmaf(gain, xi.y, q.y);
+                            *reinterpret_cast<float2 *>(ring + off) = q;
+                        }
+                        z[0] = q;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < R / 2; j++) {
+                            float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
+                            if (lane >= 16) {
+                                const float4 xi = *reinterpret_cast<const float4 *>(x + 2 * R * (lane & 15) + 4 * j);
+                                q.x = fmaf(gain, xi.x, q.x); q.y = fmaf(gain, xi.y, q.y);
+                                q.z = fmaf(gain, xi.z, q.z); q.w = fmaf(gain, xi.w, q.w);
+                                *reinterpret_cast<float4 *>(ring + off + 4 * j) = q;
+                            }
+                            z[2 * j] = make_float2(q.x, q.y);
+                            z[2 * j + 1] = make_float2(q.z, q.w);
+                        }
+                    }
+                } else {
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < R; j++) {
+                        const int n = lane + 32 * j;
+                        ring[(base + pd + n) & mask] += gain * __ldg(&x[n]);
+                    }
+                    __syncwarp();
+                    if constexpr (R == 1) {
+                        z[0] = *reinterpret_cast<const float2 *>(ring + off);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < R / 2; j++) {
+                            const float4 q = *reinterpret_cast<const float4 *>(ring + off + 4 * j);
+                            z[2 * j] = make_float2(q.x, q.y);
+                            z[2 * j + 1] = make_float2(q.z, q.w);
+                        }
+                    }
+                }
+                f.forward(z);
+                f.split_r2c(z, a.tw2M);
+                float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot_new) * B;
+                float2 *xs = xnew + (size_t)(fw * a.nv + v) * B;
+#pragma unroll
+                for (int d = 0; d < R; d++) { dst[f.c + 32 * d] = z[d]; xs[f.c + 32 * d] = z[d]; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xready);  // both FFT warps arrive, with or without work
+    } else if (warp == kMacConsumers / 32) {
+        // ===== producer warp: rows newest-last; the newest row's X comes from the FFT warps =====
+        const uint64_t pol = a.stream_hint ? l2_policy_evict_first() : l2_policy_evict_last();
+        for (int it = 0; it < n_iter; it++) {
+            const int st = it % NSTAGE;
+            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            if (it >= NSTAGE) mbar_wait(&empty[st], ph ^ 1u);
+            const int rows = min(KC, (int)total - it * KC);
+            // every lane owns at most one copy per round; count the bytes first
+            uint32_t my_bytes = 0;
+            for (int cidx = lane; cidx < rows * NARR; cidx += 32) {
+                const int r = cidx / NARR, w = cidx % NARR;
+                const uint32_t rho = it * KC + r;
+                uint32_t sidx = 0;
+#pragma unroll
+                for (int q = 1; q < 4; q++) sidx += (rho >= s_rowstart[q]) ? 1u : 0u;
+                const uint32_t k = s_nk[sidx] - 1u - (rho - s_rowstart[sidx]);
+                if (!(w == 0 && k == 0)) my_bytes += Cfg::ARR_BYTES;
+            }
+            const uint32_t bytes = __reduce_add_sync(kFull, my_bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&full[st], bytes);
+            __syncwarp();
+            for (int cidx = lane; cidx < rows * NARR; cidx += 32) {
+                const int r = cidx / NARR, w = cidx % NARR;
+                const uint32_t rho = it * KC + r;
+                uint32_t sidx = 0;
+#pragma unroll
+                for (int q = 1; q < 4; q++) sidx += (rho >= s_rowstart[q]) ? 1u : 0u;
+                const uint32_t k = s_nk[sidx] - 1u - (rho - s_rowstart[sidx]);
+                const float2 *src;
+                if (w == 0) {
+                    if (k == 0) continue;
+                    src = a.X + ((size_t)(inst * ns + sidx) * a.Lring + (slot_new + k) % a.Lring) * B;
+                } else {
+                    src = a.H + (((size_t)s_slot[sidx] * NOUT + (w - 1)) * a.P + k) * B;
+                }
+                tma_load_1d(stage + ((size_t)(st * KC + r) * NARR + w) * LR, src, Cfg::ARR_BYTES, &full[st], pol);
+            }
+        }
+    }
+
+    float4 acc[NOUT], y[NOUT];
+    float2 e0[NOUT], y0[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) { acc[o] = y[o] = make_float4(0.f, 0.f, 0.f, 0.f); e0[o] = y0[o] = make_float2(0.f, 0.f); }
+    if (tid < kMacConsumers) {
+        const int q = tid % LR, g = tid / LR;
+        const bool bin0 = q == 0;
+        bool second = false, xwaited = false;
+        for (int it = 0; it < n_iter; it++) {
+            const int st = it % NSTAGE;
+            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            const int rows = min(KC, (int)total - it * KC);
+            mbar_wait(&full[st], ph);
+            if (g < rows) {
+                const uint32_t rho = it * KC + g;
+                uint32_t sidx = 0;
+#pragma unroll
+                for (int qq = 1; qq < 4; qq++) sidx += (rho >= s_rowstart[qq]) ? 1u : 0u;
+                const uint32_t k = s_nk[sidx] - 1u - (rho - s_rowstart[sidx]);
+                if (!second && rho >= boundary) {
+                    second = true;
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) {
+                        const float pan = s_pan[0][o];
+                        y[o].x = pan * acc[o].x; y[o].y = pan * acc[o].y; y[o].z = pan * acc[o].z; y[o].w = pan * acc[o].w;
+                        y0[o].x = pan * e0[o].x; y0[o].y = pan * e0[o].y;
+                        acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        e0[o] = make_float2(0.f, 0.f);
+                    }
+                }
+                const float4 *row = stage + ((size_t)(st * KC + g) * NARR) * LR + q;
+                float4 x;
+                if (k == 0) {
+                    if (!xwaited) { mbar_wait(xready, 0); xwaited = true; }
+                    x = reinterpret_cast<const float4 *>(xnew + (size_t)sidx * B)[q];
+                } else x = row[0];
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) {
+                    const float4 h = row[(1 + o) * LR];
+                    acc[o].x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc[o].x));
+                    acc[o].y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc[o].y));
+                    acc[o].z = fmaf(x.z, h.z, fmaf(-x.w, h.w, acc[o].z));
+                    acc[o].w = fmaf(x.z, h.w, fmaf(x.w, h.z, acc[o].w));
+                    if (bin0) { e0[o].x = fmaf(x.x, h.x, e0[o].x); e0[o].y = fmaf(x.y, h.y, e0[o].y); }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) {
+            const float pan = s_pan[second ? 1 : 0][o];
+            y[o].x = fmaf(pan, acc[o].x, y[o].x); y[o].y = fmaf(pan, acc[o].y, y[o].y);
+            y[o].z = fmaf(pan, acc[o].z, y[o].z); y[o].w = fmaf(pan, acc[o].w, y[o].w);
+            y0[o].x = fmaf(pan, e0[o].x, y0[o].x); y0[o].y = fmaf(pan, e0[o].y, y0[o].y);
+        }
+    }
+
+    // ===== cross-group reduction into Ys (fixed order) =====
+    __syncthreads();  // every TMA write has landed and been consumed: stage memory is free
+    float4 *red = reinterpret_cast<float4 *>(smem);                  // [G][NOUT][LR]
+    float2 *red0 = reinterpret_cast<float2 *>(red + G * NOUT * LR);  // [G][NOUT]
+    if (tid < kMacConsumers) {
+        const int q = tid % LR, g = tid / LR;
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) {
+            red[(g * NOUT + o) * LR + q] = y[o];
+            if (q == 0) red0[g * NOUT + o] = y0[o];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NOUT * LR; idx += kFusedThreads) {
+        const int o = idx / LR, q = idx % LR;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 s0 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const float4 v = red[(g * NOUT + o) * LR + q];
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            const float2 u = red0[g * NOUT + o];
+            s0.x += u.x; s0.y += u.y;
+        }
+        if (q == 0) { sum.x = s0.x; sum.y = s0.y; }
+        reinterpret_cast<float4 *>(Ys + (size_t)o * B)[q] = sum;
+    }
+    __syncthreads();
+
+    // ===== FFT warps: inverse transform + output ring + clamp + dry mix of output fw =====
+    if (fw >= 0 && fw < NOUT) {
+        const int o = fw;
+        const uint32_t item = inst * NOUT + o;
+        WarpFft<R> f;
+        f.init(a.twM);
+        float2 v[R];
+#pragma unroll
+        for (int d = 0; d < R; d++) v[d] = Ys[(size_t)o * B + f.c + 32 * d];
+        constexpr int NV4 = R >= 2 ? R / 2 : 1;
+        float4 accv[NV4], xa[NV4], xb[NV4];
+        float dg[2] = {0.f, 0.f};
+        const int n0 = 2 * R * (lane & 15);
+        float *dst = a.out + (size_t)item * B + n0;
+        float *accp = nullptr;
+        const bool raw = a.raw_wet != 0;
+        if (lane >= 16) {
+            if (!raw) {
+                const InParamDev p0 = a.par[inst * a.n_in];
+                const InParamDev p1 = a.par[inst * a.n_in + (a.n_in - 1)];
+                dg[0] = p0.dry * pan_gain(p0.panDry, o, NOUT) * p0.level;
+                dg[1] = a.n_in > 1 ? p1.dry * pan_gain(p1.panDry, o, NOUT) * p1.level : 0.f;
+            }
+            const float *x0 = a.in + ((size_t)inst * a.n_in) * B + n0;
+            const float *x1 = x0 + (a.n_in > 1 ? B : 0);
+            if (a.accring) accp = a.accring + (size_t)item * a.acc_len + (uint32_t)((t * (unsigned long long)B) & (a.acc_len - 1)) + n0;
+            if constexpr (R == 1) {
+                const float2 q0 = *reinterpret_cast<const float2 *>(x0), q1 = *reinterpret_cast<const float2 *>(x1);
+                xa[0] = make_float4(q0.x, q0.y, 0.f, 0.f);
+                xb[0] = make_float4(q1.x, q1.y, 0.f, 0.f);
+                accv[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (accp) { const float2 q = *reinterpret_cast<const float2 *>(accp); accv[0].x = q.x; accv[0].y = q.y; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV4; j++) {
+                    xa[j] = *reinterpret_cast<const float4 *>(x0 + 4 * j);
+                    xb[j] = *reinterpret_cast<const float4 *>(x1 + 4 * j);
+                    accv[j] = accp ? *reinterpret_cast<const float4 *>(accp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        f.split_c2r(v, a.tw2M);
+        f.inverse(v);
+        if (lane >= 16) {
+            auto clampf = [raw](float w) { return raw ? w : fminf(fmaxf(w, -1.0f), 1.0f); };
+            if constexpr (R == 1) {
+                float2 yy = make_float2(clampf(v[0].x + accv[0].x), clampf(v[0].y + accv[0].y));
+                yy.x = fmaf(dg[0], xa[0].x, fmaf(dg[1], xb[0].x, yy.x));
+                yy.y = fmaf(dg[0], xa[0].y, fmaf(dg[1], xb[0].y, yy.y));
+                *reinterpret_cast<float2 *>(dst) = yy;
+                if (accp) *reinterpret_cast<float2 *>(accp) = make_float2(0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV4; j++) {
+                    float4 yy = make_float4(clampf(v[2 * j].x + accv[j].x), clampf(v[2 * j].y + accv[j].y),
+                                            clampf(v[2 * j + 1].x + accv[j].z), clampf(v[2 * j + 1].y + accv[j].w));
+                    yy.x = fmaf(dg[0], xa[j].x, fmaf(dg[1], xb[j].x, yy.x));
+                    yy.y = fmaf(dg[0], xa[j].y, fmaf(dg[1], xb[j].y, yy.y));
+                    yy.z = fmaf(dg[0], xa[j].z, fmaf(dg[1], xb[j].z, yy.z));
+                    yy.w = fmaf(dg[0], xa[j].w, fmaf(dg[1], xb[j].w, yy.w));
+                    *reinterpret_cast<float4 *>(dst + 4 * j) = yy;
+                    if (accp) *reinterpret_cast<float4 *>(accp + 4 * j) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // long tiers of the non-uniform partitioning (block S = 256 * 2^s_log, fired every m periods,
 // AFTER the period's output has been produced: k_inverse has already advanced ctl->t)
 // ------------------------------------------------------------------------------------------

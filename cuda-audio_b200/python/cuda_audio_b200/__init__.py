@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("mac_bytes", C.c_uint64), ("mac_bytes_amortized", C.c_uint64), ("partitions", C.c_uint32),
                 ("mac_split", C.c_uint32), ("device_bytes", C.c_uint64), ("n_tiers", C.c_uint32),
                 ("tier_block", C.c_uint32 * CA_MAX_TIERS), ("tier_parts", C.c_uint32 * CA_MAX_TIERS),
-                ("tier_offset", C.c_uint32 * CA_MAX_TIERS), ("reserved", C.c_uint32)]
+                ("tier_offset", C.c_uint32 * CA_MAX_TIERS), ("tier0_fused", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

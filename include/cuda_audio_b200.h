@@ -117,7 +117,7 @@ typedef struct ca_stats {
     uint64_t device_bytes;  /* device memory held by the engine                         */
     uint32_t n_tiers;
     uint32_t tier_block[CA_MAX_TIERS], tier_parts[CA_MAX_TIERS], tier_offset[CA_MAX_TIERS];
-    uint32_t reserved;
+    uint32_t tier0_fused;   /* 1: tier 0 runs as one fused kernel; its time is reported in mac_us */
 } ca_stats;
 
 int ca_api_version(void);
