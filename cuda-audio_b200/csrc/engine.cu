@@ -650,7 +650,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     {
         const char *fz = getenv("CA_FUSE");
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
-        e->fused = e->tiers.size() > 1 && fn && e->tiers[0].n_split == 1 && e->tiers[0].tiles == 1 && e->n_in * e->nv <= 4 && !(fz && fz[0] == '0');
+        e->fused = e->tiers.size() > 1 && fn && e->tiers[0].n_split == 1 && e->tiers[0].tiles == 1 && e->n_in * e->nv <= 4 &&
+                   (fz ? fz[0] == '1' : e->n_inst <= 16);  // measured: -2 us p50 for one instance, but 178 vs 132 us at 4096 instances
+                                                            // (2 CTAs/SM cannot hide the per-instance FFT latency chain)
         if (e->fused) {
             e->fused_smem = e->n_out == 1 ? (e->R == 8 ? FusedCfg<8, 1>::SMEM_BYTES : e->R == 4 ? FusedCfg<4, 1>::SMEM_BYTES : e->R == 2 ? FusedCfg<2, 1>::SMEM_BYTES : FusedCfg<1, 1>::SMEM_BYTES)
                                           : (e->R == 8 ? FusedCfg<8, 2>::SMEM_BYTES : e->R == 4 ? FusedCfg<4, 2>::SMEM_BYTES : e->R == 2 ? FusedCfg<2, 2>::SMEM_BYTES : FusedCfg<1, 2>::SMEM_BYTES);

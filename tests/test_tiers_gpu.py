@@ -155,3 +155,35 @@ def test_staggered_batch_more_instances_than_tier_period():
         for s in (0, 5, 10):
             truth = O.engine_truth(xx[s], [hs[s], hs[s]], [dict(wet=1.0)] * 2)
             assert O.rel_l2(y2[s, 0], truth[0][n:]) < 5e-6, (flags, s)
+
+
+def test_fused_tier0_kernel_matches_three_kernel_path(monkeypatch):
+    """k_fused0 (forward || TMA streaming -> MAC -> inverse in one CTA per instance, default for small
+    batches) against the k_forward / k_mac / k_inverse chain, including a cross-fade and predelay."""
+    m = ca()
+    B, L, K = 128, 128 * 8 + 1024 * 5, 3
+    tiers = [(128, 8), (1024, 0)]
+    irs = [irs2x2(L, 4000 + 8 * s) for s in range(K)]
+    n = B * 300
+    x = np.stack([np.stack([O.synth_audio(n, 5000 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(fuse):
+        monkeypatch.setenv("CA_FUSE", fuse)
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, max_voices=2) as e:
+            assert e.stats().tier0_fused == int(fuse)
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=0.9, dry=0.2, predelay=33 * s, panWet=0.1 * s)
+                    e.set_glide(s, i, 0.9)
+            out = np.empty((K, 2, n), np.float32)
+            for t in range(n // B):
+                if t == 120:
+                    e.set_params(2, 1, select=4, wet=0.9, dry=0.2, predelay=66, panWet=0.2, vsteps=20)
+                out[:, :, t * B:(t + 1) * B] = e.process(x[:, :, t * B:(t + 1) * B])
+            return out
+
+    yf, yu = go("1"), go("0")
+    assert O.rel_l2(yf, yu) < 1e-6
+    truth = O.engine_truth(x[1], irs[1], [dict(wet=0.9, dry=0.2, panWet=0.1)] * 2, predelay=33)
+    assert O.rel_l2(yf[1, 0], truth[0]) < 5e-6
