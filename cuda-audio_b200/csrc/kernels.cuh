@@ -1088,15 +1088,28 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const uint32_t mask = a.ring_len - 1;
     const float *ring = a.ring + (size_t)w * a.ring_len;
     const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
-    for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x)
-        *reinterpret_cast<float4 *>(sm + swz(2 * (int)n)) = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
+    // window load, 8 independent float4 loads in flight per thread (the loop is latency-bound otherwise)
+    for (uint32_t n0 = threadIdx.x; n0 < a.S / 2; n0 += 8 * blockDim.x) {
+        float4 r[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t n = n0 + u * blockDim.x;
+            if (n < a.S / 2) r[u] = *reinterpret_cast<const float4 *>(ring + ((start + 4 * n) & mask));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t n = n0 + u * blockDim.x;
+            if (n < a.S / 2) *reinterpret_cast<float4 *>(sm + swz(2 * (int)n)) = r[u];
+        }
+    }
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
     const unsigned long long n_fire = (tend + inst % a.m) / a.m;
     const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
-    for (uint32_t p = threadIdx.x; p < a.S; p += blockDim.x) dst[p] = sm[swz((int)p)];  // position order (fft_cta.cuh)
+    for (uint32_t p = threadIdx.x; p < a.S / 2; p += blockDim.x)  // position order (fft_cta.cuh), 16-byte stores
+        reinterpret_cast<float4 *>(dst)[p] = *reinterpret_cast<const float4 *>(sm + swz(2 * (int)p));
 }
 
 struct TierInvArgs {
@@ -1116,12 +1129,27 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
     const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = a.ctl->t;
-    for (uint32_t k = threadIdx.x; k < a.S; k += blockDim.x) {
-        float2 y = make_float2(0.f, 0.f);
-        const float2 *src = a.Ypart + (((size_t)(blockIdx.x / a.n_out) * a.n_split) * a.n_out + o) * a.S + k;
-        const size_t stride = (size_t)a.n_out * a.S;
-        for (uint32_t sp = 0; sp < a.n_split; sp++) { const float2 q = src[sp * stride]; y.x += q.x; y.y += q.y; }
-        sm[swz((int)k)] = y;  // spectra of the long tiers are stored in position order
+    // sum of the partial spectra (position order), 8 independent float4 loads in flight per thread
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)(blockIdx.x / a.n_out) * a.n_split) * a.n_out + o) * a.S);
+        const size_t stride4 = (size_t)a.n_out * a.S / 2;
+        for (uint32_t n0 = threadIdx.x; n0 < a.S / 2; n0 += 8 * blockDim.x) {
+            float4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t sp = 0; sp < a.n_split; sp++) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t n = n0 + u * blockDim.x;
+                    if (n < a.S / 2) { const float4 q = src[sp * stride4 + n]; r[u].x += q.x; r[u].y += q.y; r[u].z += q.z; r[u].w += q.w; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t n = n0 + u * blockDim.x;
+                if (n < a.S / 2) *reinterpret_cast<float4 *>(sm + swz(2 * (int)n)) = r[u];
+            }
+        }
     }
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_split_c2r(sm, (int)a.S, (int)a.s_log, tw);
@@ -1131,12 +1159,23 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     const uint32_t amask = a.acc_len - 1;
     const uint32_t pos0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask);
     float *acc = a.accring + (size_t)item * a.acc_len;
-    for (uint32_t n = threadIdx.x; n < a.S / 2; n += blockDim.x) {
-        const float2 z = sm[swz((int)(a.S / 2 + n))];
-        float2 *p = reinterpret_cast<float2 *>(acc + ((pos0 + 2 * n) & amask));
-        float2 q = *p;
-        q.x += z.x; q.y += z.y;
-        *p = q;
+    // read-modify-write of the output ring in float4s (S/4 of them), 8 loads in flight per thread
+    for (uint32_t n0 = threadIdx.x; n0 < a.S / 4; n0 += 8 * blockDim.x) {
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t n = n0 + u * blockDim.x;
+            if (n < a.S / 4) q[u] = *reinterpret_cast<const float4 *>(acc + ((pos0 + 4 * n) & amask));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t n = n0 + u * blockDim.x;
+            if (n < a.S / 4) {
+                const float4 z = *reinterpret_cast<const float4 *>(sm + swz((int)(a.S / 2 + 2 * n)));
+                q[u].x += z.x; q[u].y += z.y; q[u].z += z.z; q[u].w += z.w;
+                *reinterpret_cast<float4 *>(acc + ((pos0 + 4 * n) & amask)) = q[u];
+            }
+        }
     }
 }
 
