@@ -39,16 +39,18 @@ thread_local std::string g_last_error;
 typedef void (*fwd_fn)(const FwdArgs);
 typedef void (*ir_fn)(const IrArgs);
 typedef void (*mac_fn)(const MacArgs);
+typedef void (*macp_fn)(const MacArgs, const uint32_t, const uint32_t);
 typedef void (*inv_fn)(const InvArgs);
 
-struct MacVariant { mac_fn fn; uint32_t smem; int kc; };
+struct MacVariant { mac_fn fn; uint32_t smem; int kc; macp_fn pfn; uint32_t psmem; };
 
 template <int BT, int NOUT, int MULT, int NSTAGE>
 MacVariant mac_variant()
 {
     constexpr int G = kMacConsumers / (BT / 2);
     using Cfg = MacCfg<BT, NOUT, G * MULT, NSTAGE>;
-    return MacVariant{k_mac<BT, NOUT, G * MULT, NSTAGE>, Cfg::SMEM_BYTES, G * MULT};
+    return MacVariant{k_mac<BT, NOUT, G * MULT, NSTAGE>, Cfg::SMEM_BYTES, G * MULT,
+                      k_mac_p<BT, NOUT, G * MULT, NSTAGE>, MacPCfg<BT, NOUT, G * MULT, NSTAGE>::SMEM_BYTES};
 }
 
 // stage = G*MULT rows of (1 + NOUT) arrays of BT complex; BT = 256, NOUT = 2: 12 KB * MULT
@@ -109,9 +111,11 @@ constexpr uint32_t kIoChunks = 16;  // upper bound; the count used is io_chunks 
 
 struct Tier {
     uint32_t S = 0, m = 1, P = 0, off = 0, s_log = 0, bt = 0, tiles = 1, n_split = 1, Lring = 0;
-    float2 *H = nullptr, *X = nullptr, *Ypart = nullptr, *tw = nullptr;
+    float2 *H = nullptr, *X = nullptr, *Ypart = nullptr, *Ypart2 = nullptr, *tw = nullptr;  // Ypart2: odd periods of the pipelined schedule
     size_t h_bytes = 0, x_bytes = 0;
     MacVariant mac{};
+    uint32_t p_slots = 0;  // resident CTA slots of the persistent MAC (0: schedule disabled)
+    bool p_force = false;
 };
 
 }  // namespace
@@ -140,6 +144,21 @@ struct ca_engine {
     cudaStream_t s_tier[CA_MAX_TIERS] = {};         // side streams: forward FFT + MAC of concurrently firing tiers
     cudaEvent_t fork_ev = nullptr, join_ev[CA_MAX_TIERS] = {};
     cudaEvent_t io_ev[2][kIoChunks + 1] = {};
+    // pipelined batch schedule (run_pipelined): lane C = stream (FFT kernels), lane M = s_mac (MAC kernels)
+    cudaStream_t s_mac = nullptr;
+    cudaEvent_t pf_ev[kIoChunks + 1] = {}, pm_ev[kIoChunks + 1] = {};  // forward done / tier-0 MAC done, per chunk
+    cudaEvent_t ptf_ev[CA_MAX_TIERS] = {}, ptm_ev[CA_MAX_TIERS][2] = {};  // tier forward done / tier MAC done (by period parity)
+    cudaEvent_t pm_tail = nullptr;   // last launch on lane M
+    cudaEvent_t ptinv_ev[CA_MAX_TIERS] = {};  // tier inverse done
+    bool tinv_pending[CA_MAX_TIERS] = {};
+    uint64_t pipe_prev_tend = 0;     // period whose long-tier inverse transforms are still to be launched (0: none)
+    bool pipe_used = false;
+    int pipe_mode = 0;               // CA_PIPELINE=1 enables it (measured r01: +5 % device-resident, -8 % end to end: off by default)
+    // CA_PIPE_TRACE=n: print the device timeline (CUDA events around every launch) of periods n, n+1
+    struct TraceEv { const char *name; int lane; cudaEvent_t a, b; };
+    std::vector<TraceEv> trace;
+    uint64_t trace_at = 0;
+    bool tracing = false;
     uint32_t io_chunks = 2;  // measured at 12 288 instances: 2 chunks 1.178 ms, 3: 1.206, 4: 1.237, 8: 1.316 (device-resident 1.124)
     int upload_idx = 0;
     // parameters (host shadow)
@@ -218,6 +237,19 @@ MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
                    e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u, t.m > 1 ? 1u : 0u};
 }
 
+// One MAC launch over `count` instances of tier t.  Batches (n_split == 1 and more work items than
+// resident CTA slots) take the persistent schedule: every CTA gets the same number of work items.
+void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st)
+{
+    const uint32_t n_work = count * t.tiles;
+    if (t.p_slots && t.n_split == 1 && (t.p_force || n_work > t.p_slots)) {
+        const uint32_t per = (n_work + t.p_slots - 1) / t.p_slots;
+        t.mac.pfn<<<(n_work + per - 1) / per, kMacThreads, t.mac.psmem, st>>>(ma, n_work, t.tiles);
+    } else {
+        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, st>>>(ma);
+    }
+}
+
 // instances whose tier-j block closes at the end of period t_end - 1: s = r + i*m, r = (-t_end) mod m
 uint32_t tier_residue(const Tier &t, uint64_t tend) { return (uint32_t)((t.m - tend % t.m) % t.m); }
 uint32_t tier_count(const ca_engine *e, const Tier &t, uint64_t tend)
@@ -255,7 +287,7 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    t0.mac.fn<<<dim3(t0.n_split, t0.tiles, i1 - i0), kMacThreads, t0.mac.smem, e->stream>>>(ma);
+    launch_mac(t0, ma, i1 - i0, e->stream);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
     if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
     else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
@@ -291,7 +323,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
-        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, st>>>(ma);
+        launch_mac(t, ma, count, st);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], st));
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
@@ -353,10 +385,14 @@ void drop_graphs(ca_engine *e)
     e->graphs.clear();
 }
 
+int pipe_drain(ca_engine *e);
+
 // phase 1 of a period: everything the output block depends on
 int run_period(ca_engine *e, const float *d_in, float *d_out)
 {
-    int rc = flush_params(e);
+    int rc = pipe_drain(e);
+    if (rc) return rc;
+    rc = flush_params(e);
     if (rc) return rc;
     const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
     if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
@@ -421,6 +457,202 @@ int run_deferred(ca_engine *e)
                 }
         e->prof_n++;
     }
+    return CA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pipelined batch schedule.  The period's kernels fall into two classes: the MACs stream HBM and
+// barely issue instructions, the FFT kernels (forward, inverse, long-tier transforms) are
+// latency/issue-bound and barely touch HBM.  Run back to back they leave each resource idle half of
+// the time, so batches run them on two lanes that overlap:
+//   lane C (e->stream): fwd0(p) | tier fwd_j(p) | tier inv_j(p-1) | inv0(p)
+//   lane M (e->s_mac) : mac0(p) | tier mac_j(p)
+// fwd0 -> mac0 -> inv0 and tier fwd_j -> mac_j -> inv_j are ordered by events; the long tiers' inverse
+// of period p runs in period p + 1 (its result is first read by inv0(p + 1)), which takes the tier
+// MACs off lane C's critical path.  Lane M kernels get the period count from the host (they run
+// while inv0 advances ctl->t) and the long tiers' partial sums are double-buffered by period parity.
+// Host-driven launches, no graph: a period of a batch is hundreds of microseconds.
+// ------------------------------------------------------------------------------------------
+void trace_mark(ca_engine *e, const char *name, int lane, bool begin)
+{
+    if (!e->tracing) return;
+    cudaStream_t st = lane == 0 ? e->stream : lane == 1 ? e->s_mac : e->s_tier[lane - 1];
+    if (begin) {
+        ca_engine::TraceEv t{name, lane, nullptr, nullptr};
+        cudaEventCreate(&t.a); cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, st);
+        e->trace.push_back(t);
+    } else {
+        cudaEventRecord(e->trace.back().b, st);
+    }
+}
+
+void trace_dump(ca_engine *e)
+{
+    cudaStreamSynchronize(e->s_mac); cudaStreamSynchronize(e->stream);
+    for (auto &st : e->s_tier) cudaStreamSynchronize(st);
+    for (auto &t : e->trace) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e->trace.front().a, t.a);
+        cudaEventElapsedTime(&b, e->trace.front().a, t.b);
+        fprintf(stderr, "trace lane %c %-10s %8.1f .. %8.1f us (%6.1f)\n", "CM23456"[t.lane], t.name, 1e3 * a, 1e3 * b, 1e3 * (b - a));
+    }
+    for (auto &t : e->trace) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    e->trace.clear();
+}
+
+bool use_pipeline(const ca_engine *e)
+{
+    if (e->tiers.size() < 2 || e->fused || !e->s_mac || (e->cfg.flags & (CA_FLAG_PROFILE | CA_FLAG_GRAPH))) return false;
+    return e->pipe_mode == 1;
+}
+
+uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8)); }
+
+// long-tier lanes: inverse transforms of the tiers that fired at `pipe_prev_tend`, in tier order (they
+// accumulate into the same output ring).  e->stream joins them now (drain) or right before inv0.
+int pipe_join_tinv(ca_engine *e)
+{
+    for (size_t j = 1; j < e->tiers.size(); j++)
+        if (e->tinv_pending[j]) {
+            CA_CUDA(cudaStreamWaitEvent(e->stream, e->ptinv_ev[j], 0));
+            e->tinv_pending[j] = false;
+        }
+    return CA_OK;
+}
+
+int pipe_finish_prev(ca_engine *e, bool join_now)
+{
+    const uint64_t tend = e->pipe_prev_tend;
+    e->pipe_prev_tend = 0;
+    size_t prev = 0;
+    for (size_t j = 1; tend && j < e->tiers.size(); j++) {
+        const Tier &t = e->tiers[j];
+        const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
+        if (!count) continue;
+        cudaStream_t st = e->s_tier[j];
+        CA_CUDA(cudaStreamWaitEvent(st, e->ptm_ev[j][tend & 1], 0));
+        if (prev) CA_CUDA(cudaStreamWaitEvent(st, e->ptinv_ev[prev], 0));
+        TierInvArgs ia{(tend & 1) ? t.Ypart2 : t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, tend};
+        trace_mark(e, j == 1 ? "tinv1'" : "tinv2+'", (int)(1 + j), true);
+        k_tier_inverse<<<count * e->n_out, tier_threads(t), t.S * sizeof(float2), st>>>(ia);
+        trace_mark(e, "", (int)(1 + j), false);
+        CA_CUDA(cudaEventRecord(e->ptinv_ev[j], st));
+        e->tinv_pending[j] = true;
+        prev = j;
+        e->launches += 1;
+    }
+    CA_CUDA(cudaGetLastError());
+    return join_now ? pipe_join_tinv(e) : CA_OK;
+}
+
+// everything in flight on lane M becomes a dependency of e->stream (callers then order against / sync e->stream only)
+int pipe_drain(ca_engine *e)
+{
+    if (!e->pipe_used) return CA_OK;
+    const int rc = pipe_finish_prev(e, true);
+    if (rc) return rc;
+    for (size_t j = 1; j < e->tiers.size(); j++) CA_CUDA(cudaStreamWaitEvent(e->stream, e->ptf_ev[j], 0));  // tier lanes: last forward
+    CA_CUDA(cudaStreamWaitEvent(e->stream, e->pm_tail, 0));
+    e->pipe_used = false;
+    return CA_OK;
+}
+
+// one period of a batch; h_src / h_dst: pinned host buffers (ca_process) or nullptr (device-resident)
+int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks, const float *h_src, float *h_dst)
+{
+    if (e->par_dirty.load(std::memory_order_acquire)) {  // parameters change: lane M still reads the old ones
+        const int rc = pipe_drain(e);
+        if (rc) return rc;
+    }
+    int rc = flush_params(e);
+    if (rc) return rc;
+    const uint64_t tend = e->t_host + 1;
+    const Tier &t0 = e->tiers[0];
+    const uint32_t n_alloc = e->n_inst * e->n_in;
+    const size_t in_stride = (size_t)e->n_in * e->B, out_stride = (size_t)e->n_out * e->B;
+    auto cut = [&](uint32_t c) { return (uint32_t)((uint64_t)e->n_active * c / chunks); };
+    e->tracing = e->trace_at && (tend == e->trace_at || tend == e->trace_at + 1);
+    rc = pipe_finish_prev(e, false);  // tier lanes: the previous period's long-tier results (needed by this period's inv0)
+    if (rc) return rc;
+    // the previous period's tier forwards read the time ring this period's fwd0 writes (ahead of them, but
+    // within ring_len of a maximal predelay): order them, they finished long ago
+    for (size_t j = 1; j < e->tiers.size(); j++) CA_CUDA(cudaStreamWaitEvent(e->stream, e->ptf_ev[j], 0));
+    if (h_src)
+        for (uint32_t c = 0; c < chunks; c++) {
+            const uint32_t i0 = cut(c), i1 = cut(c + 1);
+            CA_CUDA(cudaMemcpyAsync(const_cast<float *>(d_in) + i0 * in_stride, h_src + i0 * in_stride, (i1 - i0) * in_stride * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
+            CA_CUDA(cudaEventRecord(e->io_ev[0][c], e->s_in));
+        }
+    for (uint32_t c = 0; c < chunks; c++) {
+        const uint32_t i0 = cut(c), i1 = cut(c + 1);
+        const bool last = c + 1 == chunks;
+        if (h_src) CA_CUDA(cudaStreamWaitEvent(e->stream, e->io_ev[0][c], 0));
+        // lane C: forward transforms of the chunk
+        const uint32_t n_items = (i1 - i0) * e->n_in;
+        FwdArgs fa{d_in, e->d_ring, t0.X, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
+                   n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in};
+        trace_mark(e, "fwd0", 0, true);
+        e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
+        trace_mark(e, "", 0, false);
+        CA_CUDA(cudaEventRecord(e->pf_ev[c], e->stream));
+        // lane M: tier-0 MAC of the chunk
+        CA_CUDA(cudaStreamWaitEvent(e->s_mac, e->pf_ev[c], 0));
+        MacArgs ma = mac_args(e, t0, 1u);
+        ma.inst0 = i0; ma.tend_host = tend;
+        trace_mark(e, "mac0", 1, true);
+        launch_mac(t0, ma, i1 - i0, e->s_mac);
+        trace_mark(e, "", 1, false);
+        CA_CUDA(cudaEventRecord(e->pm_ev[c], e->s_mac));
+        e->launches += 2;
+        if (last)  // every chunk's input is in the time ring: long tiers whose block closes with this period
+            for (size_t j = 1; j < e->tiers.size(); j++) {
+                const Tier &t = e->tiers[j];
+                const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
+                if (!count) continue;
+                TierFwdArgs tf{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, tend};
+                CA_CUDA(cudaStreamWaitEvent(e->s_tier[j], e->pf_ev[c], 0));
+                trace_mark(e, j == 1 ? "tfwd1" : "tfwd2+", (int)(1 + j), true);
+                k_tier_forward<<<count * e->n_in * e->nv, tier_threads(t), t.S * sizeof(float2), e->s_tier[j]>>>(tf);
+                trace_mark(e, "", (int)(1 + j), false);
+                CA_CUDA(cudaEventRecord(e->ptf_ev[j], e->s_tier[j]));
+                CA_CUDA(cudaStreamWaitEvent(e->s_mac, e->ptf_ev[j], 0));
+                MacArgs tm = mac_args(e, t, 0u);
+                tm.inst0 = r; tm.inst_stride = t.m; tm.tend_host = tend;
+                if (tend & 1) tm.Ypart = t.Ypart2;
+                trace_mark(e, j == 1 ? "tmac1" : "tmac2+", 1, true);
+                launch_mac(t, tm, count, e->s_mac);
+                trace_mark(e, "", 1, false);
+                CA_CUDA(cudaEventRecord(e->ptm_ev[j][tend & 1], e->s_mac));
+                e->launches += 2;
+            }
+        if (c == 0) {  // the previous period's long-tier results land in the output ring before any inv0 reads it
+            rc = pipe_join_tinv(e);
+            if (rc) return rc;
+        }
+        // lane C: inverse transform + mix of the chunk
+        CA_CUDA(cudaStreamWaitEvent(e->stream, e->pm_ev[c], 0));
+        InvArgs ia{t0.Ypart, d_in, d_out, e->d_acc, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
+                   t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
+        trace_mark(e, "inv0", 0, true);
+        if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
+        else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
+        trace_mark(e, "", 0, false);
+        e->launches += 1;
+        if (h_dst) {
+            CA_CUDA(cudaEventRecord(e->io_ev[1][c], e->stream));
+            CA_CUDA(cudaStreamWaitEvent(e->s_out, e->io_ev[1][c], 0));
+            CA_CUDA(cudaMemcpyAsync(h_dst + i0 * out_stride, d_out + i0 * out_stride, (i1 - i0) * out_stride * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+        }
+    }
+    CA_CUDA(cudaEventRecord(e->pm_tail, e->s_mac));
+    if (h_dst) CA_CUDA(cudaEventRecord(e->out_ready, e->s_out));
+    CA_CUDA(cudaGetLastError());
+    e->pipe_used = true;
+    e->pipe_prev_tend = tiers_firing(e, tend) ? tend : 0;
+    e->t_host = tend;
+    if (e->tracing && tend == e->trace_at + 1) trace_dump(e);
+    e->tracing = false;
     return CA_OK;
 }
 
@@ -527,6 +759,8 @@ int ca_destroy(ca_engine *e)
 {
     if (!e) return CA_OK;
     cudaSetDevice(e->device);
+    if (e->s_mac) cudaStreamSynchronize(e->s_mac);
+    for (auto &st : e->s_tier) if (st) cudaStreamSynchronize(st);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->s_out) cudaStreamSynchronize(e->s_out);
     drop_graphs(e);
@@ -540,7 +774,14 @@ int ca_destroy(ca_engine *e)
     for (auto &ev : e->join_ev) if (ev) cudaEventDestroy(ev);
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
-    for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.tw); }
+    if (e->s_mac) cudaStreamDestroy(e->s_mac);
+    for (auto &ev : e->pf_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->pm_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ptf_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &row : e->ptm_ev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+    if (e->pm_tail) cudaEventDestroy(e->pm_tail);
+    for (auto &ev : e->ptinv_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
@@ -602,17 +843,30 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
 
-    CA_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    // FFT lanes above the MAC lane: when a (memory-bound) MAC CTA retires, a waiting FFT CTA gets its slot
+    int prio_lo = 0, prio_hi = 0;
+    CA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    if (getenv("CA_PIPE_PRIO") && atoi(getenv("CA_PIPE_PRIO")) == 0) prio_hi = prio_lo;
+    CA_CUDA(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi));
     for (auto &ev : e->ev) CA_CUDA(cudaEventCreate(&ev));
     for (auto &row : e->tev) for (auto &ev : row) CA_CUDA(cudaEventCreate(&ev));
     for (auto &ev : e->upload_done) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-    for (auto &st : e->s_tier) CA_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &st : e->s_tier) CA_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
     CA_CUDA(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
     for (auto &ev : e->join_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &row : e->io_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CA_CUDA(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, prio_lo));
+    for (auto &ev : e->pf_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->pm_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->ptf_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &row : e->ptm_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CA_CUDA(cudaEventCreateWithFlags(&e->pm_tail, cudaEventDisableTiming));
+    for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
+    if (const char *tr = getenv("CA_PIPE_TRACE")) e->trace_at = (uint64_t)atoll(tr);
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
     uint32_t s_max = e->B, reach = e->B;
@@ -629,9 +883,24 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 4 : 1);
         t.mac = mac_pick((int)t.bt, (int)e->n_out, tier_variant);
         CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
+        {
+            // persistent schedule: resident CTA slots of the device (CA_MAC_PERSIST=0 off, =1 always when
+            // n_split == 1, and forces n_split = 1; CA_MAC_SLOTS=n overrides the slot count -- tests force several items per CTA)
+            const char *pe = getenv("CA_MAC_PERSIST");
+            t.p_slots = 0; t.p_force = pe && pe[0] == '1';
+            if (!(pe && pe[0] == '0')) {
+                CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.psmem));
+                int per_sm = 0;
+                CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)t.mac.pfn, kMacThreads, t.mac.psmem));
+                if (const char *cs = getenv("CA_MAC_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(cs)));  // resident MAC CTAs per SM
+                t.p_slots = (uint32_t)std::max(1, per_sm) * (uint32_t)sms;
+                if (const char *sl = getenv("CA_MAC_SLOTS")) t.p_slots = (uint32_t)std::max(1, atoi(sl));
+            }
+        }
         // split of the row list per instance: enough CTAs to cover the SMs when few instances run
         // (latency schedule), 1 when the batch alone fills the machine.
         uint32_t split = j == 0 ? cfg->mac_split : 0;
+        if (t.p_force) split = 1;  // CA_MAC_PERSIST=1 (tests): every tier on the persistent schedule
         if (!split) {
             // few instances: cut the row list so that ~2 CTAs per SM each stream >= 256 KB
             const uint64_t ctas = (uint64_t)e->n_inst * t.tiles;
@@ -688,6 +957,11 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         CA_CUDA(cudaMalloc(&t.Ypart, yp_bytes));
         CA_CUDA(cudaMemsetAsync(t.Ypart, 0, yp_bytes, e->stream));
         e->device_bytes += yp_bytes;
+        if (t.m > 1 && e->pipe_mode != 0) {  // pipelined batch schedule: the long tiers' partial sums live one period longer
+            CA_CUDA(cudaMalloc(&t.Ypart2, yp_bytes));
+            CA_CUDA(cudaMemsetAsync(t.Ypart2, 0, yp_bytes, e->stream));
+            e->device_bytes += yp_bytes;
+        }
         // twiddles, fp64 -> fp32: [W_S^n, n < S | W_2S^k, k < S]
         std::vector<float2> tw(2 * (size_t)t.S);
         for (uint32_t n = 0; n < t.S; n++) {
@@ -785,6 +1059,10 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
     // another stream) must be complete before this engine's non-blocking stream reads it;
     // the reference's prepare() does the same (conv.cu:237)
     if (foreign) CA_CUDA(cudaDeviceSynchronize());
+    {
+        const int rc = pipe_drain(e);  // lane M may still read the IR bank
+        if (rc) return rc;
+    }
     frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
     for (size_t j = 0; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
@@ -883,6 +1161,8 @@ int ca_set_active(ca_engine *e, uint32_t n)
 {
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
     if (n == e->n_active) return CA_OK;
+    const int rc = pipe_drain(e);
+    if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
     e->n_active = n;
     return prewarm_graphs(e);  // not a real-time call: rebuild the graphs for the new batch size now
@@ -893,10 +1173,16 @@ int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nf
     if (!e || !d_in || !d_out) return CA_ERR_INVALID;
     if (nframes != e->B) return CA_ERR_PERIOD;
     const double t0 = now_us();
-    int rc = run_period(e, d_in, d_out);
-    if (rc) return rc;
-    rc = run_deferred(e);
-    if (rc) return rc;
+    int rc;
+    if (use_pipeline(e)) {
+        rc = run_pipelined(e, d_in, d_out, 1, nullptr, nullptr);
+        if (rc) return rc;
+    } else {
+        rc = run_period(e, d_in, d_out);
+        if (rc) return rc;
+        rc = run_deferred(e);
+        if (rc) return rc;
+    }
     record_wall(e, now_us() - t0);
     return CA_OK;
 }
@@ -916,6 +1202,14 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     // the PCIe copies (2 KB per instance and direction) hide behind the kernels of the other chunks.
     const uint32_t chunks = (graph || profile || e->n_active < 512) ? 1u : std::min<uint32_t>(e->io_chunks, e->n_active / 256);
     int rc = CA_OK;
+    if (use_pipeline(e)) {
+        rc = run_pipelined(e, e->d_in, e->d_out, std::max(1u, chunks), src, dst);
+        if (rc) return rc;
+        CA_CUDA(cudaEventSynchronize(e->out_ready));
+        if (dst != out) memcpy(out, e->h_out, out_bytes);
+        record_wall(e, now_us() - t0);
+        return CA_OK;
+    }
     if (chunks <= 1) {
         CA_CUDA(cudaMemcpyAsync(e->d_in, src, in_bytes, cudaMemcpyHostToDevice, e->stream));
         rc = run_period(e, e->d_in, e->d_out);
@@ -955,6 +1249,8 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
 int ca_sync(ca_engine *e)
 {
     if (!e) return CA_ERR_INVALID;
+    const int rc = pipe_drain(e);
+    if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
     return CA_OK;
 }

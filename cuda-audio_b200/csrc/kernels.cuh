@@ -14,6 +14,7 @@
 //
 // Spectra are stored in packed real-FFT format: B complex per partition, bin 0 = (DC, Nyquist).
 #pragma once
+#include <cstdio>
 #include "fft_cta.cuh"
 
 namespace ca {
@@ -295,9 +296,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+#ifdef CA_MBAR_DEBUG
+__device__ int g_mbar_abort = 0;
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#ifdef CA_MBAR_DEBUG  // bounded spin: report the first barrier that never completes instead of hanging the GPU
+    for (unsigned n = 0; !mbar_try_wait(bar, parity); n++) {
+        if (*(volatile int *)&g_mbar_abort) return;
+        if (n > (1u << 14)) {
+            if (atomicExch(&g_mbar_abort, 1) == 0)
+                printf("mbar timeout: block (%d,%d,%d) thread %d bar smem 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+            return;
+        }
+    }
+#else
     while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
@@ -345,6 +360,9 @@ struct MacArgs {
     // the instances run the tier and the load per period is flat.
     uint32_t inst0, inst_stride;
     uint32_t yp_local;  // 1: Ypart is indexed by the launch's instance index (long tiers: only 1/m of the instances fire)
+    // pipelined batch schedule: the launch may run while k_inverse advances ctl->t, so the host passes
+    // the period count itself (0: read ctl->t + t_bias)
+    unsigned long long tend_host;
 };
 
 constexpr int kMacConsumers = 256;
@@ -379,7 +397,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
     const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = a.inst0 + blockIdx.z * a.inst_stride;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
-    const unsigned long long tend = a.ctl->t + a.t_bias;  // periods completed at the end of this tier block
+    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t + a.t_bias;  // periods completed at the end of this tier block
     const uint32_t phase = inst % a.m;
     const unsigned long long n_fire = (tend + phase) / a.m;
 
@@ -545,6 +563,255 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
         float2 *dst = a.Ypart + (((size_t)(a.yp_local ? blockIdx.z : inst) * a.n_split + split) * NOUT + o) * a.S + tile * BT + 2 * q;
         *reinterpret_cast<float4 *>(dst) = sum;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent schedule of the same MAC for batches (n_split == 1): a CTA walks the work list
+// (instance, bin tile) with stride gridDim.x and its producer warp keeps the TMA ring full ACROSS
+// work items, so the pipeline never drains between items (a one-item CTA streams only 96..264 KB:
+// barrier set-up, first-byte latency and the final drain cost ~15 % of the HBM rate, ncu r01).
+// Stage metadata travels with the stage (written before the full barrier is armed).
+// ------------------------------------------------------------------------------------------
+struct MacStageMeta {
+    uint32_t rows;      // rows staged (0: the item has nothing to read yet)
+    uint32_t rho0;      // index of the first staged row in the item's row list
+    uint32_t boundary;  // first row of input 1
+    uint32_t last;      // 1: last stage of the item
+    float pan[4];       // [input][output] wet pan gains
+};
+
+template <int BT, int NOUT, int KC, int NSTAGE>
+struct MacPCfg {
+    using Base = MacCfg<BT, NOUT, KC, NSTAGE>;
+    static constexpr int G = Base::G, LR = Base::LR;
+    static constexpr uint32_t RING_BYTES = NSTAGE * Base::STAGE_BYTES;
+    static constexpr uint32_t BAR_BYTES = 2 * NSTAGE * 8;
+    static constexpr uint32_t META_BYTES = NSTAGE * sizeof(MacStageMeta);
+    static constexpr uint32_t RED_BYTES = (G - 1) * NOUT * LR * 16 + G * NOUT * 8;
+    static constexpr uint32_t SMEM_BYTES = RING_BYTES + BAR_BYTES + META_BYTES + RED_BYTES + 16;
+};
+
+template <int BT, int NOUT, int KC, int NSTAGE>
+__global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const uint32_t n_work, const uint32_t n_tiles)
+{
+    using Cfg = MacCfg<BT, NOUT, KC, NSTAGE>;
+    using PCfg = MacPCfg<BT, NOUT, KC, NSTAGE>;
+    constexpr int NARR = Cfg::NARR, LR = Cfg::LR, G = Cfg::G;
+    static_assert(NOUT <= 2, "pan table holds two outputs");
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *stage = reinterpret_cast<float4 *>(smem);  // [NSTAGE][KC][NARR][LR] float4
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + PCfg::RING_BYTES);
+    uint64_t *empty = full + NSTAGE;
+    MacStageMeta *meta = reinterpret_cast<MacStageMeta *>(smem + PCfg::RING_BYTES + PCfg::BAR_BYTES);
+    float4 *red = reinterpret_cast<float4 *>(smem + PCfg::RING_BYTES + PCfg::BAR_BYTES + PCfg::META_BYTES);  // [G-1][NOUT][LR]
+    float2 *red0 = reinterpret_cast<float2 *>(red + (G - 1) * NOUT * LR);                                     // [G][NOUT]
+    __shared__ uint32_t s_rs[kMaxStreams], s_sl[kMaxStreams];  // producer-private: first row / IR slot of every stream
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ns = a.n_in * a.nv;
+    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t + a.t_bias;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMacConsumers / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kMacConsumers / 32) {
+        // ===== producer warp =====
+        const uint64_t pol = a.stream_hint ? l2_policy_evict_first() : l2_policy_evict_last();
+        // raw descriptor of a work item, one stream (lane < ns) / one pan gain (lane < 2 NOUT) per lane;
+        // the loads of item j + 1 are issued before item j is streamed so their latency is hidden
+        struct Raw { uint32_t active, slot; unsigned long long start; float pan; };
+        auto load_raw = [&](uint32_t j) {
+            Raw r{0u, 0u, 0ull, 0.f};
+            const uint32_t inst = a.inst0 + (j / n_tiles) * a.inst_stride;
+            if ((uint32_t)lane < ns) {
+                const uint32_t i = lane / a.nv, v = lane % a.nv;
+                const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + inst * a.n_in + i];
+                r.active = (st.active >> v) & 1u;
+                r.start = st.start[v];
+                r.slot = st.slot[v];
+            }
+            if (lane < 2 * NOUT) {
+                const uint32_t i = lane / NOUT;
+                r.pan = pan_gain(a.par[inst * a.n_in + min(i, a.n_in - 1)].panWet, lane % NOUT, NOUT);
+            }
+            return r;
+        };
+        uint32_t it = 0;
+        Raw cur = load_raw(blockIdx.x), nxt = cur;
+        for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
+            if (j + gridDim.x < n_work) nxt = load_raw(j + gridDim.x);
+            const uint32_t tile = j % n_tiles, inst = a.inst0 + (j / n_tiles) * a.inst_stride;
+            const uint32_t phase = inst % a.m;
+            const unsigned long long n_fire = (tend + phase) / a.m;
+            uint32_t nk = 0;
+            if (cur.active) {  // see k_mac: partitions whose FDL block was built after the voice's (re)start
+                const long long first_fire = (long long)((cur.start + phase + a.m) / a.m);
+                const long long cnt = (long long)n_fire - first_fire + 1 - (long long)a.k_off;
+                nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
+            }
+            uint32_t incl = nk;
+#pragma unroll
+            for (int d = 1; d < kMaxStreams; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const uint32_t excl = incl - nk;
+            __syncwarp();  // every lane has issued the previous item's copies: the row table may change
+            if (lane < kMaxStreams) { s_rs[lane] = excl; s_sl[lane] = cur.slot; }
+            __syncwarp();
+            const uint32_t total = __shfl_sync(kFull, incl, kMaxStreams - 1);
+            const uint32_t boundary = a.nv < kMaxStreams ? __shfl_sync(kFull, excl, a.nv) : total;
+            float pan[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) pan[q] = __shfl_sync(kFull, cur.pan, q < 2 * NOUT ? q : 0);
+            const uint32_t head = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
+            const uint32_t n_iter = max(1u, (total + KC - 1) / KC);
+            for (uint32_t i = 0; i < n_iter; i++, it++) {
+                const uint32_t st = it % NSTAGE;
+                const uint32_t ph = (it / NSTAGE) & 1u;
+                if (it >= NSTAGE) mbar_wait(&empty[st], ph ^ 1u);
+                const uint32_t rows = total > i * KC ? min((uint32_t)KC, total - i * KC) : 0u;
+                if (lane == 0) {
+                    MacStageMeta &m = meta[st];
+                    m.rows = rows; m.rho0 = i * KC; m.boundary = boundary; m.last = (i + 1 == n_iter) ? 1u : 0u;
+                    m.pan[0] = pan[0]; m.pan[1] = pan[1]; m.pan[2] = pan[2]; m.pan[3] = pan[3];
+                    if (rows) mbar_arrive_expect_tx(&full[st], rows * NARR * Cfg::ARR_BYTES);
+                    else mbar_arrive(&full[st]);
+                }
+                __syncwarp();
+                for (uint32_t cidx = lane; cidx < rows * NARR; cidx += 32) {
+                    const uint32_t r = cidx / NARR, w = cidx % NARR;
+                    const uint32_t rho = i * KC + r;
+                    uint32_t s = 0;
+#pragma unroll
+                    for (int q = 1; q < kMaxStreams; q++) s += (rho >= s_rs[q]) ? 1u : 0u;
+                    const uint32_t k = rho - s_rs[s], slot = s_sl[s];
+                    const float2 *src;
+                    if (w == 0) {
+                        const uint32_t pos = (head + a.k_off + k) % a.Lring;
+                        src = a.X + ((size_t)(inst * ns + s) * a.Lring + pos) * a.S + tile * BT;
+                    } else {
+                        src = a.H + (((size_t)slot * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
+                    }
+                    float4 *dst = stage + ((size_t)(st * KC + r) * NARR + w) * LR;
+                    tma_load_1d(dst, src, Cfg::ARR_BYTES, &full[st], pol);
+                }
+            }
+            cur = nxt;
+        }
+    } else {
+        // ===== consumers: thread (g, q) owns bins (2q, 2q+1) of every G-th row =====
+        const int q = tid % LR, g = tid / LR;
+        uint32_t it = 0;
+        for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
+            const uint32_t tile = j % n_tiles, z = j / n_tiles;
+            const bool bin0 = (q == 0) && (tile == 0);
+            float4 acc[NOUT], y[NOUT];
+            float2 e0[NOUT], y0[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) {
+                acc[o] = y[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                e0[o] = y0[o] = make_float2(0.f, 0.f);
+            }
+            bool second = false;
+            uint32_t last;
+            float pan0[NOUT], pan1[NOUT];
+            do {
+                const uint32_t st = it % NSTAGE;
+                const uint32_t ph = (it / NSTAGE) & 1u;
+                mbar_wait(&full[st], ph);
+                const MacStageMeta &m = meta[st];
+                const uint32_t rows = m.rows, rho0 = m.rho0, boundary = m.boundary;
+                last = m.last;
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) { pan0[o] = m.pan[o]; pan1[o] = m.pan[NOUT + o]; }
+#pragma unroll
+                for (int rr = 0; rr < KC / G; rr++) {
+                    const uint32_t r = g + rr * G;
+                    if (r < rows) {
+                        if (!second && rho0 + r >= boundary) {
+                            second = true;
+#pragma unroll
+                            for (int o = 0; o < NOUT; o++) {
+                                const float pan = pan0[o];
+                                y[o].x = pan * acc[o].x; y[o].y = pan * acc[o].y; y[o].z = pan * acc[o].z; y[o].w = pan * acc[o].w;
+                                y0[o].x = pan * e0[o].x; y0[o].y = pan * e0[o].y;
+                                acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                e0[o] = make_float2(0.f, 0.f);
+                            }
+                        }
+                        const float4 *row = stage + ((size_t)(st * KC + r) * NARR) * LR + q;
+                        const float4 x = row[0];
+#pragma unroll
+                        for (int o = 0; o < NOUT; o++) {
+                            const float4 h = row[(1 + o) * LR];
+                            acc[o].x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc[o].x));
+                            acc[o].y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc[o].y));
+                            acc[o].z = fmaf(x.z, h.z, fmaf(-x.w, h.w, acc[o].z));
+                            acc[o].w = fmaf(x.z, h.w, fmaf(x.w, h.z, acc[o].w));
+                            if (bin0) {
+                                e0[o].x = fmaf(x.x, h.x, e0[o].x);
+                                e0[o].y = fmaf(x.y, h.y, e0[o].y);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                it++;
+            } while (!last);
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) {  // fold the last input's sum with its pan (conv.cu:392-401)
+                const float pan = second ? pan1[o] : pan0[o];
+                y[o].x = fmaf(pan, acc[o].x, y[o].x); y[o].y = fmaf(pan, acc[o].y, y[o].y);
+                y[o].z = fmaf(pan, acc[o].z, y[o].z); y[o].w = fmaf(pan, acc[o].w, y[o].w);
+                y0[o].x = fmaf(pan, e0[o].x, y0[o].x); y0[o].y = fmaf(pan, e0[o].y, y0[o].y);
+            }
+            float2 *ybase = a.Ypart + ((size_t)(a.yp_local ? z : a.inst0 + z * a.inst_stride) * NOUT) * a.S + tile * BT + 2 * q;
+            if constexpr (G == 1) {
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) {
+                    if (bin0) { y[o].x = y0[o].x; y[o].y = y0[o].y; }
+                    *reinterpret_cast<float4 *>(ybase + (size_t)o * a.S) = y[o];
+                }
+            } else {
+                // cross-group sum in fixed order (deterministic); consumer-only named barrier
+                if (g > 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) red[((g - 1) * NOUT + o) * LR + q] = y[o];
+                }
+                if (q == 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) red0[g * NOUT + o] = y0[o];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kMacConsumers) : "memory");
+                if (g == 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) {
+                        float4 sum = y[o];
+#pragma unroll
+                        for (int gg = 1; gg < G; gg++) {
+                            const float4 v = red[((gg - 1) * NOUT + o) * LR + q];
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        }
+                        if (bin0) {
+                            float2 s0 = make_float2(0.f, 0.f);
+#pragma unroll
+                            for (int gg = 0; gg < G; gg++) { s0.x += red0[gg * NOUT + o].x; s0.y += red0[gg * NOUT + o].y; }
+                            sum.x = s0.x; sum.y = s0.y;
+                        }
+                        *reinterpret_cast<float4 *>(ybase + (size_t)o * a.S) = sum;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kMacConsumers) : "memory");  // scratch free for the next item
+            }
+        }
+    }
+    __syncthreads();  // the producer warp stays resident until every copy it issued has been consumed
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1071,6 +1338,7 @@ struct TierFwdArgs {
     const float2 *twM, *tw2M;
     uint32_t n_items_alloc, n_in, nv, Lring, ring_len, S, s_log, m, B;
     uint32_t inst0, inst_stride;  // firing instances: inst0 + i * inst_stride
+    unsigned long long tend_host;  // see MacArgs
 };
 
 // one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
@@ -1082,7 +1350,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     const uint32_t inst = a.inst0 + (blockIdx.x / per) * a.inst_stride;
     const uint32_t item = inst * a.n_in + (blockIdx.x % per) / a.nv, v = blockIdx.x % a.nv;
     const uint32_t w = item * a.nv + v;
-    const unsigned long long tend = a.ctl->t;
+    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
     const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
     if (!((st.active >> v) & 1u)) return;
     const uint32_t mask = a.ring_len - 1;
@@ -1119,6 +1387,7 @@ struct TierInvArgs {
     const float2 *twM, *tw2M;
     uint32_t n_split, n_out, S, s_log, B, off, acc_len;
     uint32_t inst0, inst_stride;
+    unsigned long long tend_host;  // see MacArgs
 };
 
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
@@ -1128,7 +1397,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs
     __shared__ CtaTw tw;
     const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
     const uint32_t item = inst * a.n_out + o;
-    const unsigned long long tend = a.ctl->t;
+    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
     // sum of the partial spectra (position order), 8 independent float4 loads in flight per thread
     {
         const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)(blockIdx.x / a.n_out) * a.n_split) * a.n_out + o) * a.S);

@@ -187,3 +187,123 @@ def test_fused_tier0_kernel_matches_three_kernel_path(monkeypatch):
     assert O.rel_l2(yf, yu) < 1e-6
     truth = O.engine_truth(x[1], irs[1], [dict(wet=0.9, dry=0.2, panWet=0.1)] * 2, predelay=33)
     assert O.rel_l2(yf[1, 0], truth[0]) < 5e-6
+
+
+@pytest.mark.parametrize("slots", ["1", "3"])
+def test_persistent_mac_schedule_matches_one_cta_per_item(monkeypatch, slots):
+    """k_mac_p (batches: a CTA walks several (instance, bin tile) work items and its TMA ring stays
+    full across them) against k_mac (one CTA per item): same partial sums in the same order, so the
+    output must agree to the last bit -- through a cross-fade (row lists of different lengths per
+    instance, a second voice), staggered long tiers, and instances that have nothing to read yet."""
+    m = ca()
+    B, K = 64, 11
+    tiers = [(64, 8), (512, 3), (2048, 0)]
+    L = 64 * 8 + 512 * 3 + 2048 * 2 - 100
+    irs = [irs2x2(L, 9000 + 8 * s) for s in range(K)]
+    n = B * 200
+    x = np.stack([np.stack([O.synth_audio(n, 9500 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(persist, tr):
+        monkeypatch.setenv("CA_MAC_PERSIST", persist)
+        monkeypatch.setenv("CA_MAC_SLOTS", slots)
+        monkeypatch.setenv("CA_FUSE", "0")
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tr, max_voices=2, mac_split=1) as e:
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=0.8, dry=0.1, predelay=7 * s, panWet=0.05 * s - 0.2)
+                    e.set_glide(s, i, 0.8)
+            out = np.empty((K, 2, n), np.float32)
+            for t in range(n // B):
+                if t == 90:
+                    e.set_params(4, 0, select=3, wet=0.8, dry=0.1, predelay=28, panWet=0.0, vsteps=30)
+                out[:, :, t * B:(t + 1) * B] = e.process(x[:, :, t * B:(t + 1) * B])
+            return out
+
+    for tr in (tiers, None):
+        yp, y1 = go("1", tr), go("0", tr)
+        assert np.array_equal(yp, y1), (tr, O.rel_l2(yp, y1))
+        truth = O.engine_truth(x[2], irs[2], [dict(wet=0.8, dry=0.1, panWet=-0.1)] * 2, predelay=14)
+        assert O.rel_l2(yp[2, 1], truth[1]) < 5e-6
+
+
+def test_pipelined_batch_schedule_matches_sequential(monkeypatch):
+    """run_pipelined (batches: FFT kernels and MAC kernels on two overlapping lanes, the long tiers'
+    inverse transforms one period late, partial sums double-buffered) against the sequential schedule:
+    same kernels on the same data, so bit-identical -- host path, device path, a cross-fade, a change
+    of the active count mid-run and an IR load while the pipeline is in flight."""
+    import torch
+    m = ca()
+    B, K = 64, 11
+    tiers = [(64, 8), (512, 3), (2048, 0)]
+    L = 64 * 8 + 512 * 3 + 2048 * 2 - 100
+    irs = [irs2x2(L, 9100 + 8 * s) for s in range(K)]
+    n = B * 150
+    x = np.stack([np.stack([O.synth_audio(n, 9700 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(pipe, device_path):
+        monkeypatch.setenv("CA_PIPELINE", pipe)
+        monkeypatch.setenv("CA_FUSE", "0")
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K + 1, tiers=tiers, max_voices=2) as e:
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=0.8, dry=0.1, predelay=5 * s, panWet=0.05 * s - 0.2)
+                    e.set_glide(s, i, 0.8)
+            out = np.zeros((K, 2, n), np.float32)
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.empty(K, 2, B, device="cuda")
+            for t in range(n // B):
+                if t == 60:
+                    e.set_params(4, 0, select=3, wet=0.8, dry=0.1, predelay=20, panWet=0.0, vsteps=30)
+                if t == 70:
+                    e.load_ir(2 * K, irs[0][0][0], irs[0][0][1])
+                if t == 100:
+                    e.set_active(7)
+                k = e.n_active
+                if device_path:
+                    xb = xd[:k, :, t * B:(t + 1) * B].contiguous()
+                    torch.cuda.synchronize()
+                    e.process_device(xb.data_ptr(), yd.data_ptr())
+                    e.sync()
+                    out[:k, :, t * B:(t + 1) * B] = yd[:k].cpu().numpy()
+                else:
+                    out[:k, :, t * B:(t + 1) * B] = e.process(x[:k, :, t * B:(t + 1) * B])
+            return out
+
+    ref = go("0", False)
+    for device_path in (False, True):
+        y = go("1", device_path)
+        assert np.array_equal(y, ref), (device_path, O.rel_l2(y, ref))
+    truth = O.engine_truth(x[2], irs[2], [dict(wet=0.8, dry=0.1, panWet=-0.1)] * 2, predelay=10)
+    assert O.rel_l2(ref[2, 1], truth[1]) < 5e-6
+
+
+def test_pipelined_chunked_host_path_large_batch(monkeypatch):
+    """600 instances (two host-pipeline chunks, every tier-residue class populated): pipelined against
+    sequential through ca_process, and instance 0 / 599 against the fp64 oracle."""
+    m = ca()
+    B, K = 32, 600
+    tiers = [(32, 8), (256, 3), (1024, 0)]
+    L = 32 * 8 + 256 * 3 + 1024 * 2 - 30
+    bank = [[O.synth_ir(L, FS, 9900 + 2 * b + o) for o in range(2)] for b in range(4)]
+    n = B * 100
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((K, 2, n)) * 0.1).astype(np.float32)
+
+    def go(pipe):
+        monkeypatch.setenv("CA_PIPELINE", pipe)
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=4, tiers=tiers, flags=m.FLAG_STREAMING) as e:
+            for b in range(4):
+                e.load_ir(b, bank[b][0], bank[b][1])
+            for s in range(K):
+                for i in range(2):
+                    e.set_params(s, i, select=(s + i) % 4, wet=1.0, dry=0.0)
+                    e.set_glide(s, i, 1.0)
+            return e.render(x)
+
+    y1, y0 = go("1"), go("0")
+    assert np.array_equal(y1, y0), O.rel_l2(y1, y0)
+    for s in (0, 599):
+        truth = O.engine_truth(x[s], [bank[s % 4], bank[(s + 1) % 4]], [dict(wet=1.0)] * 2)
+        assert O.rel_l2(y1[s, 0], truth[0]) < 5e-6

@@ -21,7 +21,7 @@ dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 n = torch.arange(L, device=dev, dtype=torch.float32)
 env = torch.exp(-6.91 * n / (0.8 * L))
-flags = ca.FLAG_PROFILE | (ca.FLAG_STREAMING if K >= 16 else 0)
+flags = (0 if os.environ.get('CA_NOPROFILE') else ca.FLAG_PROFILE) | (ca.FLAG_STREAMING if K >= 16 else 0)
 t0 = time.time()
 e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split, tiers=tiers, max_voices=nvoices,
               tier_growth=int(os.environ.get('CA_TIER_GROWTH', '0')), tier_max_block=int(os.environ.get('CA_TIER_MAXBLOCK', '0')))
@@ -50,6 +50,20 @@ for _ in range(periods):
 e.sync()
 dt = (time.time() - t0) / periods
 st = e.stats()
+if os.environ.get('CA_NOPROFILE'):
+    pin, pout = ca.PinnedArray((K, 2, B)), ca.PinnedArray((K, 2, B))
+    pin.array[...] = x.cpu().numpy()
+    for _ in range(20):
+        e.process_raw(pin.ptr, pout.ptr)
+    t0 = time.time()
+    for _ in range(periods):
+        e.process_raw(pin.ptr, pout.ptr)
+    e.sync()
+    dte = (time.time() - t0) / periods
+    print(f"K={K} device wall/period={dt * 1e6:.1f}us rt_channels={K * (B / fs) / dt:.0f} | e2e {dte * 1e6:.1f}us rt_channels={K * (B / fs) / dte:.0f} "
+          f"persist={os.environ.get('CA_MAC_PERSIST', 'auto')} ctas={os.environ.get('CA_MAC_CTAS', '-')} pipeline={os.environ.get('CA_PIPELINE', 'auto')} "
+          f"y_rms={float(y.pow(2).mean().sqrt()):.4f}/{float((pout.array.astype('f8') ** 2).mean() ** 0.5):.4f}", flush=True)
+    sys.exit(0)
 gbs = st.mac_bytes / (st.mac_us * 1e-6) / 1e9
 print(f"tiers={list(st.tier_block[:st.n_tiers])}x{list(st.tier_parts[:st.n_tiers])} dev_bytes={st.device_bytes/1e9:.1f}GB total={st.total_us:.1f} fwd0={st.fwd_us:.1f} mac0={st.mac_us:.1f} inv0={st.inv_us:.1f} tfwd={st.tier_fwd_us:.1f} tmac={st.tier_mac_us:.1f} tinv={st.tier_inv_us:.1f} bytes/period={st.mac_bytes_amortized/1e9:.2f}GB")
 print(f"variant={os.environ.get('CA_MAC_VARIANT', '1')} K={K} split={st.mac_split} fwd={st.fwd_us:.1f}us mac={st.mac_us:.1f}us inv={st.inv_us:.1f}us "
