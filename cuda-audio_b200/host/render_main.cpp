@@ -15,6 +15,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <iterator>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -39,6 +41,8 @@ struct Options {
     int bits = 32, device = 0, warmup = 0;
     float wet = -1, dry = -1, level = -1, panWet = -2, panDry = -2;
     long predelay = -1;
+    bool resample = false;
+    unsigned resampleTo = 0;
 };
 
 void usage()
@@ -47,7 +51,8 @@ void usage()
             "usage: ca_render [--settings FILE] [--ir WAV | --synthetic-ir SEC] [--in WAV | --synthetic-in SEC] --out WAV\n"
             "                 [--period N] [--rate HZ] [--fft-size N] [--mono] [--bits 16|24|32] [--device N]\n"
             "                 [--wet X] [--dry X] [--level X] [--pan-wet X] [--pan-dry X] [--predelay N]\n"
-            "                 [--warmup PERIODS] [--json FILE]\n");
+            "                 [--warmup PERIODS] [--json FILE] [--resample]\n"
+            "       ca_render [--resample-to HZ] --dump-wav WAV SCALE OUT.f32 | --dump-settings FILE | --midi-parse FILE\n");
 }
 
 // exponentially decaying Gaussian noise, T60 = 0.8 x length, unit energy
@@ -100,10 +105,33 @@ int main(int argc, char **argv)
         else if (a == "--pan-wet") o.panWet = (float)atof(next());
         else if (a == "--pan-dry") o.panDry = (float)atof(next());
         else if (a == "--predelay") o.predelay = atol(next());
+        else if (a == "--resample") o.resample = true;             // IRs whose rate differs from the run's are converted on load
+        else if (a == "--resample-to") o.resampleTo = (unsigned)atol(next());  // for --dump-wav (give it first)
         else if (a == "--dump-settings") {  // parser check (no GPU needed): one "key=value" line per key, then typed reads
             Settings st;
             try { st.open(next()); } catch (std::exception &e) { fprintf(stderr, "ca_render: %s\n", e.what()); return 1; }
             for (auto &kv : st) printf("%s=%s\n", kv.first.c_str(), kv.second.value.c_str());
+            return 0;
+        } else if (a == "--midi-parse") {   // stream-parser check (no GPU needed): one hex line per complete message
+            std::ifstream f(next(), std::ios::binary);
+            std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            MidiParser parser([](const uint8_t *m, size_t len) { for (size_t k = 0; k < len; k++) printf("%02x%s", m[k], k + 1 == len ? "\n" : " "); });
+            for (size_t k = 0; k < bytes.size(); k += 5) parser.feed(bytes.data() + k, std::min<size_t>(5, bytes.size() - k));  // odd chunking on purpose
+            return 0;
+        } else if (a == "--midi-listen") {  // device-thread check: open PATH, print CC -> parameter changes of a Convolution for SECONDS
+            const char *path = next();
+            const double seconds = atof(next());
+            Convolution c("midi_probe", 1024);
+            RawMidi::Device dev(path);
+            auto &cc = c.cc[0];
+            cc.device = &dev; dev.handler = &c;
+            cc.message = 0xB0; cc.select = 20; cc.predelay = 21; cc.dry = 22; cc.wet = 23; cc.speed = 24; cc.panDry = 25; cc.panWet = 26; cc.level = 27;
+            if (!dev.start()) { fprintf(stderr, "ca_render: %s\n", dev.error.c_str()); return 1; }
+            printf("listening\n"); fflush(stdout);
+            usleep((useconds_t)(seconds * 1e6));
+            dev.stop();
+            printf("{\"predelay\": %zu, \"dry\": %.6f, \"wet\": %.6f, \"speed\": %zu, \"panDry\": %.6f, \"panWet\": %.6f, \"level\": %.6f}\n",
+                   cc.value.predelay, cc.value.dry, cc.value.wet, cc.value.speed, cc.value.panDry, cc.value.panWet, cc.value.level);
             return 0;
         } else if (a == "--dump-wav") {     // decoder check (no GPU needed): header + raw float32 samples to a file
             const char *path = next();
@@ -111,6 +139,7 @@ int main(int argc, char **argv)
             const char *outPath = next();
             WavData w = wav_read(path, scale);
             if (!w.ok()) { fprintf(stderr, "ca_render: %s\n", w.error.c_str()); return 1; }
+            if (o.resampleTo) w = wav_resample(w, o.resampleTo);
             printf("{\"channels\": %u, \"rate\": %u, \"bits\": %u, \"format\": %u, \"frames\": %zu}\n", w.channels, w.sampleRate, w.bitsPerSample, w.audioFormat, w.frames);
             FILE *f = fopen(outPath, "wb");
             if (!f) return 1;
@@ -146,12 +175,18 @@ int main(int argc, char **argv)
         if (count % 2) { fprintf(stderr, "ca_render: conv.count must be a multiple of 2\n"); return 1; }
         numInstances = count / 2;
     }
+    // optional IR sample-rate conversion: --resample (to the run's rate) or `resample <Hz>` in the settings file
+    unsigned irRate = o.resample ? rate : 0;
+    if (!o.settings.empty() && settings.has("resample")) irRate = settings.u32("resample");
     std::vector<std::unique_ptr<Convolution>> inst;
     for (size_t n = 0; n < numInstances; n++) {
         size_t fftSize = o.fftSize ? o.fftSize : CONV_DEFAULT_FFTSIZE;
         if (o.settings.empty() && !o.fftSize) {  // size the IR capacity to the IR (the reference needs a hand-picked fftSize)
             size_t frames = (size_t)((o.synthIr > 0 ? o.synthIr : 1.0) * rate);
-            if (!o.ir.empty()) { WavData probe = wav_read(o.ir, 0.5f); if (probe.ok()) frames = probe.frames; }
+            if (!o.ir.empty()) {
+                WavData probe = wav_read(o.ir, 0.5f);
+                if (probe.ok()) frames = irRate && probe.sampleRate ? (size_t)std::ceil((double)probe.frames * irRate / probe.sampleRate) : probe.frames;
+            }
             fftSize = 1;
             while (fftSize < frames + o.period) fftSize <<= 1;
         }
@@ -188,7 +223,7 @@ int main(int argc, char **argv)
                 std::string path;
                 for (size_t j = 0; std::getline(index, path); j++) {
                     if (path.empty()) continue;
-                    WavFile w(path);
+                    WavFile w(path, irRate);
                     if (!w.error.empty()) { fprintf(stderr, "ca_render: %s\n", w.error.c_str()); return 1; }
                     c->prepare(j, w, o.period);
                 }
@@ -202,7 +237,7 @@ int main(int argc, char **argv)
         }
         if (o.settings.empty()) {
             if (!o.ir.empty()) {
-                WavFile w(o.ir);
+                WavFile w(o.ir, irRate);
                 if (!w.error.empty()) { fprintf(stderr, "ca_render: %s\n", w.error.c_str()); return 1; }
                 c->prepare(0, w, o.period);
             } else {

@@ -1,5 +1,6 @@
 #include "wavfile.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -63,6 +64,52 @@ WavData wav_read(const std::string &path, float scale)
     return w;
 }
 
+namespace {
+double bessel_i0(double x)
+{
+    double sum = 1.0, term = 1.0;
+    for (int k = 1; k < 64; k++) {
+        term *= (x / (2.0 * k)) * (x / (2.0 * k));
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+}  // namespace
+
+WavData wav_resample(const WavData &in, uint32_t toRate)
+{
+    WavData out = in;
+    if (!in.ok() || !toRate || !in.sampleRate || toRate == in.sampleRate) return out;
+    const double ratio = (double)toRate / (double)in.sampleRate;
+    const double fc = std::min(1.0, ratio);        // cutoff relative to the input Nyquist
+    const int zc = 32;                             // zero crossings per side (at the cutoff rate)
+    const double beta = 10.0, i0b = bessel_i0(beta);
+    const double half = zc / fc;                   // half width of the kernel in input samples
+    out.sampleRate = toRate;
+    out.frames = (size_t)std::ceil((double)in.frames * ratio - 1e-9);
+    for (auto &c : out.ch) c.assign(out.frames, 0.0f);
+    std::vector<double> acc(in.ch.size());
+    for (size_t m = 0; m < out.frames; m++) {
+        const double t = (double)m / ratio;        // position in input samples
+        const long n0 = (long)std::ceil(t - half), n1 = (long)std::floor(t + half);
+        double wsum = 0.0;
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (long n = n0; n <= n1; n++) {
+            const double d = (double)n - t, u = d / half;
+            const double win = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - u * u))) / i0b;
+            const double a = M_PI * fc * d;
+            const double w = fc * (std::fabs(a) < 1e-12 ? 1.0 : std::sin(a) / a) * win;
+            wsum += w;
+            if (n < 0 || n >= (long)in.frames) continue;
+            for (size_t c = 0; c < in.ch.size(); c++) acc[c] += w * (double)in.ch[c][(size_t)n];
+        }
+        // normalising by the kernel's own sum makes the DC gain exactly 1 at every output phase
+        for (size_t c = 0; c < in.ch.size(); c++) out.ch[c][m] = (float)(acc[c] / wsum);
+    }
+    return out;
+}
+
 bool wav_write(const std::string &path, const std::vector<std::vector<float>> &planar, uint32_t sampleRate, int bits)
 {
     if (planar.empty() || (bits != 16 && bits != 24 && bits != 32)) return false;
@@ -112,10 +159,14 @@ void WavFile::upload(const float *left, const float *right, size_t frames)
     }
 }
 
-WavFile::WavFile(const std::string &path) : path(path)
+WavFile::WavFile(const std::string &path, uint32_t resampleTo) : path(path)
 {
     WavData w = wav_read(path, 0.5f);  // half scale like wav.cu
     if (!w.ok()) { error = w.error; Log::error("wav", "%s", error.c_str()); return; }
+    if (resampleTo && w.sampleRate && resampleTo != w.sampleRate) {
+        Log::info("wav", "resampling %u -> %u Hz: %s", w.sampleRate, resampleTo, path.c_str());
+        w = wav_resample(w, resampleTo);
+    }
     sampleRate = w.sampleRate;
     Log::info("wav", "IR [%0.2f s] %s", w.sampleRate ? (double)w.frames / w.sampleRate : 0.0, path.c_str());
     const std::vector<float> &L = w.ch[0], &R = w.channels > 1 ? w.ch[1] : w.ch[0];

@@ -26,6 +26,12 @@ struct WavData {
 
 // scale: 1.0 = full scale; 0.5 = the reference's IR convention
 WavData wav_read(const std::string &path, float scale = 1.0f);
+// Band-limited sample-rate conversion (Kaiser-windowed sinc, 32 zero crossings per side, about -100 dB
+// stop band, evaluated in fp64): the shipped IR library is 44.1 kHz while the x86 script runs JACK at
+// 48 kHz (run_x64_86.sh:4); the reference plays such IRs 8.8 % fast / sharp.  Opt-in (`resample = 1`
+// in the settings file, --resample on the harness): off, the reference's behaviour is kept.
+// Gain 1 at DC; output frames = ceil(frames * toRate / fromRate).
+WavData wav_resample(const WavData &in, uint32_t toRate);
 // bits: 16 / 24 (PCM) or 32 (IEEE float)
 bool wav_write(const std::string &path, const std::vector<std::vector<float>> &planar, uint32_t sampleRate, int bits = 32);
 
@@ -37,7 +43,8 @@ public:
     uint32_t sampleRate = 0;
     std::string error;
 
-    explicit WavFile(const std::string &path);
+    // resampleTo: 0 = keep the file's rate (reference behaviour), else convert to that rate on load
+    explicit WavFile(const std::string &path, uint32_t resampleTo = 0);
     // from planar host data (no file): used by the harness for synthetic IRs
     WavFile(const float *left, const float *right, size_t frames, uint32_t sampleRate = 48000);
     ~WavFile();

@@ -163,3 +163,76 @@ def test_live_executable_fails_cleanly_without_libjack(tmp_path):
     assert "cannot start JACK client" in r.stderr or "cannot open JACK client" in r.stderr
     r = subprocess.run([live, str(tmp_path / "missing.txt")], capture_output=True, text=True, stdin=subprocess.DEVNULL)
     assert r.returncode == 1 and "cannot open settings file" in r.stderr
+
+
+def test_resampler_44k1_to_48k_matches_analytic_sines(tmp_path):
+    """wav_resample (opt-in IR sample-rate conversion): two sines below the input
+    Nyquist come out as the same sines at the new rate, DC gain is exactly 1, length = ceil(n*160/147),
+    and a tone above the output band of a DOWN-conversion is removed."""
+    fs0, fs1, n = 44100, 48000, 44100
+    t0 = np.arange(n) / fs0
+    x = 0.4 * np.sin(2 * np.pi * 1000 * t0) + 0.3 * np.sin(2 * np.pi * 15000 * t0 + 0.5) + 0.1
+    p = tmp_path / "a.wav"
+    p.write_bytes(wav_bytes(3, 2, fs0, 32, np.stack([x, -x], axis=1).astype(np.float32).tobytes()))
+    outp = tmp_path / "r.f32"
+    meta = json.loads(subprocess.check_output([RENDER, "--resample-to", str(fs1), "--dump-wav", str(p), "1.0", str(outp)], text=True))
+    assert meta["rate"] == fs1 and meta["frames"] == int(np.ceil(n * fs1 / fs0))
+    y = np.fromfile(outp, np.float32).reshape(2, -1)
+    t1 = np.arange(y.shape[1]) / fs1
+    want = 0.4 * np.sin(2 * np.pi * 1000 * t1) + 0.3 * np.sin(2 * np.pi * 15000 * t1 + 0.5) + 0.1
+    mid = slice(200, y.shape[1] - 200)  # away from the ends, where the kernel sees the file boundary
+    assert np.max(np.abs(y[0, mid] - want[mid])) < 2e-5
+    assert np.max(np.abs(y[1, mid] + want[mid])) < 2e-5
+    # 48 k -> 32 k: a 20 kHz tone is above the new Nyquist and must vanish (> 90 dB down), 1 kHz stays
+    t = np.arange(48000) / 48000
+    z = 0.5 * np.sin(2 * np.pi * 20000 * t) + 0.25 * np.sin(2 * np.pi * 1000 * t)
+    p2 = tmp_path / "b.wav"
+    p2.write_bytes(wav_bytes(3, 1, 48000, 32, z.astype(np.float32).tobytes()))
+    subprocess.check_output([RENDER, "--resample-to", "32000", "--dump-wav", str(p2), "1.0", str(outp)], text=True)
+    d = np.fromfile(outp, np.float32)
+    td = np.arange(d.size) / 32000
+    resid = d[300:-300] - 0.25 * np.sin(2 * np.pi * 1000 * td[300:-300])
+    assert np.max(np.abs(resid)) < 0.5 * 10 ** (-90 / 20)
+
+
+def test_midi_stream_parser(tmp_path):
+    """MidiParser (rawmidi.cpp): running status, real-time bytes inside a message, 2-byte messages,
+    system common, SysEx kept whole, stray data ignored -- midi.cu:3-20,49-51 handles only the
+    3-byte subset and asserts on the rest."""
+    stream = bytes([0x40,                                  # data byte before any status: ignored
+                    0xB0, 20, 64,                          # CC
+                    21, 0xF8, 100,                         # running status, clock byte in the middle
+                    0xC1, 5,                               # program change (2 bytes)
+                    6,                                     # running status program change
+                    0x90, 60, 0xFE, 127,                   # note on with active sensing inside
+                    0xF0, 1, 2, 3, 0xF7,                   # SysEx
+                    0xF2, 0x10, 0x20,                      # song position
+                    7,                                     # running status was cancelled by system common: ignored
+                    0xF6,                                  # tune request
+                    0xE0, 0, 64,                           # pitch bend
+                    0xF0, 9, 9, 0xB1, 22, 33])             # SysEx aborted by a status byte, CC follows
+    p = tmp_path / "m.bin"
+    p.write_bytes(stream)
+    out = subprocess.check_output([RENDER, "--midi-parse", str(p)], text=True).split("\n")
+    assert [l for l in out if l] == ["b0 14 40", "f8", "b0 15 64", "c1 05", "c1 06", "fe", "90 3c 7f", "f0 01 02 03 f7",
+                                     "f2 10 20", "f6", "e0 00 40", "b1 16 21"]
+
+
+def test_midi_device_thread_drives_cc_mapping(tmp_path):
+    """RawMidi::Device on a FIFO standing in for /dev/snd/midiC*D*: the reader thread parses the byte
+    stream and Convolution::onMidiMessage applies the reference's CC -> parameter mapping
+    (conv.cu:255-276): dry/wet/level = v/128, pan = v/64 - 1, predelay = v*8192/128, speed = v*1024/128."""
+    assert subprocess.check_output([RENDER, "--midi-parse", os.devnull], text=True) == ""
+    fifo = tmp_path / "midi.fifo"
+    os.mkfifo(fifo)
+    proc = subprocess.Popen([RENDER, "--midi-listen", str(fifo), "1.0"], stdout=subprocess.PIPE, text=True)
+    assert proc.stdout.readline().strip() == "listening"
+    with open(fifo, "wb", buffering=0) as f:
+        f.write(bytes([0xB0, 22, 32, 23, 96]))         # dry = 0.25, wet = 0.75 (running status)
+        f.write(bytes([0xB0, 25, 0, 0xB0, 26, 127]))   # panDry = -1, panWet = 127/64 - 1
+        f.write(bytes([0xB0, 21, 64, 24, 16, 27, 64])) # predelay 4096, speed 128, level 0.5
+        f.write(bytes([0xB1, 22, 127]))                # other channel: ignored (cc.message is 0xB0)
+    out = json.loads(proc.stdout.read().strip().split("\n")[-1])
+    proc.wait(timeout=10)
+    assert out == {"predelay": 4096, "dry": 0.25, "wet": 0.75, "speed": 128, "panDry": -1.0, "panWet": 127 / 64 - 1, "level": 0.5}
+    assert RENDER and subprocess.run([RENDER, "--midi-listen", str(tmp_path / "nope"), "0.1"], capture_output=True).returncode == 1
