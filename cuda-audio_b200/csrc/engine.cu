@@ -319,7 +319,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
-        k_tier_forward<<<count * e->n_in * e->nv, threads, smem, st>>>(fa);
+        k_tier_forward<<<dim3(e->nv, e->n_in, count), threads, smem, st>>>(fa);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
@@ -328,7 +328,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-            k_tier_inverse<<<count * e->n_out, threads, smem, st>>>(ia);
+            k_tier_inverse<<<dim3(e->n_out, count), threads, smem, st>>>(ia);
             if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
         }
     }
@@ -340,7 +340,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
             CA_CUDA(cudaStreamWaitEvent(e->stream, e->join_ev[j], 0));
             const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-            k_tier_inverse<<<count * e->n_out, threads, t.S * sizeof(float2), e->stream>>>(ia);
+            k_tier_inverse<<<dim3(e->n_out, count), threads, t.S * sizeof(float2), e->stream>>>(ia);
         }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -535,7 +535,7 @@ int pipe_finish_prev(ca_engine *e, bool join_now)
         if (prev) CA_CUDA(cudaStreamWaitEvent(st, e->ptinv_ev[prev], 0));
         TierInvArgs ia{(tend & 1) ? t.Ypart2 : t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, tend};
         trace_mark(e, j == 1 ? "tinv1'" : "tinv2+'", (int)(1 + j), true);
-        k_tier_inverse<<<count * e->n_out, tier_threads(t), t.S * sizeof(float2), st>>>(ia);
+        k_tier_inverse<<<dim3(e->n_out, count), tier_threads(t), t.S * sizeof(float2), st>>>(ia);
         trace_mark(e, "", (int)(1 + j), false);
         CA_CUDA(cudaEventRecord(e->ptinv_ev[j], st));
         e->tinv_pending[j] = true;
@@ -613,7 +613,7 @@ int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks
                 TierFwdArgs tf{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, tend};
                 CA_CUDA(cudaStreamWaitEvent(e->s_tier[j], e->pf_ev[c], 0));
                 trace_mark(e, j == 1 ? "tfwd1" : "tfwd2+", (int)(1 + j), true);
-                k_tier_forward<<<count * e->n_in * e->nv, tier_threads(t), t.S * sizeof(float2), e->s_tier[j]>>>(tf);
+                k_tier_forward<<<dim3(e->nv, e->n_in, count), tier_threads(t), t.S * sizeof(float2), e->s_tier[j]>>>(tf);
                 trace_mark(e, "", (int)(1 + j), false);
                 CA_CUDA(cudaEventRecord(e->ptf_ev[j], e->s_tier[j]));
                 CA_CUDA(cudaStreamWaitEvent(e->s_mac, e->ptf_ev[j], 0));
@@ -879,8 +879,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         t.bt = std::min<uint32_t>(t.S, j == 0 ? 256u : bt_max);
         t.tiles = t.S / t.bt;
         // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /
-        // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 48 KB / 4 CTAs per SM
-        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 4 : 1);
+        // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 4 CTAs per SM (the register limit) of 3 x 12 KB
+        // stages (measured r01, K = 4096: tier-0 MAC 83 us with 96 KB, 78 with 4 x 12 KB, 74.5 with 3 x 12 KB)
+        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 6 : 1);
         t.mac = mac_pick((int)t.bt, (int)e->n_out, tier_variant);
         CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
         {

@@ -128,7 +128,7 @@ struct FwdArgs {
 // One warp per (instance, input); it steps the voice state once and then runs every audible voice
 // (one in steady state, two or three during an IR cross-fade).
 template <int R>
-__global__ void __launch_bounds__(kFwdWarps * 32) k_forward(const FwdArgs a)
+__global__ void __launch_bounds__(kFwdWarps * 32, 5) k_forward(const FwdArgs a)
 {
     constexpr int B = 32 * R;
     const int lane = threadIdx.x & 31;
@@ -1342,17 +1342,23 @@ struct TierFwdArgs {
 };
 
 // one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
-__global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs a)
+__global__ void __launch_bounds__(kTierThreads, 2) k_tier_forward(const TierFwdArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     __shared__ CtaTw tw;
-    const uint32_t per = a.n_in * a.nv;
-    const uint32_t inst = a.inst0 + (blockIdx.x / per) * a.inst_stride;
-    const uint32_t item = inst * a.n_in + (blockIdx.x % per) / a.nv, v = blockIdx.x % a.nv;
+    // grid (voice, input, firing instance): no integer divisions in the prologue
+    const uint32_t v = blockIdx.x;
+    const uint32_t inst = a.inst0 + blockIdx.z * a.inst_stride;
+    const uint32_t item = inst * a.n_in + blockIdx.y;
     const uint32_t w = item * a.nv + v;
     const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
     const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
     if (!((st.active >> v) & 1u)) return;
+    __shared__ uint32_t s_slot;
+    if (threadIdx.x == 0) {  // m is a power of two; the 64-bit modulo runs once per CTA
+        const unsigned long long n_fire = (tend + (inst & (a.m - 1u))) >> (31 - __clz((int)a.m));
+        s_slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
+    }
     const uint32_t mask = a.ring_len - 1;
     const float *ring = a.ring + (size_t)w * a.ring_len;
     const uint32_t start = (uint32_t)((tend * (unsigned long long)a.B - 2ull * a.S) & mask);
@@ -1373,9 +1379,7 @@ __global__ void __launch_bounds__(kTierThreads) k_tier_forward(const TierFwdArgs
     cta_tw_init(tw, (int)a.S, a.twM, a.tw2M);
     cta_fft_forward(sm, (int)a.S, (int)a.s_log, tw, a.twM);
     cta_split_r2c(sm, (int)a.S, (int)a.s_log, tw);
-    const unsigned long long n_fire = (tend + inst % a.m) / a.m;
-    const uint32_t slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
-    float2 *dst = a.X + ((size_t)w * a.Lring + slot) * a.S;
+    float2 *dst = a.X + ((size_t)w * a.Lring + s_slot) * a.S;  // written before the transform's barriers
     for (uint32_t p = threadIdx.x; p < a.S / 2; p += blockDim.x)  // position order (fft_cta.cuh), 16-byte stores
         reinterpret_cast<float4 *>(dst)[p] = *reinterpret_cast<const float4 *>(sm + swz(2 * (int)p));
 }
@@ -1391,16 +1395,17 @@ struct TierInvArgs {
 };
 
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
-__global__ void __launch_bounds__(kTierThreads) k_tier_inverse(const TierInvArgs a)
+__global__ void __launch_bounds__(kTierThreads, 2) k_tier_inverse(const TierInvArgs a)
 {
     extern __shared__ __align__(16) float2 sm[];
     __shared__ CtaTw tw;
-    const uint32_t inst = a.inst0 + (blockIdx.x / a.n_out) * a.inst_stride, o = blockIdx.x % a.n_out;
+    const uint32_t z = blockIdx.y, o = blockIdx.x;  // grid (output, firing instance)
+    const uint32_t inst = a.inst0 + z * a.inst_stride;
     const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
     // sum of the partial spectra (position order), 8 independent float4 loads in flight per thread
     {
-        const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)(blockIdx.x / a.n_out) * a.n_split) * a.n_out + o) * a.S);
+        const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)z * a.n_split) * a.n_out + o) * a.S);
         const size_t stride4 = (size_t)a.n_out * a.S / 2;
         for (uint32_t n0 = threadIdx.x; n0 < a.S / 2; n0 += 8 * blockDim.x) {
             float4 r[8];
