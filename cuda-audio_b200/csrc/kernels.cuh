@@ -592,7 +592,7 @@ struct MacPCfg {
 };
 
 template <int BT, int NOUT, int KC, int NSTAGE>
-__global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const uint32_t n_work, const uint32_t n_tiles)
+__global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const uint32_t n_work, const uint32_t n_tiles)
 {
     using Cfg = MacCfg<BT, NOUT, KC, NSTAGE>;
     using PCfg = MacPCfg<BT, NOUT, KC, NSTAGE>;
@@ -610,6 +610,10 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
     const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t + a.t_bias;
+    // m (tier block / period) and n_tiles (S / BT) are powers of two: shifts and masks instead of the
+    // software 64-bit divisions, which sat on the producer's critical path at every work item (ncu r01)
+    const uint32_t m_log = 31 - __clz((int)a.m), m_mask = a.m - 1u;
+    const uint32_t t_log = 31 - __clz((int)n_tiles), t_mask = n_tiles - 1u;
 
     if (tid == 0) {
 #pragma unroll
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
         struct Raw { uint32_t active, slot; unsigned long long start; float pan; };
         auto load_raw = [&](uint32_t j) {
             Raw r{0u, 0u, 0ull, 0.f};
-            const uint32_t inst = a.inst0 + (j / n_tiles) * a.inst_stride;
+            const uint32_t inst = a.inst0 + (j >> t_log) * a.inst_stride;
             if ((uint32_t)lane < ns) {
                 const uint32_t i = lane / a.nv, v = lane % a.nv;
                 const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + inst * a.n_in + i];
@@ -644,12 +648,12 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
         Raw cur = load_raw(blockIdx.x), nxt = cur;
         for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
             if (j + gridDim.x < n_work) nxt = load_raw(j + gridDim.x);
-            const uint32_t tile = j % n_tiles, inst = a.inst0 + (j / n_tiles) * a.inst_stride;
-            const uint32_t phase = inst % a.m;
-            const unsigned long long n_fire = (tend + phase) / a.m;
+            const uint32_t tile = j & t_mask, inst = a.inst0 + (j >> t_log) * a.inst_stride;
+            const uint32_t phase = inst & m_mask;
+            const unsigned long long n_fire = (tend + phase) >> m_log;
             uint32_t nk = 0;
             if (cur.active) {  // see k_mac: partitions whose FDL block was built after the voice's (re)start
-                const long long first_fire = (long long)((cur.start + phase + a.m) / a.m);
+                const long long first_fire = (long long)((cur.start + phase + a.m) >> m_log);
                 const long long cnt = (long long)n_fire - first_fire + 1 - (long long)a.k_off;
                 nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
             }
@@ -668,7 +672,9 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
             float pan[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) pan[q] = __shfl_sync(kFull, cur.pan, q < 2 * NOUT ? q : 0);
-            const uint32_t head = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
+            // ring position of partition 0: (Lring - 1 - n_fire % Lring + k_off) % Lring; 32-bit fast path
+            const uint32_t nf_mod = (n_fire >> 32) ? (uint32_t)(n_fire % a.Lring) : (uint32_t)n_fire % a.Lring;
+            const uint32_t head0 = ((a.Lring - 1u) - nf_mod + a.k_off % a.Lring) % a.Lring;
             const uint32_t n_iter = max(1u, (total + KC - 1) / KC);
             for (uint32_t i = 0; i < n_iter; i++, it++) {
                 const uint32_t st = it % NSTAGE;
@@ -692,7 +698,8 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
                     const uint32_t k = rho - s_rs[s], slot = s_sl[s];
                     const float2 *src;
                     if (w == 0) {
-                        const uint32_t pos = (head + a.k_off + k) % a.Lring;
+                        uint32_t pos = head0 + k;  // k < P <= Lring
+                        if (pos >= a.Lring) pos -= a.Lring;
                         src = a.X + ((size_t)(inst * ns + s) * a.Lring + pos) * a.S + tile * BT;
                     } else {
                         src = a.H + (((size_t)slot * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
@@ -704,22 +711,29 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
             cur = nxt;
         }
     } else {
-        // ===== consumers: thread (g, q) owns bins (2q, 2q+1) of every G-th row =====
+        // ===== consumers: thread (g, q) owns bins (2q, 2q+1).  Row groups g take every G-th row and their
+        // sums are added through shared memory at the end of the item -- except when there are as many
+        // groups as outputs (BT = 256, true stereo): then group g takes EVERY row for output g, and the
+        // item ends without a barrier or a reduction (OSPLIT). =====
+        constexpr bool OSPLIT = (G == NOUT) && (G > 1);
+        constexpr int NO = OSPLIT ? 1 : NOUT;     // outputs per thread
+        constexpr int RSTEP = OSPLIT ? 1 : G;     // row stride of a thread
         const int q = tid % LR, g = tid / LR;
+        const int r_first = OSPLIT ? 0 : g, o_base = OSPLIT ? g : 0;
         uint32_t it = 0;
         for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
-            const uint32_t tile = j % n_tiles, z = j / n_tiles;
+            const uint32_t tile = j & t_mask, z = j >> t_log;
             const bool bin0 = (q == 0) && (tile == 0);
-            float4 acc[NOUT], y[NOUT];
-            float2 e0[NOUT], y0[NOUT];
+            float4 acc[NO], y[NO];
+            float2 e0[NO], y0[NO];
 #pragma unroll
-            for (int o = 0; o < NOUT; o++) {
+            for (int o = 0; o < NO; o++) {
                 acc[o] = y[o] = make_float4(0.f, 0.f, 0.f, 0.f);
                 e0[o] = y0[o] = make_float2(0.f, 0.f);
             }
             bool second = false;
             uint32_t last;
-            float pan0[NOUT], pan1[NOUT];
+            float pan0[NO], pan1[NO];
             do {
                 const uint32_t st = it % NSTAGE;
                 const uint32_t ph = (it / NSTAGE) & 1u;
@@ -728,15 +742,15 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
                 const uint32_t rows = m.rows, rho0 = m.rho0, boundary = m.boundary;
                 last = m.last;
 #pragma unroll
-                for (int o = 0; o < NOUT; o++) { pan0[o] = m.pan[o]; pan1[o] = m.pan[NOUT + o]; }
+                for (int o = 0; o < NO; o++) { pan0[o] = m.pan[o_base + o]; pan1[o] = m.pan[NOUT + o_base + o]; }
 #pragma unroll
-                for (int rr = 0; rr < KC / G; rr++) {
-                    const uint32_t r = g + rr * G;
+                for (int rr = 0; rr < KC / RSTEP; rr++) {
+                    const uint32_t r = r_first + rr * RSTEP;
                     if (r < rows) {
                         if (!second && rho0 + r >= boundary) {
                             second = true;
 #pragma unroll
-                            for (int o = 0; o < NOUT; o++) {
+                            for (int o = 0; o < NO; o++) {
                                 const float pan = pan0[o];
                                 y[o].x = pan * acc[o].x; y[o].y = pan * acc[o].y; y[o].z = pan * acc[o].z; y[o].w = pan * acc[o].w;
                                 y0[o].x = pan * e0[o].x; y0[o].y = pan * e0[o].y;
@@ -747,8 +761,8 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
                         const float4 *row = stage + ((size_t)(st * KC + r) * NARR) * LR + q;
                         const float4 x = row[0];
 #pragma unroll
-                        for (int o = 0; o < NOUT; o++) {
-                            const float4 h = row[(1 + o) * LR];
+                        for (int o = 0; o < NO; o++) {
+                            const float4 h = row[(1 + o_base + o) * LR];
                             acc[o].x = fmaf(x.x, h.x, fmaf(-x.y, h.y, acc[o].x));
                             acc[o].y = fmaf(x.x, h.y, fmaf(x.y, h.x, acc[o].y));
                             acc[o].z = fmaf(x.z, h.z, fmaf(-x.w, h.w, acc[o].z));
@@ -765,18 +779,18 @@ __global__ void __launch_bounds__(kMacThreads) k_mac_p(const MacArgs a, const ui
                 it++;
             } while (!last);
 #pragma unroll
-            for (int o = 0; o < NOUT; o++) {  // fold the last input's sum with its pan (conv.cu:392-401)
+            for (int o = 0; o < NO; o++) {  // fold the last input's sum with its pan (conv.cu:392-401)
                 const float pan = second ? pan1[o] : pan0[o];
                 y[o].x = fmaf(pan, acc[o].x, y[o].x); y[o].y = fmaf(pan, acc[o].y, y[o].y);
                 y[o].z = fmaf(pan, acc[o].z, y[o].z); y[o].w = fmaf(pan, acc[o].w, y[o].w);
                 y0[o].x = fmaf(pan, e0[o].x, y0[o].x); y0[o].y = fmaf(pan, e0[o].y, y0[o].y);
             }
             float2 *ybase = a.Ypart + ((size_t)(a.yp_local ? z : a.inst0 + z * a.inst_stride) * NOUT) * a.S + tile * BT + 2 * q;
-            if constexpr (G == 1) {
+            if constexpr (G == 1 || OSPLIT) {
 #pragma unroll
-                for (int o = 0; o < NOUT; o++) {
+                for (int o = 0; o < NO; o++) {
                     if (bin0) { y[o].x = y0[o].x; y[o].y = y0[o].y; }
-                    *reinterpret_cast<float4 *>(ybase + (size_t)o * a.S) = y[o];
+                    *reinterpret_cast<float4 *>(ybase + (size_t)(o_base + o) * a.S) = y[o];
                 }
             } else {
                 // cross-group sum in fixed order (deterministic); consumer-only named barrier
