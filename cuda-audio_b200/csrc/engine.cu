@@ -42,6 +42,19 @@ typedef void (*mac_fn)(const MacArgs);
 typedef void (*macp_fn)(const MacArgs, const uint32_t, const uint32_t);
 typedef void (*inv_fn)(const InvArgs);
 
+// Launch with (pdl) or without the programmatic-stream-serialization attribute, see pdl_wait() in kernels.cuh.
+template <class... P, class... A>
+inline void launch_k(bool pdl, void (*fn)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const A &...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, fn, P(args)...);
+}
+
 struct MacVariant { mac_fn fn; uint32_t smem; int kc; macp_fn pfn; uint32_t psmem; };
 
 template <int BT, int NOUT, int MULT, int NSTAGE>
@@ -153,6 +166,7 @@ struct ca_engine {
     bool tinv_pending[CA_MAX_TIERS] = {};
     uint64_t pipe_prev_tend = 0;     // period whose long-tier inverse transforms are still to be launched (0: none)
     bool pipe_used = false;
+    bool pdl = false;                // programmatic dependent launch between the period's kernels (CA_PDL; default: batches without a graph)
     int pipe_mode = 0;               // CA_PIPELINE=1 enables it (measured r01: +5 % device-resident, -8 % end to end: off by default)
     // CA_PIPE_TRACE=n: print the device timeline (CUDA events around every launch) of periods n, n+1
     struct TraceEv { const char *name; int lane; cudaEvent_t a, b; };
@@ -239,14 +253,14 @@ MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
 
 // One MAC launch over `count` instances of tier t.  Batches (n_split == 1 and more work items than
 // resident CTA slots) take the persistent schedule: every CTA gets the same number of work items.
-void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st)
+void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st, bool pdl = false)
 {
     const uint32_t n_work = count * t.tiles;
     if (t.p_slots && t.n_split == 1 && (t.p_force || n_work > t.p_slots)) {
         const uint32_t per = (n_work + t.p_slots - 1) / t.p_slots;
-        t.mac.pfn<<<(n_work + per - 1) / per, kMacThreads, t.mac.psmem, st>>>(ma, n_work, t.tiles);
+        launch_k(pdl, t.mac.pfn, dim3((n_work + per - 1) / per), dim3(kMacThreads), t.mac.psmem, st, ma, n_work, t.tiles);
     } else {
-        t.mac.fn<<<dim3(t.n_split, t.tiles, count), kMacThreads, t.mac.smem, st>>>(ma);
+        launch_k(pdl, t.mac.fn, dim3(t.n_split, t.tiles, count), dim3(kMacThreads), t.mac.smem, st, ma);
     }
 }
 
@@ -285,12 +299,13 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
         return CA_OK;
     }
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
+    const bool pdl = e->pdl && !profile;
+    launch_k(pdl, e->fft.fwd, dim3((n_items + kFwdWarps - 1) / kFwdWarps), dim3(kFwdWarps * 32), 0, e->stream, fa);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    launch_mac(t0, ma, i1 - i0, e->stream);
+    launch_mac(t0, ma, i1 - i0, e->stream, pdl);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
-    else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
+    if (t0.n_split <= 4) launch_k(pdl, e->fft.inv_packed, dim3((ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32)), dim3(kInvThreads), 0, e->stream, ia);
+    else launch_k(pdl, e->fft.inv, dim3(ia.n_items), dim3(kInvThreads), 0, e->stream, ia);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -319,16 +334,17 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
-        k_tier_forward<<<dim3(e->nv, e->n_in, count), threads, smem, st>>>(fa);
+        const bool pdl = e->pdl && !profile;
+        launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(threads), smem, st, fa);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m;
-        launch_mac(t, ma, count, st);
+        launch_mac(t, ma, count, st, pdl);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], st));
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-            k_tier_inverse<<<dim3(e->n_out, count), threads, smem, st>>>(ia);
+            launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), smem, st, ia);
             if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
         }
     }
@@ -340,7 +356,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
             CA_CUDA(cudaStreamWaitEvent(e->stream, e->join_ev[j], 0));
             const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
-            k_tier_inverse<<<dim3(e->n_out, count), threads, t.S * sizeof(float2), e->stream>>>(ia);
+            launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), e->stream, ia);
         }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -866,6 +882,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaEventCreateWithFlags(&e->pm_tail, cudaEventDisableTiming));
     for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
+    e->pdl = !(cfg->flags & CA_FLAG_GRAPH);
+    if (const char *pd = getenv("CA_PDL")) e->pdl = atoi(pd) != 0;
     if (const char *tr = getenv("CA_PIPE_TRACE")) e->trace_at = (uint64_t)atoll(tr);
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;

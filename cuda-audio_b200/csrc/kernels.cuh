@@ -56,6 +56,14 @@ struct Ctl {
     unsigned long long t, t_next;
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may become resident while the previous kernel of the stream drains; pdl_wait() blocks until
+// that kernel has completed and its writes are visible, so everything after it sees normal stream
+// order.  Both are no-ops for ordinary launches.  Hides the launch gap and CTA ramp between the
+// period's dependent kernels (2.5-5 us each, `CA_PIPE_TRACE` timeline).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // pan law, conv.cu:386-389 / 418-421
 __device__ __forceinline__ float pan_gain(float pan, int o, int n_out)
 {
@@ -130,6 +138,8 @@ struct FwdArgs {
 template <int R>
 __global__ void __launch_bounds__(kFwdWarps * 32, 5) k_forward(const FwdArgs a)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     constexpr int B = 32 * R;
     const int lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
@@ -384,6 +394,8 @@ struct MacCfg {
 template <int BT, int NOUT, int KC, int NSTAGE>
 __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     using Cfg = MacCfg<BT, NOUT, KC, NSTAGE>;
     constexpr int NARR = Cfg::NARR, LR = Cfg::LR, G = Cfg::G;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -594,6 +606,8 @@ struct MacPCfg {
 template <int BT, int NOUT, int KC, int NSTAGE>
 __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const uint32_t n_work, const uint32_t n_tiles)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     using Cfg = MacCfg<BT, NOUT, KC, NSTAGE>;
     using PCfg = MacPCfg<BT, NOUT, KC, NSTAGE>;
     constexpr int NARR = Cfg::NARR, LR = Cfg::LR, G = Cfg::G;
@@ -854,6 +868,8 @@ constexpr int kInvThreads = 128;
 template <int R, bool PACKED>
 __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     constexpr int B = 32 * R;
     __shared__ __align__(16) float2 Ys[PACKED ? 2 : B];
     const int tid = threadIdx.x;
@@ -1358,6 +1374,8 @@ struct TierFwdArgs {
 // one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
 __global__ void __launch_bounds__(kTierThreads, 2) k_tier_forward(const TierFwdArgs a)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     extern __shared__ __align__(16) float2 sm[];
     __shared__ CtaTw tw;
     // grid (voice, input, firing instance): no integer divisions in the prologue
@@ -1411,6 +1429,8 @@ struct TierInvArgs {
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
 __global__ void __launch_bounds__(kTierThreads, 2) k_tier_inverse(const TierInvArgs a)
 {
+    pdl_trigger();  // the next kernel of the stream may become resident while this one drains
+    pdl_wait();     // before any global access and before any early exit: stream order holds transitively
     extern __shared__ __align__(16) float2 sm[];
     __shared__ CtaTw tw;
     const uint32_t z = blockIdx.y, o = blockIdx.x;  // grid (output, firing instance)
