@@ -463,3 +463,39 @@ def test_channel_layouts(n_in, n_out, tiers):
     truth = O.engine_truth(x, irs, pr, predelay=9)
     for o in range(n_out):
         assert O.rel_l2(y[o], truth[o]) < 5e-6, (n_in, n_out, o, O.rel_l2(y[o], truth[o]))
+
+
+@pytest.mark.parametrize("tiers", [None, "auto"])
+def test_edge_cases_tiny_truncated_and_zero_irs_silence(tiers):
+    """Ragged / degenerate inputs: a 1-frame IR (a pure gain), an IR one frame longer than a partition,
+    an IR longer than the engine's capacity (truncated like conv.cu:239), an all-zero IR, silent input,
+    and an input block of denormal-sized values."""
+    m = ca()
+    B, cap = 64, 64 * 40
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((2, B * 70)) * 0.2).astype(np.float32)
+    x[:, B * 30:B * 40] = 0.0                       # ten periods of silence in the middle
+    x[:, B * 50:B * 51] = 1e-39                     # denormals
+    long_ir = (rng.standard_normal((2, cap + 500)) * 0.05).astype(np.float32)
+    cases = {
+        "one_frame": np.array([[0.5], [-0.25]], np.float32),
+        "partition_plus_one": (rng.standard_normal((2, B + 1)) * 0.1).astype(np.float32),
+        "truncated": long_ir,
+        "zeros": np.zeros((2, 300), np.float32),
+    }
+    pr = [dict(wet=1.0, dry=0.0, level=1.0, panWet=0.0, panDry=0.0)] * 2
+    for name, h in cases.items():
+        with m.Engine(period=B, max_ir_frames=cap, tiers=tiers) as e:
+            for i in range(2):
+                e.load_ir(i, h[0], h[1])
+                e.set_params(0, i, select=i, **pr[i])
+                e.set_glide(0, i, 1.0)
+            y = e.render(x[None])[0]
+        hh = h[:, :cap]
+        truth = O.engine_truth(x, [[hh[0], hh[1]], [hh[0], hh[1]]], pr)
+        assert np.isfinite(y).all(), name
+        if name == "zeros":
+            assert np.abs(y).max() == 0.0
+        else:
+            for o in range(2):
+                assert O.rel_l2(y[o], truth[o]) < 5e-6, (name, o, O.rel_l2(y[o], truth[o]))
