@@ -279,12 +279,14 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     const Tier &t0 = e->tiers[0];
     const uint32_t n_items = (i1 - i0) * e->n_in;
     const uint32_t n_alloc = e->n_inst * e->n_in;
+    // without a graph the host passes the period count itself (e->t_host == ctl->t between periods)
+    const unsigned long long tp1 = (e->cfg.flags & CA_FLAG_GRAPH) ? 0ull : e->t_host + 1ull;
     FwdArgs fa{d_in, e->d_ring, t0.X, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
-               n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in};
+               n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in, tp1};
     MacArgs ma = mac_args(e, t0, 1u);
-    ma.inst0 = i0;
+    ma.inst0 = i0; ma.tend_host = tp1;
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
-               t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
+               t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, tp1};
     if (e->fused) {
         // tiered throughput schedule: forward + MAC + inverse of tier 0 in one CTA per instance
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
@@ -322,6 +324,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
     // launches too few CTAs to fill the GPU alone), then the inverse kernels run in tier order on the
     // main stream so the output-ring accumulation stays race-free and deterministic.
     const bool fork = firing >= 2 && !profile;
+    const unsigned long long th = (e->cfg.flags & CA_FLAG_GRAPH) ? 0ull : tend;  // graphs replay: the kernels read ctl->t
     if (fork) CA_CUDA(cudaEventRecord(e->fork_ev, e->stream));
     for (size_t j = 1; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
@@ -332,18 +335,18 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
         if (fork) CA_CUDA(cudaStreamWaitEvent(st, e->fork_ev, 0));
         const uint32_t smem = t.S * sizeof(float2);
         const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
-        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m};
+        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, th};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
         const bool pdl = e->pdl && !profile;
         launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(threads), smem, st, fa);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
-        ma.inst0 = r; ma.inst_stride = t.m;
+        ma.inst0 = r; ma.inst_stride = t.m; ma.tend_host = th;
         launch_mac(t, ma, count, st, pdl);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], st));
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
-            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th};
             launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), smem, st, ia);
             if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
         }
@@ -355,7 +358,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
             if (!count) continue;
             CA_CUDA(cudaStreamWaitEvent(e->stream, e->join_ev[j], 0));
             const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
-            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m};
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th};
             launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), e->stream, ia);
         }
     CA_CUDA(cudaGetLastError());

@@ -131,6 +131,9 @@ struct FwdArgs {
     uint32_t n_items_alloc;  // stride between the two state buffers
     uint32_t n_in, nv, Lring, ring_len, ring_out;
     uint32_t item0;    // first (instance, input) item of this launch (chunked host pipeline)
+    // host-driven launches (no graph): the period count + 1 comes as an argument, which takes the
+    // ctl->t round trip off the head of every warp's chain of dependent loads (0: read ctl->t)
+    unsigned long long t_host_p1;
 };
 
 // One warp per (instance, input); it steps the voice state once and then runs every audible voice
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 5) k_forward(const FwdArgs a)
     const uint32_t w = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
     if (w >= a.n_items) return;
     const uint32_t item = a.item0 + w;
-    const unsigned long long t = a.ctl->t;
+    const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t;
     if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
 
     const InParamDev p = a.par[item];
@@ -858,6 +861,7 @@ struct InvArgs {
     uint32_t item0;    // first item of this launch
     uint32_t advance;  // 1: this launch completes the period (advances ctl->t)
     uint32_t raw_wet;  // 1: store the unclamped wet block only (partition-range shards: clamp + dry after the reduce)
+    unsigned long long t_host_p1;  // see FwdArgs
 };
 
 constexpr int kInvThreads = 128;
@@ -877,7 +881,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
     if (PACKED && local >= a.n_items) return;
     const uint32_t item = a.item0 + local;
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
-    const unsigned long long t = a.ctl->t_next - 1ull;
+    const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t_next - 1ull;
 
     if constexpr (!PACKED) {
         // --- sum the partial spectra of the MAC splits (fixed order) ---
