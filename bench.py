@@ -331,8 +331,10 @@ def run_ours(args):
     # ---- latency of ONE instance through the public call (p50/p99) ----
     if rank == 0 and world == 1 and not args.no_latency:
         lat = {}
-        for name, tr in (("non_uniform", "auto"), ("uniform", None)):
-            e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH, tiers=tr)
+        # non_uniform: long tiers with two periods of slack on a low-priority stream (CA_FLAG_ASYNC_TIERS);
+        # non_uniform_sync_tiers: the same partitioning with the tiers queued in front of the next period
+        for name, tr, fl in (("non_uniform", "auto", ca.FLAG_ASYNC_TIERS), ("non_uniform_sync_tiers", "auto", 0), ("uniform", None, 0)):
+            e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH | fl, tiers=tr)
             a, b = ca.PinnedArray((1, 2, B)), ca.PinnedArray((1, 2, B))
             a.array[...] = 0.05
             for _ in range(STEADY + 200):
@@ -343,6 +345,18 @@ def run_ours(args):
             s1 = e1.stats()
             lat[name] = {"periods": int(s1.periods), "p50_us": round(s1.p50_us, 1), "p99_us": round(s1.p99_us, 1), "max_us": round(s1.max_us, 1),
                          "p99_frac_of_deadline": round(s1.p99_us / (DEADLINE_MS * 1e3), 4), "mac_split": int(s1.mac_split)}
+            # the same call issued on a clock (one period every args.pace_us, 10 x faster than real time by
+            # default) like a JACK callback, instead of back to back: work deferred past the output has
+            # the time a real period leaves it
+            e1.reset_stats()
+            tick = time.perf_counter()
+            for _ in range(args.latency_periods):
+                tick += args.pace_us * 1e-6
+                while time.perf_counter() < tick:
+                    pass
+                e1.process_raw(a.ptr, b.ptr)
+            s2 = e1.stats()
+            lat[name]["paced"] = {"interval_us": args.pace_us, "p50_us": round(s2.p50_us, 1), "p99_us": round(s2.p99_us, 1), "max_us": round(s2.max_us, 1)}
             e1.close()
             a.free()
             b.free()
@@ -569,6 +583,7 @@ def main():
     ap.add_argument("--round-to-cycle", action="store_true", help="round --steps up to a multiple of the tier launch-pattern period")
     ap.add_argument("--sustain-periods", type=int, default=2000)
     ap.add_argument("--latency-periods", type=int, default=2000)
+    ap.add_argument("--pace-us", type=float, default=533.3, help="period interval of the paced latency measurement (real time: 5333.3)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-max-instances", type=int, default=32)
     ap.add_argument("--no-roofline", action="store_true")

@@ -166,6 +166,10 @@ struct ca_engine {
     bool tinv_pending[CA_MAX_TIERS] = {};
     uint64_t pipe_prev_tend = 0;     // period whose long-tier inverse transforms are still to be launched (0: none)
     bool pipe_used = false;
+    // CA_FLAG_ASYNC_TIERS: deferred tiers on their own low-priority stream, two periods of slack
+    bool async_tiers = false, async_used = false;
+    cudaStream_t s_def = nullptr;
+    cudaEvent_t ev_period = nullptr, ev_def[2] = {};
     bool pdl = false;                // programmatic dependent launch between the period's kernels (CA_PDL; default: batches without a graph)
     int pipe_mode = 0;               // CA_PIPELINE=1 enables it (measured r01: +5 % device-resident, -8 % end to end: off by default)
     // CA_PIPE_TRACE=n: print the device timeline (CUDA events around every launch) of periods n, n+1
@@ -314,8 +318,9 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
 }
 
 // deferred tiers: for every tier the phase-staggered subset of instances whose block just closed
-int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
+int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = nullptr)
 {
+    if (!base) base = e->stream;
     const uint32_t n_alloc = e->n_inst * e->n_in;
     uint32_t firing = 0;
     for (size_t j = 1; j < e->tiers.size(); j++) firing += tier_count(e, e->tiers[j], tend) ? 1u : 0u;
@@ -323,30 +328,31 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
     // with >= 2 tiers firing, each tier's forward FFT + MAC runs on its own side stream (the 16 K tier
     // launches too few CTAs to fill the GPU alone), then the inverse kernels run in tier order on the
     // main stream so the output-ring accumulation stays race-free and deterministic.
-    const bool fork = firing >= 2 && !profile;
-    const unsigned long long th = (e->cfg.flags & CA_FLAG_GRAPH) ? 0ull : tend;  // graphs replay: the kernels read ctl->t
-    if (fork) CA_CUDA(cudaEventRecord(e->fork_ev, e->stream));
+    const bool fork = firing >= 2 && !profile && !e->async_tiers;
+    const unsigned long long th = (e->cfg.flags & CA_FLAG_GRAPH) ? 0ull : tend;  // graphs replay: the kernels read ctl->t ...
+    const uint32_t tsel = e->async_tiers ? 1u + (uint32_t)(tend & 1) : 0u;       // ... or its parity slot (asynchronous tiers)
+    if (fork) CA_CUDA(cudaEventRecord(e->fork_ev, base));
     for (size_t j = 1; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
         const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
         e->tev_used[j] = profile && count;
         if (!count) continue;
-        cudaStream_t st = fork ? e->s_tier[j] : e->stream;
+        cudaStream_t st = fork ? e->s_tier[j] : base;
         if (fork) CA_CUDA(cudaStreamWaitEvent(st, e->fork_ev, 0));
         const uint32_t smem = t.S * sizeof(float2);
         const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
-        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, th};
+        TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, th, tsel};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
         const bool pdl = e->pdl && !profile;
         launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(threads), smem, st, fa);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
-        ma.inst0 = r; ma.inst_stride = t.m; ma.tend_host = th;
+        ma.inst0 = r; ma.inst_stride = t.m; ma.tend_host = th; ma.t_sel = tsel;
         launch_mac(t, ma, count, st, pdl);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][2], st));
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
-            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th};
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th, tsel};
             launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), smem, st, ia);
             if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
         }
@@ -356,10 +362,10 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile)
             const Tier &t = e->tiers[j];
             const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
             if (!count) continue;
-            CA_CUDA(cudaStreamWaitEvent(e->stream, e->join_ev[j], 0));
+            CA_CUDA(cudaStreamWaitEvent(base, e->join_ev[j], 0));
             const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
-            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th};
-            launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), e->stream, ia);
+            TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th, tsel};
+            launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), base, ia);
         }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -411,6 +417,13 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
 {
     int rc = pipe_drain(e);
     if (rc) return rc;
+    if (e->async_used) {
+        // asynchronous tiers: this period (t_end = t_host + 1) needs the tiers that fired at t_end - 2 (their
+        // results start in this period's output block, and their state buffer is the one fwd0 rewrites now);
+        // the tiers of t_end - 1 keep running beside this period
+        if (e->par_dirty.load(std::memory_order_acquire)) CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[e->t_host & 1], 0));  // they read the parameters
+        CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[(e->t_host + 1) & 1], 0));
+    }
     rc = flush_params(e);
     if (rc) return rc;
     const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
@@ -442,6 +455,13 @@ int run_deferred(ca_engine *e)
     const bool profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
     const uint32_t firing = tiers_firing(e, tend);
     int rc = CA_OK;
+    cudaStream_t ts = e->stream;
+    if (firing && e->async_tiers && !profile) {
+        ts = e->s_def;
+        CA_CUDA(cudaEventRecord(e->ev_period, e->stream));  // forward transforms (time ring, voice state) of this period
+        CA_CUDA(cudaStreamWaitEvent(ts, e->ev_period, 0));
+        e->async_used = true;
+    }
     if (firing) {
         if ((e->cfg.flags & CA_FLAG_GRAPH) && !profile) {
             const uint64_t key = tiers_key(e, tend);
@@ -452,11 +472,12 @@ int run_deferred(ca_engine *e)
                 if (rc) return rc;
                 it = e->graphs.emplace(key, ge).first;
             }
-            CA_CUDA(cudaGraphLaunch(it->second, e->stream));
+            CA_CUDA(cudaGraphLaunch(it->second, ts));
         } else {
-            rc = launch_tiers(e, tend, profile);
+            rc = launch_tiers(e, tend, profile, ts);
             if (rc) return rc;
         }
+        if (ts != e->stream) CA_CUDA(cudaEventRecord(e->ev_def[tend & 1], ts));
         e->launches += 3 * firing;
     }
     if (profile) {
@@ -522,7 +543,7 @@ void trace_dump(ca_engine *e)
 
 bool use_pipeline(const ca_engine *e)
 {
-    if (e->tiers.size() < 2 || e->fused || !e->s_mac || (e->cfg.flags & (CA_FLAG_PROFILE | CA_FLAG_GRAPH))) return false;
+    if (e->tiers.size() < 2 || e->fused || !e->s_mac || e->async_tiers || (e->cfg.flags & (CA_FLAG_PROFILE | CA_FLAG_GRAPH))) return false;
     return e->pipe_mode == 1;
 }
 
@@ -575,6 +596,17 @@ int pipe_drain(ca_engine *e)
     CA_CUDA(cudaStreamWaitEvent(e->stream, e->pm_tail, 0));
     e->pipe_used = false;
     return CA_OK;
+}
+
+// quiescence for callers that touch shared state (IR bank, active count, sync): the pipelined lanes and
+// the asynchronous tier stream become dependencies of e->stream
+int drain_all(ca_engine *e)
+{
+    if (e->async_used) {
+        CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[0], 0));
+        CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[1], 0));
+    }
+    return pipe_drain(e);
 }
 
 // one period of a batch; h_src / h_dst: pinned host buffers (ca_process) or nullptr (device-resident)
@@ -761,10 +793,13 @@ int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block)
         uint32_t next = S * growth;
         if (next < 256) next = 256;  // long tiers use the CTA-level FFT: block >= 256
         if (next > max_block && S < max_block) next = max_block;
-        const bool last = (n + 1 == CA_MAX_TIERS) || next > max_block || off + next >= cfg->max_ir_frames;
+        const bool last = (n + 1 == CA_MAX_TIERS) || next > max_block || off + next + ((cfg->flags & CA_FLAG_ASYNC_TIERS) ? cfg->period : 0u) >= cfg->max_ir_frames;
         cfg->tier_block[n] = S;
         if (last) { cfg->tier_parts[n] = 0; n++; break; }
-        const uint32_t parts = (next - off + S - 1) / S;  // reach offset >= next
+        // reach offset >= next (the tier's result is due the period after its block closes), one period
+        // more with CA_FLAG_ASYNC_TIERS (due two periods later: the tier runs beside the next period)
+        const uint32_t slack = (cfg->flags & CA_FLAG_ASYNC_TIERS) ? cfg->period : 0u;
+        const uint32_t parts = (next + slack - off + S - 1) / S;
         cfg->tier_parts[n] = parts;
         off += parts * S;
         S = next;
@@ -779,6 +814,7 @@ int ca_destroy(ca_engine *e)
     if (!e) return CA_OK;
     cudaSetDevice(e->device);
     if (e->s_mac) cudaStreamSynchronize(e->s_mac);
+    if (e->s_def) cudaStreamSynchronize(e->s_def);
     for (auto &st : e->s_tier) if (st) cudaStreamSynchronize(st);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->s_out) cudaStreamSynchronize(e->s_out);
@@ -794,6 +830,9 @@ int ca_destroy(ca_engine *e)
     if (e->s_in) cudaStreamDestroy(e->s_in);
     if (e->s_out) cudaStreamDestroy(e->s_out);
     if (e->s_mac) cudaStreamDestroy(e->s_mac);
+    if (e->s_def) cudaStreamDestroy(e->s_def);
+    if (e->ev_period) cudaEventDestroy(e->ev_period);
+    for (auto &ev : e->ev_def) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pf_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->pm_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ptf_ev) if (ev) cudaEventDestroy(ev);
@@ -834,6 +873,7 @@ static int plan_tiers(const ca_config *cfg, ca_engine *e)
         if (j == 0 && t.S != B) { g_last_error = "tier 0 block must equal the period"; return CA_ERR_INVALID; }
         if (!is_pow2(t.S) || (j > 0 && (t.S <= e->tiers[j - 1].S || t.S < 256 || t.S > 16384))) { g_last_error = "tier blocks must be increasing powers of two, 256..16384 above tier 0"; return CA_ERR_INVALID; }
         if (j > 0 && off < t.S) { g_last_error = "tier offset must be >= its block size (previous tiers too short)"; return CA_ERR_INVALID; }
+        if (j > 0 && (cfg->flags & CA_FLAG_ASYNC_TIERS) && off < t.S + B) { g_last_error = "CA_FLAG_ASYNC_TIERS: tier offset must be >= block + period"; return CA_ERR_INVALID; }
         if (off >= cfg->max_ir_frames) { e->tiers.resize(j); break; }
         t.m = t.S / B; t.off = off;
         const uint32_t rest = (cfg->max_ir_frames - off + t.S - 1) / t.S;
@@ -885,6 +925,10 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaEventCreateWithFlags(&e->pm_tail, cudaEventDisableTiming));
     for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
+    e->async_tiers = (cfg->flags & CA_FLAG_ASYNC_TIERS) && e->tiers.size() > 1 && !(cfg->flags & CA_FLAG_PROFILE);
+    CA_CUDA(cudaStreamCreateWithPriority(&e->s_def, cudaStreamNonBlocking, prio_lo));
+    CA_CUDA(cudaEventCreateWithFlags(&e->ev_period, cudaEventDisableTiming));
+    for (auto &ev : e->ev_def) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->pdl = !(cfg->flags & CA_FLAG_GRAPH);
     if (const char *pd = getenv("CA_PDL")) e->pdl = atoi(pd) != 0;
     if (const char *tr = getenv("CA_PIPE_TRACE")) e->trace_at = (uint64_t)atoll(tr);
@@ -1082,7 +1126,7 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
     // the reference's prepare() does the same (conv.cu:237)
     if (foreign) CA_CUDA(cudaDeviceSynchronize());
     {
-        const int rc = pipe_drain(e);  // lane M may still read the IR bank
+        const int rc = drain_all(e);  // lane M / the asynchronous tiers may still read the IR bank
         if (rc) return rc;
     }
     frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
@@ -1183,7 +1227,7 @@ int ca_set_active(ca_engine *e, uint32_t n)
 {
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
     if (n == e->n_active) return CA_OK;
-    const int rc = pipe_drain(e);
+    const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
     e->n_active = n;
@@ -1222,7 +1266,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     const bool graph = (e->cfg.flags & CA_FLAG_GRAPH) != 0, profile = (e->cfg.flags & CA_FLAG_PROFILE) != 0;
     // Large batches: cut the instances into chunks and pipeline H2D | kernels | D2H on three streams so
     // the PCIe copies (2 KB per instance and direction) hide behind the kernels of the other chunks.
-    const uint32_t chunks = (graph || profile || e->n_active < 512) ? 1u : std::min<uint32_t>(e->io_chunks, e->n_active / 256);
+    const uint32_t chunks = (graph || profile || e->n_active < 512 || e->async_tiers) ? 1u : std::min<uint32_t>(e->io_chunks, e->n_active / 256);
     int rc = CA_OK;
     if (use_pipeline(e)) {
         rc = run_pipelined(e, e->d_in, e->d_out, std::max(1u, chunks), src, dst);
@@ -1271,7 +1315,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
 int ca_sync(ca_engine *e)
 {
     if (!e) return CA_ERR_INVALID;
-    const int rc = pipe_drain(e);
+    const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
     return CA_OK;

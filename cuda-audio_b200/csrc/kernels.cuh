@@ -54,7 +54,18 @@ struct Ctl {
     // period counter.  k_forward and k_mac read t; k_forward publishes t_next = t + 1; k_inverse reads
     // only t_next and finally sets t = t_next, so no kernel reads a field another CTA of it writes.
     unsigned long long t, t_next;
+    // CA_FLAG_ASYNC_TIERS under a graph: the long tiers of the block that closed at t_end run while the
+    // next period advances t, so they read t_end from t_def[t_end & 1] (written together with t)
+    unsigned long long t_def[2];
 };
+
+// period count for the deferred kernels: host argument (host-driven launches), the parity slot
+// (t_sel = 1 + (t_end & 1), asynchronous tiers inside a graph) or the live counter
+__device__ __forceinline__ unsigned long long ctl_tend(const Ctl *ctl, unsigned long long tend_host, uint32_t t_sel, uint32_t bias)
+{
+    if (tend_host) return tend_host;
+    return t_sel ? ctl->t_def[t_sel - 1u] : ctl->t + bias;
+}
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
 // attribute may become resident while the previous kernel of the stream drains; pdl_wait() blocks until
@@ -376,6 +387,7 @@ struct MacArgs {
     // pipelined batch schedule: the launch may run while k_inverse advances ctl->t, so the host passes
     // the period count itself (0: read ctl->t + t_bias)
     unsigned long long tend_host;
+    uint32_t t_sel;  // see ctl_tend()
 };
 
 constexpr int kMacConsumers = 256;
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
     const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = a.inst0 + blockIdx.z * a.inst_stride;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
-    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t + a.t_bias;  // periods completed at the end of this tier block
+    const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, a.t_bias);  // periods completed at the end of this tier block
     const uint32_t phase = inst % a.m;
     const unsigned long long n_fire = (tend + phase) / a.m;
 
@@ -626,7 +638,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
-    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t + a.t_bias;
+    const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, a.t_bias);
     // m (tier block / period) and n_tiles (S / BT) are powers of two: shifts and masks instead of the
     // software 64-bit divisions, which sat on the producer's critical path at every work item (ncu r01)
     const uint32_t m_log = 31 - __clz((int)a.m), m_mask = a.m - 1u;
@@ -978,7 +990,7 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
             }
         }
     }
-    if (a.advance && local == 0 && tid == 0) a.ctl->t = t + 1ull;  // forward + MAC of this period are done (nobody here reads ctl->t)
+    if (a.advance && local == 0 && tid == 0) { a.ctl->t = t + 1ull; a.ctl->t_def[(t + 1ull) & 1ull] = t + 1ull; }  // forward + MAC of this period are done (nobody here reads ctl->t)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1017,7 +1029,7 @@ struct FusedCfg {
     static constexpr uint32_t SMEM_BYTES = kFusedStages * STAGE_BYTES + XNEW_BYTES + YS_BYTES + (2 * kFusedStages + 1) * 8 + 16;
 };
 
-__global__ void k_tick(Ctl *ctl) { ctl->t = ctl->t_next; }  // the fused kernel reads ctl->t in every CTA: advance afterwards
+__global__ void k_tick(Ctl *ctl) { ctl->t = ctl->t_next; ctl->t_def[ctl->t_next & 1ull] = ctl->t_next; }  // the fused kernel reads ctl->t in every CTA: advance afterwards
 
 template <int R, int NOUT>
 __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
@@ -1373,6 +1385,7 @@ struct TierFwdArgs {
     uint32_t n_items_alloc, n_in, nv, Lring, ring_len, S, s_log, m, B;
     uint32_t inst0, inst_stride;  // firing instances: inst0 + i * inst_stride
     unsigned long long tend_host;  // see MacArgs
+    uint32_t t_sel;
 };
 
 // one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
@@ -1387,7 +1400,7 @@ __global__ void __launch_bounds__(kTierThreads, 2) k_tier_forward(const TierFwdA
     const uint32_t inst = a.inst0 + blockIdx.z * a.inst_stride;
     const uint32_t item = inst * a.n_in + blockIdx.y;
     const uint32_t w = item * a.nv + v;
-    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
+    const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
     if (!((st.active >> v) & 1u)) return;
     __shared__ uint32_t s_slot;
@@ -1428,6 +1441,7 @@ struct TierInvArgs {
     uint32_t n_split, n_out, S, s_log, B, off, acc_len;
     uint32_t inst0, inst_stride;
     unsigned long long tend_host;  // see MacArgs
+    uint32_t t_sel;
 };
 
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off
@@ -1440,7 +1454,7 @@ __global__ void __launch_bounds__(kTierThreads, 2) k_tier_inverse(const TierInvA
     const uint32_t z = blockIdx.y, o = blockIdx.x;  // grid (output, firing instance)
     const uint32_t inst = a.inst0 + z * a.inst_stride;
     const uint32_t item = inst * a.n_out + o;
-    const unsigned long long tend = a.tend_host ? a.tend_host : a.ctl->t;
+    const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     // sum of the partial spectra (position order), 8 independent float4 loads in flight per thread
     {
         const float4 *src = reinterpret_cast<const float4 *>(a.Ypart + (((size_t)z * a.n_split) * a.n_out + o) * a.S);

@@ -57,8 +57,13 @@ enum ca_flags {
     CA_FLAG_STREAMING = 1u << 1,  /* working set >> L2: evict-first hints on spectra loads     */
     CA_FLAG_L2_PERSIST = 1u << 2, /* pin IR spectra + FDL in L2 (access-policy window)         */
     CA_FLAG_PROFILE = 1u << 3,    /* record CUDA events around every kernel (ca_get_stats)     */
-    CA_FLAG_RAW_WET = 1u << 4     /* output the unclamped wet signal only: for partition-range
+    CA_FLAG_RAW_WET = 1u << 4,    /* output the unclamped wet signal only: for partition-range
                                    * shards whose partial outputs are summed before clamp + dry */
+    CA_FLAG_ASYNC_TIERS = 1u << 5 /* non-uniform partitioning, latency schedule: every long tier starts one
+                                   * period later in the IR (offset >= block + period; ca_config_auto_tiers
+                                   * plans it), so its result is due two periods after its block closes and
+                                   * the tier work runs on a low-priority stream BESIDE the next period's
+                                   * output path instead of in front of it (flat p99) */
 };
 
 typedef struct ca_engine ca_engine;

@@ -307,3 +307,60 @@ def test_pipelined_chunked_host_path_large_batch(monkeypatch):
     for s in (0, 599):
         truth = O.engine_truth(x[s], [bank[s % 4], bank[(s + 1) % 4]], [dict(wet=1.0)] * 2)
         assert O.rel_l2(y1[s, 0], truth[0]) < 5e-6
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_async_tiers_match_fp64_and_never_race(graph):
+    """CA_FLAG_ASYNC_TIERS: every long tier starts one period later in the IR, its work runs on a
+    low-priority stream beside the next period (result due two periods after its block closes).
+    Checked against the fp64 oracle (the partition plan differs from the synchronous one, so not
+    bitwise against it) for one and several instances, with and without a CUDA graph, through a
+    cross-fade, a predelay, an IR load and a change of the active count while tiers are in flight;
+    two identical runs must agree to the last bit (no race between the tier stream and the periods)."""
+    m = ca()
+    B, K = 64, 5
+    L = 64 * 9 + 512 * 4 + 2048 * 3 - 77
+    irs = [irs2x2(L, 9300 + 8 * s) for s in range(K)]
+    n = B * 220
+    x = np.stack([np.stack([O.synth_audio(n, 9800 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    flags = m.FLAG_ASYNC_TIERS | (m.FLAG_GRAPH if graph else 0)
+
+    def go():
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K + 1, tiers="auto", tier_growth=8, tier_max_block=2048,
+                      max_voices=2, flags=flags) as e:
+            st = e.stats()
+            blocks, offs = list(st.tier_block[:st.n_tiers]), list(st.tier_offset[:st.n_tiers])
+            assert len(blocks) == 3 and all(offs[j] >= blocks[j] + B for j in range(1, 3)), (blocks, offs)
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=0.8, dry=0.1, predelay=9 * s, panWet=0.1 * s - 0.2)
+                    e.set_glide(s, i, 0.8)
+            out = np.zeros((K, 2, n), np.float32)
+            for t in range(n // B):
+                if t == 70:
+                    e.set_params(3, 1, select=2, wet=0.8, dry=0.1, predelay=27, panWet=0.1, vsteps=25)
+                if t == 90:
+                    e.load_ir(2 * K, irs[0][0][0], irs[0][0][1])
+                if t == 150:
+                    e.set_active(3)
+                k = e.n_active
+                out[:k, :, t * B:(t + 1) * B] = e.process(x[:k, :, t * B:(t + 1) * B])
+            return out
+
+    y = go()
+    assert np.array_equal(y, go())
+    for s in (0, 2, 4):
+        truth = O.engine_truth(x[s], irs[s], [dict(wet=0.8, dry=0.1, panWet=0.1 * s - 0.2)] * 2, predelay=9 * s)
+        stop = n if s < 3 else B * 150
+        for o in range(2):
+            assert O.rel_l2(y[s, o, :stop], truth[o][:stop]) < 5e-6, (graph, s, o, O.rel_l2(y[s, o, :stop], truth[o][:stop]))
+
+
+def test_async_tiers_reject_plans_without_slack():
+    m = ca()
+    with pytest.raises(m.CaError) as ei:
+        m.Engine(period=64, max_ir_frames=64 * 8 + 512 * 4, tiers=[(64, 8), (512, 0)], flags=m.FLAG_ASYNC_TIERS)
+    assert ei.value.code == -1
+    with m.Engine(period=64, max_ir_frames=64 * 9 + 512 * 4, tiers=[(64, 9), (512, 0)], flags=m.FLAG_ASYNC_TIERS) as e:
+        assert e.stats().n_tiers == 2
