@@ -91,3 +91,44 @@ def test_auto_tiers_plan_is_valid():
     assert m.lib().ca_config_auto_tiers(ctypes.byref(cfg), 0, 0) == -1
     cfg = m.default_config(period=64)
     assert m.lib().ca_config_auto_tiers(ctypes.byref(cfg), 3, 0) == -1
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (gcc -std=c99 -pedantic -Werror) includes the header,
+    calls the configuration entry points and links against the shared library -- what a cgo / JNI / ctypes
+    binding relies on.  Without a GPU ca_create must return CA_ERR_CUDA, never fall back."""
+    import shutil
+    import subprocess
+    import cuda_audio_b200 as m
+    m.build()
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "cuda_audio_b200.h"
+int main(void)
+{
+    ca_config cfg;
+    ca_engine *e = NULL;
+    int rc;
+    ca_config_init(&cfg);
+    cfg.period = 64; cfg.max_ir_frames = 480000; cfg.flags = CA_FLAG_ASYNC_TIERS;
+    rc = ca_config_auto_tiers(&cfg, 0, 0);
+    printf("api=%d rc=%d tiers=%u", ca_api_version(), rc, cfg.n_tiers);
+    { unsigned j; for (j = 0; j < cfg.n_tiers; j++) printf(" %ux%u", cfg.tier_block[j], cfg.tier_parts[j]); }
+    rc = ca_create(&cfg, &e);
+    printf(" create=%d (%s)\n", rc, ca_strerror(rc));
+    if (rc == CA_OK) ca_destroy(e);
+    return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    lib_dir = os.path.dirname(m.LIB_PATH)
+    cc = shutil.which("gcc")
+    r = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", lib_dir, "-lcuda_audio_b200", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout
+    assert "api=1 rc=0 tiers=4 64x9 512x7 4096x3 16384x0" in out, out   # one more tier-0 partition than the synchronous plan
+    from tests import conftest
+    assert ("create=0" in out) if conftest._has_gpu() else ("create=-2" in out), out
