@@ -55,6 +55,21 @@ inline void launch_k(bool pdl, void (*fn)(P...), dim3 grid, dim3 block, size_t s
     cudaLaunchKernelEx(&cfg, fn, P(args)...);
 }
 
+// complex points per thread of the CTA-level tier FFT: threads = clamp(S / div, min, 512).  Measured r01
+// (K = 4096, tier forward + inverse per period): div 4: 149 us, 8: 134, 16: 123 (128 threads for the 2 K
+// tier: twice the CTAs per SM, one wave instead of 1.7), 32 with min 64: 128; 12 288 instances: +3.9 %.
+inline uint32_t tier_div()
+{
+    static const uint32_t d = [] { const char *v = getenv("CA_TIER_DIV"); const int x = v ? atoi(v) : 16; return (uint32_t)(x >= 2 && x <= 64 ? x : 16); }();
+    return d;
+}
+
+inline uint32_t tier_min()
+{
+    static const uint32_t d = [] { const char *v = getenv("CA_TIER_MIN"); const int x = v ? atoi(v) : 128; return (uint32_t)(x >= 32 && x <= 512 ? x : 128); }();
+    return d;
+}
+
 struct MacVariant { mac_fn fn; uint32_t smem; int kc; macp_fn pfn; uint32_t psmem; };
 
 template <int BT, int NOUT, int MULT, int NSTAGE>
@@ -340,7 +355,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = 
         cudaStream_t st = fork ? e->s_tier[j] : base;
         if (fork) CA_CUDA(cudaStreamWaitEvent(st, e->fork_ev, 0));
         const uint32_t smem = t.S * sizeof(float2);
-        const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
+        const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div()));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, th, tsel};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
         const bool pdl = e->pdl && !profile;
@@ -363,7 +378,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = 
             const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
             if (!count) continue;
             CA_CUDA(cudaStreamWaitEvent(base, e->join_ev[j], 0));
-            const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8));
+            const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div()));
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th, tsel};
             launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), base, ia);
         }
@@ -547,7 +562,7 @@ bool use_pipeline(const ca_engine *e)
     return e->pipe_mode == 1;
 }
 
-uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8)); }
+uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div())); }
 
 // long-tier lanes: inverse transforms of the tiers that fired at `pipe_prev_tend`, in tier order (they
 // accumulate into the same output ring).  e->stream joins them now (drain) or right before inv0.
@@ -1148,7 +1163,7 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
             a.h[0] = d_left; a.h[1] = d_right ? d_right : d_left;
             a.H = H; a.twM = t.tw; a.tw2M = t.tw + t.S;
             a.frames = frames; a.P = t.P; a.n_out = e->n_out; a.frame_off = t.off; a.S = t.S; a.s_log = t.s_log; a.scale = scale;
-            k_tier_ir<<<e->n_out * t.P, std::min<uint32_t>(kTierThreads, std::max<uint32_t>(128, t.S / 8)), t.S * sizeof(float2), e->stream>>>(a);
+            k_tier_ir<<<e->n_out * t.P, std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div())), t.S * sizeof(float2), e->stream>>>(a);
         }
         e->launches += 1;
     }

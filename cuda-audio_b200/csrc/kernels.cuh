@@ -1374,7 +1374,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
 // long tiers of the non-uniform partitioning (block S = 256 * 2^s_log, fired every m periods,
 // AFTER the period's output has been produced: k_inverse has already advanced ctl->t)
 // ------------------------------------------------------------------------------------------
-constexpr int kTierThreads = 512;  // launch bound; the host launches M/8 threads clamped to [128, 512]
+constexpr int kTierThreads = 512;  // launch bound; the host launches S/16 threads clamped to [128, 512] (engine.cu: tier_div)
 
 struct TierFwdArgs {
     const float *ring;    // [(item*nv + v)][ring_len]

@@ -1,5 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "^.\[3" | tail -6
-timeout 200 python tools/latency.py 256 192000 3000 2>&1 | grep "uniform \|g8 max16384"
-timeout 200 python tools/latency.py 64 480000 3000 2>&1 | grep "uniform \|g8 max16384"
+for d in 16 8; do CA_TIER_DIV=$d timeout 300 python bench.py --steps 100 --warmup 10 --no-latency --no-sustained --no-cpu-baseline --no-roofline 2>/dev/null | python -c "
+import json,sys
+j=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('div=$d value',j['value'],j['ms_per_step'],'e2e',j['e2e']['value'],j['e2e']['ms_per_step'])"; done
