@@ -20,7 +20,10 @@
 namespace ca {
 
 constexpr uint32_t kMaxPredelay = 8192;  // CONV_MAX_PREDELAY, conv.h:26-28
-constexpr int kFwdWarps = 4;
+#ifndef CA_FWD_WARPS
+#define CA_FWD_WARPS 4
+#endif
+constexpr int kFwdWarps = CA_FWD_WARPS;
 constexpr int kMaxVoices = 4;
 
 // per (instance, input): written by the host (ca_set_params), read by the kernels
@@ -150,7 +153,7 @@ struct FwdArgs {
 // One warp per (instance, input); it steps the voice state once and then runs every audible voice
 // (one in steady state, two or three during an IR cross-fade).
 template <int R>
-__global__ void __launch_bounds__(kFwdWarps * 32, 5) k_forward(const FwdArgs a)
+__global__ void __launch_bounds__(kFwdWarps * 32, 20 / kFwdWarps) k_forward(const FwdArgs a)
 {
     pdl_trigger();  // the next kernel of the stream may become resident while this one drains
     pdl_wait();     // before any global access and before any early exit: stream order holds transitively
@@ -876,7 +879,10 @@ struct InvArgs {
     unsigned long long t_host_p1;  // see FwdArgs
 };
 
-constexpr int kInvThreads = 128;
+#ifndef CA_INV_THREADS
+#define CA_INV_THREADS 128
+#endif
+constexpr int kInvThreads = CA_INV_THREADS;
 
 // PACKED: one warp per (instance, output), the warp sums the (few) partial spectra itself -- the
 // throughput schedule.  !PACKED: one CTA per item, all 128 threads sum the n_split partials through

@@ -14,7 +14,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.normpath(os.path.join(_PKG, "..", ".."))          # cuda-audio_b200/
-LIB_PATH = os.path.join(ROOT, "libcuda_audio_b200.so")
+LIB_PATH = os.environ.get("CA_B200_LIB") or os.path.join(ROOT, "libcuda_audio_b200.so")  # override: development A/B builds
 
 CA_MAX_TIERS = 4
 FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 4, 8, 16
