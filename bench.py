@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -131,6 +131,53 @@ def mac_traffic(kind, instances):
         return int(j["dram_bytes_per_instance_period" if kind == "tiered" else "dram_bytes_per_instance"] * instances)
     except Exception:
         return None
+
+
+def synth_ir_pair(torch, dev, slot):
+    """The stereo IR of bank slot `slot` exactly as build_engine() loads it (same device generator)."""
+    n = torch.arange(IR_FRAMES, device=dev, dtype=torch.float32)
+    env = torch.exp(-6.91 * n / (0.8 * IR_FRAMES))
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + slot)
+    h = torch.randn(2, IR_FRAMES, device=dev, generator=g) * env
+    return h / h.pow(2).sum(dim=1, keepdim=True).sqrt()
+
+
+def parity_check(e, ca, torch, dev, K, x_dev, y_dev, stream, periods, rank):
+    """Run `periods` more periods on the benchmarked engine; instances first / two middle / last get fresh
+    noise and a restarted history and are compared with the fp64 oracle (test infrastructure: oracle/)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    picks = sorted(set([0, K // 3, (2 * K) // 3, K - 1]))
+    idx = torch.tensor(picks, device=dev, dtype=torch.long)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242 + rank)
+    xs = (torch.randn(len(picks), 2, periods * B, device=dev, generator=g) * 0.1).clamp_(-0.9, 0.9)
+    ys = torch.zeros_like(xs)
+    keep = x_dev[idx].clone()
+    e.sync()
+    for s in picks:
+        for i in range(2):
+            e.set_glide(s, i, 0.5)          # jump: one voice at coefficient 0.5, history dropped
+    with torch.cuda.stream(stream):         # the engine's own stream: copies ordered with its kernels
+        for t in range(periods):
+            x_dev[idx] = xs[:, :, t * B:(t + 1) * B]
+            e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
+            ys[:, :, t * B:(t + 1) * B] = y_dev[idx]
+        x_dev[idx] = keep
+    e.sync()
+    torch.cuda.synchronize()
+    xs_h, ys_h = xs.cpu().numpy().astype(np.float64), ys.cpu().numpy().astype(np.float64)
+    pr = [dict(wet=0.5, dry=0.5)] * 2
+    errs = []
+    for j, s in enumerate(picks):
+        irs = [synth_ir_pair(torch, dev, 2 * s + i).cpu().numpy().astype(np.float64) for i in range(2)]
+        truth = O.engine_truth(xs_h[j], [[irs[i][o] for o in range(2)] for i in range(2)], pr)
+        errs.append(max(O.rel_l2(ys_h[j, o], truth[o]) for o in range(2)))
+    return {"instances": picks, "periods": periods, "rel_l2": [float(f"{v:.3e}") for v in errs], "rel_l2_max": float(f"{max(errs):.3e}"),
+            "against": "fp64 FFT convolution (oracle.engine_truth), wet = dry = 0.5", "tolerance": 1e-5}
 
 
 def tier_desc(st):
@@ -204,7 +251,9 @@ def run_ours(args):
     for _ in range(warm):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
     e.sync()
-    steps = ((args.steps + cycle - 1) // cycle) * cycle if args.round_to_cycle else args.steps
+    # a whole number of tier launch-pattern cycles (64 periods with the 16 K tier): every timed region sees
+    # the same mix of long-tier launches whatever --steps is
+    steps = args.steps if args.no_round_to_cycle else ((args.steps + cycle - 1) // cycle) * cycle
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -236,12 +285,30 @@ def run_ours(args):
     st_main = e.stats()
 
     extras = {}
+    # ---- parity spot-check of THIS engine (same allocation, flags and schedule as the timed loops): four
+    #      instances spread over the arena restart their history (ca_set_glide drops it), get fresh noise
+    #      for `parity_periods` periods while all the others keep running, and are compared with the fp64
+    #      oracle (oracle.engine_truth) ----
+    if not args.no_parity:
+        extras["parity_check"] = parity_check(e, ca, torch, dev, K, x_dev, y_dev, stream, args.parity_periods, rank)
+        if world > 1:
+            worst = max_over_ranks(extras["parity_check"]["rel_l2_max"])
+            extras["parity_check"]["rel_l2_max_over_ranks"] = worst
     # ---- sustained real-time channels through ca_process: largest K whose p99 per-period wall time
     #      over >= 2000 consecutive periods stays below the deadline / 25 % of it ----
     if rank == 0 and world == 1 and not args.no_sustained:
+        active = [K]
+
         def p99_at(k, periods):
+            prev, grow = active[0], k > active[0]
             e.set_active(k)
-            for _ in range(2 * cycle):
+            active[0] = k
+            if grow:
+                for s_ in range(prev, k):       # reactivated instances restart (ca_set_active): skip their fade-in ...
+                    for i_ in range(2):
+                        e.set_glide(s_, i_, 0.5)
+            # ... and run them back into steady state (every delay-line slot in use) before timing
+            for _ in range(STEADY + cycle if grow else 2 * cycle):
                 e.process_raw(pin.ptr, pout.ptr)
             e.reset_stats()
             for _ in range(periods):
@@ -273,6 +340,7 @@ def run_ours(args):
         res["note"] = (f"{K} instances hold {st_main.device_bytes / 1e9:.0f} GB of distinct IR spectra + delay lines; "
                        "'capped_by_allocation' means HBM capacity, not time, limits the count")
         extras["sustained_through_ca_process"] = res
+        extras["sustained_channels"] = res["p99_lt_25pct_deadline"]["channels"]
         e.set_active(K)
     e.close()
     e = None
@@ -371,7 +439,9 @@ def run_ours(args):
     if rank == 0:
         out = {
             "metric": METRIC, "value": round(world * K * deadline_s / (ms_dev * 1e-3), 1), "unit": "rt_channels",
-            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(ms_dev, 4),
+            "n_gpus": world, "steps": steps, "steps_requested": args.steps, "warmup": warm, "warmup_requested": args.warmup,
+            "warmup_note": "warm-up runs past the IR length + one tier cycle: the engine skips delay-line slots older than a voice's start, so earlier periods do less work than a running system",
+            "ms_per_step": round(ms_dev, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_rate": FS, "period": B, "ir_frames": IR_FRAMES,
                        "partitioning": "uniform" if args.uniform else "non-uniform (tiers phase-staggered over instances)",
@@ -382,7 +452,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": round(world * K * deadline_s / (ms_e2e * 1e-3), 1), "unit": "rt_channels", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": K * 2 * B * 4, "d2h_bytes_per_step": K * 2 * B * 4, "api": "ca_process (C ABI), pinned host buffers"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "library": os.path.relpath(ca.LIB_PATH, ROOT),
             "roofline": roof, "cpu_baseline": cpu, "output_rms": round(y_rms, 5),
         }
         out.update(extras)
@@ -580,7 +650,9 @@ def main():
     ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
     ap.add_argument("--uniform-instances", type=int, default=2048)
     ap.add_argument("--profile-instances", type=int, default=4096)
-    ap.add_argument("--round-to-cycle", action="store_true", help="round --steps up to a multiple of the tier launch-pattern period")
+    ap.add_argument("--no-round-to-cycle", action="store_true", help="time exactly --steps periods instead of rounding up to a multiple of the tier launch-pattern period (64)")
+    ap.add_argument("--parity-periods", type=int, default=896, help="periods of the in-bench parity spot-check (>= 832: the 16 K tier's delay line wraps)")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--sustain-periods", type=int, default=2000)
     ap.add_argument("--latency-periods", type=int, default=2000)
     ap.add_argument("--pace-us", type=float, default=533.3, help="period interval of the paced latency measurement (real time: 5333.3)")

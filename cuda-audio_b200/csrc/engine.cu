@@ -1014,9 +1014,11 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
         CA_CUDA(cudaFuncSetAttribute((const void *)k_tier_ir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s_max * sizeof(float2))));
     }
-    // time-domain ring per voice: predelay reach + the longest overlap-save window
+    // time-domain ring per voice: predelay reach + the longest overlap-save window + one period: with
+    // CA_FLAG_ASYNC_TIERS a tier forward of t_end reads [t_end*B - 2S, t_end*B) WHILE the forward of period
+    // t_end clears [t_end*B + 8192, +B) and scatter-adds up to t_end*B + 8191 + B; those must not alias
     e->ring_len = 1;
-    while (e->ring_len < kMaxPredelay + 2 * s_max) e->ring_len <<= 1;
+    while (e->ring_len < kMaxPredelay + 2 * s_max + e->B) e->ring_len <<= 1;
     uint32_t total_periods = 0;
     for (auto &t : e->tiers) total_periods = std::max(total_periods, (t.off + t.P * t.S) / e->B + 2 * t.m);
     e->ring_out = std::max(total_periods + e->k_off, e->ring_len / e->B) + 2;
@@ -1245,6 +1247,16 @@ int ca_set_active(ca_engine *e, uint32_t n)
     const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
+    if (n > e->n_active) {
+        // instances that were parked keep frozen voice state, delay lines and tier output: a reactivated
+        // instance must start like a new one (voices restart at the current period, so every older
+        // delay-line block is skipped, and the voice's first forward clears its time ring) instead of
+        // replaying pre-deactivation audio as a tail
+        const size_t i0 = (size_t)e->n_active * e->n_in, cnt = (size_t)(n - e->n_active) * e->n_in, n_alloc = (size_t)e->n_inst * e->n_in;
+        for (int b = 0; b < 2; b++) CA_CUDA(cudaMemsetAsync(e->d_st + b * n_alloc + i0, 0, cnt * sizeof(ItemState), e->stream));
+        if (e->d_acc) CA_CUDA(cudaMemsetAsync(e->d_acc + (size_t)e->n_active * e->n_out * e->acc_len, 0, (size_t)(n - e->n_active) * e->n_out * e->acc_len * sizeof(float), e->stream));
+        CA_CUDA(cudaStreamSynchronize(e->stream));
+    }
     e->n_active = n;
     return prewarm_graphs(e);  // not a real-time call: rebuild the graphs for the new batch size now
 }

@@ -45,8 +45,12 @@ WavData wav_read(const std::string &path, float scale)
     const bool isFloat = w.audioFormat == 3 && bytes == 4;
     const bool isPcm = w.audioFormat == 1 && (bytes == 2 || bytes == 3 || bytes == 4);
     if (!w.channels || (!isFloat && !isPcm)) { w.error = "unsupported sample format in " + path; return w; }
-    if (!blockAlign) blockAlign = (uint16_t)(bytes * w.channels);
+    // a header whose blockAlign is smaller than one frame would walk the sample loop past the data chunk
+    const size_t frameBytes = (size_t)bytes * w.channels;
+    if (!blockAlign) blockAlign = (uint16_t)frameBytes;
+    if (blockAlign < frameBytes) { w.error = "blockAlign smaller than channels x bytes per sample in " + path; return w; }
     w.frames = dataLen / blockAlign;
+    if (w.frames && (w.frames - 1) * blockAlign + frameBytes > dataLen) w.frames--;  // last frame must lie inside the chunk
     w.ch.assign(w.channels, std::vector<float>(w.frames));
     const unsigned char *d = file.data() + dataPos;
     for (size_t n = 0; n < w.frames; n++)

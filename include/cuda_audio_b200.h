@@ -150,7 +150,9 @@ int ca_get_params(ca_engine *e, uint32_t instance, uint32_t input, ca_params *p)
 /* jump the wet glide of (instance, input) to `g` (tests: skip the 1-0.8^k fade-in) */
 int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g);
 
-/* Only the first n instances are processed by ca_process* (default: all). */
+/* Only the first n instances are processed by ca_process* (default: all).  Not a real-time call.
+ * Instances that become active again restart like new ones: voices, delay lines and pending tier
+ * output are reset (no replay of pre-deactivation audio); re-apply ca_set_glide to skip their fade-in. */
 int ca_set_active(ca_engine *e, uint32_t n);
 
 /* One period for every active instance.

@@ -364,3 +364,69 @@ def test_async_tiers_reject_plans_without_slack():
     assert ei.value.code == -1
     with m.Engine(period=64, max_ir_frames=64 * 9 + 512 * 4, tiers=[(64, 9), (512, 0)], flags=m.FLAG_ASYNC_TIERS) as e:
         assert e.stats().n_tiers == 2
+
+
+def test_async_tiers_block_4096_max_predelay_ring_has_slack():
+    """Largest tier block 4096 with the maximal predelay: the time ring must be long enough that the
+    forward of period t_end (clear-ahead at +8192, scatter up to +8191 + B) never aliases the window
+    [t_end*B - 2*4096, t_end*B) a tier forward still reads on the asynchronous stream."""
+    m = ca()
+    B = 64
+    L = 64 * 9 + 512 * 8 + 4096 * 3 - 5
+    irs = irs2x2(L, 9700)
+    n = B * 600
+    x = np.stack([O.synth_audio(n, 9900 + i) for i in range(2)])
+    pr = [dict(wet=0.9, dry=0.1), dict(wet=0.7, dry=0.2)]
+
+    def go():
+        with m.Engine(period=B, max_ir_frames=L, tiers="auto", tier_growth=8, tier_max_block=4096, flags=m.FLAG_ASYNC_TIERS) as e:
+            st = e.stats()
+            assert list(st.tier_block[:st.n_tiers]) == [64, 512, 4096]
+            for i in range(2):
+                e.load_ir(i, irs[i][0], irs[i][1])
+                e.set_params(0, i, select=i, predelay=8191, **pr[i])
+                e.set_glide(0, i, pr[i]["wet"])
+            return e.render(x[None])[0]
+
+    y = go()
+    for _ in range(3):
+        assert np.array_equal(y, go())
+    truth = O.engine_truth(x, irs, pr, predelay=8191)
+    for o in range(2):
+        assert O.rel_l2(y[o], truth[o]) < 5e-6, (o, O.rel_l2(y[o], truth[o]))
+
+
+def test_reactivated_instances_start_clean():
+    """ca_set_active(n) followed by a later increase: the instances that were parked restart like new
+    ones (no replay of pre-deactivation audio as a tail)."""
+    m = ca()
+    B, L, K = 64, 64 * 8 + 512 * 5 - 3, 3
+    irs = irs2x2(L, 9750)
+    n1, n2, n3 = 40, 30, 120
+    x = np.stack([np.stack([O.synth_audio(B * (n1 + n2 + n3), 9950 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    pr = [dict(wet=1.0, dry=0.0)] * 2
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, tiers=[(64, 8), (512, 0)]) as e:
+        for i in range(2):
+            e.load_ir(i, irs[i][0], irs[i][1])
+        for s in range(K):
+            for i in range(2):
+                e.set_params(s, i, select=i, **pr[i])
+                e.set_glide(s, i, 1.0)
+        out = np.zeros((K, 2, B * (n1 + n2 + n3)), np.float32)
+        for t in range(n1 + n2 + n3):
+            if t == n1:
+                e.set_active(1)
+            if t == n1 + n2:
+                e.set_active(K)
+                for s in range(1, K):
+                    for i in range(2):
+                        e.set_glide(s, i, 1.0)      # skip the fade-in of the restarted voices
+            k = e.n_active
+            out[:k, :, t * B:(t + 1) * B] = e.process(x[:k, :, t * B:(t + 1) * B])
+    t0 = B * (n1 + n2)
+    truth0 = O.engine_truth(x[0], irs, pr)
+    assert O.rel_l2(out[0, 0], truth0[0]) < 5e-6               # instance 0 never stopped
+    for s in range(1, K):
+        truth = O.engine_truth(x[s][:, t0:], irs, pr)          # restarted: history before t0 is gone
+        for o in range(2):
+            assert O.rel_l2(out[s, o, t0:], truth[o]) < 5e-6, (s, o, O.rel_l2(out[s, o, t0:], truth[o]))
