@@ -172,11 +172,14 @@ def parity_check(e, ca, torch, dev, K, x_dev, y_dev, stream, periods, rank):
     xs_h, ys_h = xs.cpu().numpy().astype(np.float64), ys.cpu().numpy().astype(np.float64)
     pr = [dict(wet=0.5, dry=0.5)] * 2
     errs = []
+    # the restart drops the voices' delay-line history, but long-tier results computed before it are already
+    # queued in the output ring for up to 16384 + 256 samples: compare from period 80 on
+    skip = 80 * B
     for j, s in enumerate(picks):
         irs = [synth_ir_pair(torch, dev, 2 * s + i).cpu().numpy().astype(np.float64) for i in range(2)]
         truth = O.engine_truth(xs_h[j], [[irs[i][o] for o in range(2)] for i in range(2)], pr)
-        errs.append(max(O.rel_l2(ys_h[j, o], truth[o]) for o in range(2)))
-    return {"instances": picks, "periods": periods, "rel_l2": [float(f"{v:.3e}") for v in errs], "rel_l2_max": float(f"{max(errs):.3e}"),
+        errs.append(max(O.rel_l2(ys_h[j, o, skip:], truth[o][skip:]) for o in range(2)))
+    return {"instances": picks, "periods": periods, "compared_from_period": skip // B, "rel_l2": [float(f"{v:.3e}") for v in errs], "rel_l2_max": float(f"{max(errs):.3e}"),
             "against": "fp64 FFT convolution (oracle.engine_truth), wet = dry = 0.5", "tolerance": 1e-5}
 
 
