@@ -5,6 +5,7 @@
 // No cuFFT, no CPU fallback: if CUDA is not usable every entry point returns CA_ERR_CUDA.
 #include "../../include/cuda_audio_b200.h"
 #include "kernels.cuh"
+#include "kernels_rows.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -144,6 +145,10 @@ struct Tier {
     MacVariant mac{};
     uint32_t p_slots = 0;  // resident CTA slots of the persistent MAC (0: schedule disabled)
     bool p_force = false;
+    // FFT family of this tier's transforms: 0 = fft_warp / fft_cta (general), 1 = row FFTs, one CTA per
+    // transform (M1 = S / 256 <= 16), 2 = row FFTs, columns and rows as two launches (M1 = 32, 64)
+    int rows_mode = 0;
+    uint32_t M1 = 0;
 };
 
 }  // namespace
@@ -201,6 +206,8 @@ struct ca_engine {
     std::atomic<bool> par_dirty{true};
     std::vector<uint8_t> ir_loaded;
     FftFns fft{};
+    float2 *d_rowtw = nullptr;  // [W_256^n | W_512^k]: twiddles of the 256-point row FFT
+    bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
     bool fused = false;       // tier 0 runs as one fused kernel (k_fused0)
     uint32_t fused_smem = 0;
     // graphs: [0] = the period pipeline (tier 0), [mask] = the deferred tiers that fire together
@@ -283,6 +290,83 @@ void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t s
     }
 }
 
+// ---- FFT launches: row-FFT family (kernels_rows.cuh) where the size allows, else the general kernels ----
+void launch_fwd0(ca_engine *e, bool pdl, FwdArgs fa, cudaStream_t st)
+{
+    fa.rowtw = e->d_rowtw;
+    if (e->rows0) launch_k(pdl, k_fwd0_rows, dim3((fa.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, fa);
+    else launch_k(pdl, e->fft.fwd, dim3((fa.n_items + kFwdWarps - 1) / kFwdWarps), dim3(kFwdWarps * 32), 0, st, fa);
+}
+
+void launch_inv0(ca_engine *e, bool pdl, InvArgs ia, cudaStream_t st)
+{
+    ia.rowtw = e->d_rowtw;
+    if (ia.n_split <= 4) {
+        if (e->rows0) launch_k(pdl, k_inv0_rows, dim3((ia.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, ia);
+        else launch_k(pdl, e->fft.inv_packed, dim3((ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32)), dim3(kInvThreads), 0, st, ia);
+    } else {
+        launch_k(pdl, e->fft.inv, dim3(ia.n_items), dim3(kInvThreads), 0, st, ia);  // latency schedule: one CTA sums up to 256 partials
+    }
+}
+
+uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div())); }
+
+template <int M1>
+void launch_tfwd_rows(const Tier &t, bool pdl, const TierFwdArgs &fa, uint32_t nv, uint32_t n_in, uint32_t count, cudaStream_t st)
+{
+    if constexpr (M1 <= 16) {
+        launch_k(pdl, k_tfwd_fused<M1>, dim3(nv, n_in, count), dim3(M1 * 32), M1 * kRowSlots * sizeof(float2), st, fa);
+    } else {
+        launch_k(pdl, k_tcols_fwd<M1>, dim3(nv * 8, n_in, count), dim3(256), 0, st, fa);
+        launch_k(pdl, k_trows_fwd<M1>, dim3(nv * (M1 / 8), n_in, count), dim3(kRowsThreads), kRowsSmem, st, fa);
+    }
+}
+
+template <int M1>
+void launch_tinv_rows(const Tier &t, bool pdl, const TierInvArgs &ia, uint32_t n_out, uint32_t count, cudaStream_t st)
+{
+    if constexpr (M1 <= 16) {
+        launch_k(pdl, k_tinv_fused<M1>, dim3(n_out, count), dim3(M1 * 32), M1 * kRowSlots * sizeof(float2), st, ia);
+    } else {
+        launch_k(pdl, k_trows_inv<M1>, dim3(n_out * (M1 / 8), count), dim3(kRowsThreads), kRowsSmem, st, ia);
+        launch_k(pdl, k_tcols_inv<M1>, dim3(n_out * 8, count), dim3(256), 0, st, ia);
+    }
+}
+
+// forward transforms of tier t for `count` firing instances; returns the number of kernels launched
+uint32_t launch_tier_fwd(ca_engine *e, const Tier &t, bool pdl, TierFwdArgs fa, uint32_t count, cudaStream_t st)
+{
+    fa.rowtw = e->d_rowtw;
+    switch (t.rows_mode ? t.M1 : 0u) {
+    case 1: launch_tfwd_rows<1>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 2: launch_tfwd_rows<2>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 4: launch_tfwd_rows<4>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 8: launch_tfwd_rows<8>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 16: launch_tfwd_rows<16>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 32: launch_tfwd_rows<32>(t, pdl, fa, e->nv, e->n_in, count, st); return 2;
+    case 64: launch_tfwd_rows<64>(t, pdl, fa, e->nv, e->n_in, count, st); return 2;
+    default: launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(tier_threads(t)), t.S * sizeof(float2), st, fa); return 1;
+    }
+}
+
+uint32_t launch_tier_inv(ca_engine *e, const Tier &t, bool pdl, TierInvArgs ia, uint32_t count, cudaStream_t st)
+{
+    ia.rowtw = e->d_rowtw;
+    switch (t.rows_mode ? t.M1 : 0u) {
+    case 1: launch_tinv_rows<1>(t, pdl, ia, e->n_out, count, st); return 1;
+    case 2: launch_tinv_rows<2>(t, pdl, ia, e->n_out, count, st); return 1;
+    case 4: launch_tinv_rows<4>(t, pdl, ia, e->n_out, count, st); return 1;
+    case 8: launch_tinv_rows<8>(t, pdl, ia, e->n_out, count, st); return 1;
+    case 16: launch_tinv_rows<16>(t, pdl, ia, e->n_out, count, st); return 1;
+    case 32: launch_tinv_rows<32>(t, pdl, ia, e->n_out, count, st); return 2;
+    case 64: launch_tinv_rows<64>(t, pdl, ia, e->n_out, count, st); return 2;
+    default: launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(tier_threads(t)), t.S * sizeof(float2), st, ia); return 1;
+    }
+}
+
+// kernels of one firing of tier t (forward + MAC + inverse)
+uint32_t tier_launch_count(const Tier &t) { return t.rows_mode == 2 ? 5u : 3u; }
+
 // instances whose tier-j block closes at the end of period t_end - 1: s = r + i*m, r = (-t_end) mod m
 uint32_t tier_residue(const Tier &t, uint64_t tend) { return (uint32_t)((t.m - tend % t.m) % t.m); }
 uint32_t tier_count(const ca_engine *e, const Tier &t, uint64_t tend)
@@ -321,12 +405,11 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     }
     if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
     const bool pdl = e->pdl && !profile;
-    launch_k(pdl, e->fft.fwd, dim3((n_items + kFwdWarps - 1) / kFwdWarps), dim3(kFwdWarps * 32), 0, e->stream, fa);
+    launch_fwd0(e, pdl, fa, e->stream);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
     launch_mac(t0, ma, i1 - i0, e->stream, pdl);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    if (t0.n_split <= 4) launch_k(pdl, e->fft.inv_packed, dim3((ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32)), dim3(kInvThreads), 0, e->stream, ia);
-    else launch_k(pdl, e->fft.inv, dim3(ia.n_items), dim3(kInvThreads), 0, e->stream, ia);
+    launch_inv0(e, pdl, ia, e->stream);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -354,12 +437,10 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = 
         if (!count) continue;
         cudaStream_t st = fork ? e->s_tier[j] : base;
         if (fork) CA_CUDA(cudaStreamWaitEvent(st, e->fork_ev, 0));
-        const uint32_t smem = t.S * sizeof(float2);
-        const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div()));
         TierFwdArgs fa{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, th, tsel};
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][0], st));
         const bool pdl = e->pdl && !profile;
-        launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(threads), smem, st, fa);
+        launch_tier_fwd(e, t, pdl, fa, count, st);
         if (profile) CA_CUDA(cudaEventRecord(e->tev[j][1], st));
         MacArgs ma = mac_args(e, t, 0u);
         ma.inst0 = r; ma.inst_stride = t.m; ma.tend_host = th; ma.t_sel = tsel;
@@ -368,7 +449,7 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = 
         if (fork) CA_CUDA(cudaEventRecord(e->join_ev[j], st));
         else {
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th, tsel};
-            launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), smem, st, ia);
+            launch_tier_inv(e, t, pdl, ia, count, st);
             if (profile) CA_CUDA(cudaEventRecord(e->tev[j][3], st));
         }
     }
@@ -378,9 +459,8 @@ int launch_tiers(ca_engine *e, uint64_t tend, bool profile, cudaStream_t base = 
             const uint32_t count = tier_count(e, t, tend), r = tier_residue(t, tend);
             if (!count) continue;
             CA_CUDA(cudaStreamWaitEvent(base, e->join_ev[j], 0));
-            const uint32_t threads = std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div()));
             TierInvArgs ia{t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, th, tsel};
-            launch_k(e->pdl, k_tier_inverse, dim3(e->n_out, count), dim3(threads), t.S * sizeof(float2), base, ia);
+            launch_tier_inv(e, t, e->pdl, ia, count, base);
         }
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -493,7 +573,8 @@ int run_deferred(ca_engine *e)
             if (rc) return rc;
         }
         if (ts != e->stream) CA_CUDA(cudaEventRecord(e->ev_def[tend & 1], ts));
-        e->launches += 3 * firing;
+        for (size_t j = 1; j < e->tiers.size(); j++)
+            if (tier_count(e, e->tiers[j], tend)) e->launches += tier_launch_count(e->tiers[j]);
     }
     if (profile) {
         CA_CUDA(cudaEventRecord(e->ev[4], e->stream));
@@ -562,8 +643,6 @@ bool use_pipeline(const ca_engine *e)
     return e->pipe_mode == 1;
 }
 
-uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div())); }
-
 // long-tier lanes: inverse transforms of the tiers that fired at `pipe_prev_tend`, in tier order (they
 // accumulate into the same output ring).  e->stream joins them now (drain) or right before inv0.
 int pipe_join_tinv(ca_engine *e)
@@ -590,12 +669,11 @@ int pipe_finish_prev(ca_engine *e, bool join_now)
         if (prev) CA_CUDA(cudaStreamWaitEvent(st, e->ptinv_ev[prev], 0));
         TierInvArgs ia{(tend & 1) ? t.Ypart2 : t.Ypart, e->d_acc, e->d_ctl, t.tw, t.tw + t.S, t.n_split, e->n_out, t.S, t.s_log, e->B, t.off, e->acc_len, r, t.m, tend};
         trace_mark(e, j == 1 ? "tinv1'" : "tinv2+'", (int)(1 + j), true);
-        k_tier_inverse<<<dim3(e->n_out, count), tier_threads(t), t.S * sizeof(float2), st>>>(ia);
+        e->launches += launch_tier_inv(e, t, false, ia, count, st);
         trace_mark(e, "", (int)(1 + j), false);
         CA_CUDA(cudaEventRecord(e->ptinv_ev[j], st));
         e->tinv_pending[j] = true;
         prev = j;
-        e->launches += 1;
     }
     CA_CUDA(cudaGetLastError());
     return join_now ? pipe_join_tinv(e) : CA_OK;
@@ -659,7 +737,7 @@ int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks
         FwdArgs fa{d_in, e->d_ring, t0.X, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
                    n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in};
         trace_mark(e, "fwd0", 0, true);
-        e->fft.fwd<<<(n_items + kFwdWarps - 1) / kFwdWarps, kFwdWarps * 32, 0, e->stream>>>(fa);
+        launch_fwd0(e, false, fa, e->stream);
         trace_mark(e, "", 0, false);
         CA_CUDA(cudaEventRecord(e->pf_ev[c], e->stream));
         // lane M: tier-0 MAC of the chunk
@@ -679,7 +757,7 @@ int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks
                 TierFwdArgs tf{e->d_ring, t.X, e->d_st, e->d_ctl, t.tw, t.tw + t.S, n_alloc, e->n_in, e->nv, t.Lring, e->ring_len, t.S, t.s_log, t.m, e->B, r, t.m, tend};
                 CA_CUDA(cudaStreamWaitEvent(e->s_tier[j], e->pf_ev[c], 0));
                 trace_mark(e, j == 1 ? "tfwd1" : "tfwd2+", (int)(1 + j), true);
-                k_tier_forward<<<dim3(e->nv, e->n_in, count), tier_threads(t), t.S * sizeof(float2), e->s_tier[j]>>>(tf);
+                e->launches += launch_tier_fwd(e, t, false, tf, count, e->s_tier[j]) - 1;
                 trace_mark(e, "", (int)(1 + j), false);
                 CA_CUDA(cudaEventRecord(e->ptf_ev[j], e->s_tier[j]));
                 CA_CUDA(cudaStreamWaitEvent(e->s_mac, e->ptf_ev[j], 0));
@@ -701,8 +779,7 @@ int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks
         InvArgs ia{t0.Ypart, d_in, d_out, e->d_acc, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
                    t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
         trace_mark(e, "inv0", 0, true);
-        if (t0.n_split <= 4) e->fft.inv_packed<<<(ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32), kInvThreads, 0, e->stream>>>(ia);
-        else e->fft.inv<<<ia.n_items, kInvThreads, 0, e->stream>>>(ia);
+        launch_inv0(e, false, ia, e->stream);
         trace_mark(e, "", 0, false);
         e->launches += 1;
         if (h_dst) {
@@ -856,7 +933,7 @@ int ca_destroy(ca_engine *e)
     for (auto &ev : e->ptinv_ev) if (ev) cudaEventDestroy(ev);
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -951,9 +1028,13 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     const size_t n_items = (size_t)e->n_inst * e->n_in;
     uint32_t s_max = e->B, reach = e->B;
     e->arena_bytes = 0;
+    const bool legacy_fft = (cfg->flags & CA_FLAG_LEGACY_FFT) != 0;
+    e->rows0 = !legacy_fft && e->B == 256;
     for (size_t j = 0; j < e->tiers.size(); j++) {
         Tier &t = e->tiers[j];
         t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
+        t.M1 = t.S / 256;
+        t.rows_mode = (j == 0 || legacy_fft || t.S < 256) ? 0 : (t.M1 <= 16 ? 1 : 2);
         // bin tile of the long tiers: 512 complex (4 KB arrays) halves the CTA count per byte (+6 % measured)
         const uint32_t bt_max = getenv("CA_MAC_BT") ? (uint32_t)atoi(getenv("CA_MAC_BT")) : 512u;
         t.bt = std::min<uint32_t>(t.S, j == 0 ? 256u : bt_max);
@@ -1072,6 +1153,18 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaMemsetAsync(e->d_st, 0, 2 * n_items * sizeof(ItemState), e->stream));
     CA_CUDA(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
     CA_CUDA(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
+    {
+        // twiddles of the 256-point row FFT, fp64 -> fp32: [W_256^n | W_512^k]
+        std::vector<float2> tw(512);
+        for (int n = 0; n < 256; n++) {
+            const double a = -2.0 * M_PI * n / 256.0, b = -2.0 * M_PI * n / 512.0;
+            tw[n] = make_float2((float)cos(a), (float)sin(a));
+            tw[256 + n] = make_float2((float)cos(b), (float)sin(b));
+        }
+        CA_CUDA(cudaMalloc(&e->d_rowtw, tw.size() * sizeof(float2)));
+        CA_CUDA(cudaMemcpyAsync(e->d_rowtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+        CA_CUDA(cudaStreamSynchronize(e->stream));  // pageable source: staged before `tw` goes out of scope
+    }
     CA_CUDA(cudaMallocHost(&e->h_in, in_bytes));
     CA_CUDA(cudaMallocHost(&e->h_out, out_bytes));
     for (auto &u : e->h_upload) CA_CUDA(cudaMallocHost(&u, n_items * sizeof(InParamDev)));

@@ -148,6 +148,7 @@ struct FwdArgs {
     // host-driven launches (no graph): the period count + 1 comes as an argument, which takes the
     // ctl->t round trip off the head of every warp's chain of dependent loads (0: read ctl->t)
     unsigned long long t_host_p1;
+    const float2 *rowtw;  // [W_256^n | W_512^k] for the row-FFT kernels (kernels_rows.cuh)
 };
 
 // One warp per (instance, input); it steps the voice state once and then runs every audible voice
@@ -877,6 +878,7 @@ struct InvArgs {
     uint32_t advance;  // 1: this launch completes the period (advances ctl->t)
     uint32_t raw_wet;  // 1: store the unclamped wet block only (partition-range shards: clamp + dry after the reduce)
     unsigned long long t_host_p1;  // see FwdArgs
+    const float2 *rowtw;           // see FwdArgs
 };
 
 #ifndef CA_INV_THREADS
@@ -1392,6 +1394,7 @@ struct TierFwdArgs {
     uint32_t inst0, inst_stride;  // firing instances: inst0 + i * inst_stride
     unsigned long long tend_host;  // see MacArgs
     uint32_t t_sel;
+    const float2 *rowtw;           // see FwdArgs
 };
 
 // one CTA per (firing instance, input, voice): window of the last 2S samples -> R2C -> FDL slot
@@ -1448,6 +1451,7 @@ struct TierInvArgs {
     uint32_t inst0, inst_stride;
     unsigned long long tend_host;  // see MacArgs
     uint32_t t_sel;
+    const float2 *rowtw;           // see FwdArgs
 };
 
 // one CTA per (instance, output): partial-sum -> C2R -> overlap discard -> += output ring at +off

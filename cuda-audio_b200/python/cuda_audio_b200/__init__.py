@@ -19,6 +19,7 @@ LIB_PATH = os.environ.get("CA_B200_LIB") or os.path.join(ROOT, "libcuda_audio_b2
 CA_MAX_TIERS = 4
 FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 4, 8, 16
 FLAG_ASYNC_TIERS = 32
+FLAG_LEGACY_FFT = 64
 
 EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",

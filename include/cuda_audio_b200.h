@@ -59,11 +59,14 @@ enum ca_flags {
     CA_FLAG_PROFILE = 1u << 3,    /* record CUDA events around every kernel (ca_get_stats)     */
     CA_FLAG_RAW_WET = 1u << 4,    /* output the unclamped wet signal only: for partition-range
                                    * shards whose partial outputs are summed before clamp + dry */
-    CA_FLAG_ASYNC_TIERS = 1u << 5 /* non-uniform partitioning, latency schedule: every long tier starts one
+    CA_FLAG_ASYNC_TIERS = 1u << 5,/* non-uniform partitioning, latency schedule: every long tier starts one
                                    * period later in the IR (offset >= block + period; ca_config_auto_tiers
                                    * plans it), so its result is due two periods after its block closes and
                                    * the tier work runs on a low-priority stream BESIDE the next period's
                                    * output path instead of in front of it (flat p99) */
+    CA_FLAG_LEGACY_FFT = 1u << 6  /* A/B: transforms on the warp-shuffle / whole-transform-per-CTA FFT kernels
+                                   * of round 1 instead of the row-FFT family (same layouts, same results
+                                   * to fp32 rounding) */
 };
 
 typedef struct ca_engine ca_engine;

@@ -82,3 +82,68 @@ def test_cta_fft_layout(s):
     assert np.allclose(sm[pos], ref)
     back = wm.cta_inv(sm, s)
     assert np.allclose(back / M, z)
+
+
+# ---- row-FFT family (fft_rows.cuh / kernels_rows.cuh) ---------------------------------------------
+def test_row_fft_256_matches_numpy_and_is_bank_conflict_free():
+    from tests import _rows_fft_model as R
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    X, cf = R.row_fft(x)
+    assert np.abs(X - np.fft.fft(x)).max() < 1e-12
+    assert all(v == 1 for v in cf.worst.values()), cf.worst
+    Xi, _ = R.row_fft(x, inv=True)
+    assert np.abs(Xi - np.fft.ifft(x) * 256).max() < 1e-12
+    assert 8 * 36 <= R.ROW_SLOTS and 4 * 68 <= R.ROW_SLOTS and R.e3(255) < R.ROW_SLOTS
+
+
+@pytest.mark.parametrize("s", [0, 1, 3, 5])
+def test_four_step_position_order_and_split(s):
+    from tests import _rows_fft_model as R
+    rng = np.random.default_rng(s)
+    M = 256 << s
+    w = rng.standard_normal(2 * M)
+    z = w[0::2] + 1j * w[1::2]
+    Zp = R.four_step_forward(z, s)
+    pos = np.array([R.zpos(k, s) for k in range(M)])
+    assert np.abs(Zp[pos] - np.fft.fft(z)).max() < 1e-10
+    Xp = R.split_r2c_pos(Zp, s)
+    Xr = np.fft.rfft(w)
+    want = Xr[:M].copy()
+    want[0] = complex(Xr[0].real, Xr[M].real)
+    assert np.abs(Xp[pos] - want).max() < 1e-10
+    back = R.four_step_inverse(R.split_c2r_pos(Xp, s), s) / (2 * M)
+    assert np.abs(back - z).max() < 1e-12
+
+
+@pytest.mark.parametrize("M1", [32, 64])
+def test_two_stage_column_dft_and_row_pairing(M1):
+    """k_tcols_*: n1 = j + 8 b, radix M1/8 over b, twiddle W_M1^(jq), radix 8 over j, k1 = q + (M1/8) r;
+    k_trows_*: every row appears once and its split partner sits in the neighbouring warp (or is itself)."""
+    from tests import _rows_fft_model as R
+    rng = np.random.default_rng(M1)
+    Mb = M1 // 8
+    x = rng.standard_normal(M1) + 1j * rng.standard_normal(M1)
+    S = np.zeros((Mb, 8), complex)
+    for j in range(8):
+        y = R.dft(np.array([x[j + 8 * b] for b in range(Mb)]), False)
+        for q in range(Mb):
+            S[q, j] = y[q] * R.W(M1, j * q)
+    A = np.zeros(M1, complex)
+    for q in range(Mb):
+        u = R.dft(S[q], False)
+        for r in range(8):
+            A[q + Mb * r] = u[r]
+    assert np.abs(A - np.fft.fft(x)).max() < 1e-12
+
+    def row_of(rg, warp):
+        p, second = 4 * rg + (warp >> 1), warp & 1
+        return (M1 // 2 if second else 0) if p == 0 else (M1 - p if second else p)
+
+    rows = []
+    for rg in range(M1 // 8):
+        for warp in range(8):
+            r = row_of(rg, warp)
+            rows.append(r)
+            assert (M1 - r) % M1 in (r, row_of(rg, warp ^ 1))
+    assert sorted(rows) == list(range(M1))

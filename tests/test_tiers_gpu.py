@@ -430,3 +430,71 @@ def test_reactivated_instances_start_clean():
         truth = O.engine_truth(x[s][:, t0:], irs, pr)          # restarted: history before t0 is gone
         for o in range(2):
             assert O.rel_l2(out[s, o, t0:], truth[o]) < 5e-6, (s, o, O.rel_l2(out[s, o, t0:], truth[o]))
+
+
+@pytest.mark.parametrize("B,tiers", [
+    (256, [(256, 4), (1024, 4), (4096, 4), (16384, 0)]),    # row-FFT family: M1 = 4, 16 (one CTA), 64 (columns + rows)
+    (256, [(256, 2), (512, 3), (2048, 3), (8192, 0)]),      # M1 = 2, 8, 32
+    (32, [(32, 8), (256, 8), (2048, 0)]),                   # M1 = 1, 8 under a warp-FFT tier 0
+])
+def test_row_fft_family_matches_legacy_and_fp64(B, tiers):
+    """Every transform size of the row-FFT kernels (kernels_rows.cuh) against the round-1 FFT kernels on the
+    same input (CA_FLAG_LEGACY_FFT: same layouts, so only fp32 rounding differs) and against fp64, three
+    phase-staggered instances, predelay, pans, a mid-run IR switch (two voices active)."""
+    m = ca()
+    K = 3
+    L = sum(b * p for b, p in tiers[:-1]) + 3 * tiers[-1][0] - 11
+    n = ((L + 5 * tiers[-1][0]) // B) * B
+    irs = [irs2x2(L, 7100 + 8 * s) for s in range(K)]
+    x = np.stack([np.stack([O.synth_audio(n, 7200 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    pr = [dict(wet=0.9, dry=0.2, level=0.8, panWet=0.2, panDry=-0.3), dict(wet=0.7, dry=0.1, level=1.0, panWet=-0.4, panDry=0.1)]
+    t_switch = (n // B) // 2
+
+    def go(flags):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, flags=flags) as e:
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, predelay=5 + 40 * s, **pr[i])
+                    e.set_glide(s, i, pr[i]["wet"])
+            out = np.zeros((K, 2, n), np.float32)
+            for t in range(n // B):
+                if t == t_switch:
+                    e.set_params(2, 0, select=1, predelay=85, vsteps=20, **pr[0])   # instance 2 cross-fades input 0 to another IR
+                out[:, :, t * B:(t + 1) * B] = e.process(x[:, :, t * B:(t + 1) * B])
+            return out
+
+    y_new, y_old = go(0), go(m.FLAG_LEGACY_FFT)
+    for s in range(K):
+        for o in range(2):
+            assert O.rel_l2(y_new[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_new[s, o], y_old[s, o]))
+    for s in range(2):
+        truth = O.engine_truth(x[s], irs[s], pr, predelay=5 + 40 * s)
+        for o in range(2):
+            assert O.rel_l2(y_new[s, o], truth[o]) < 5e-6, (s, o, O.rel_l2(y_new[s, o], truth[o]))
+
+
+def test_row_fft_tier0_uniform_matches_legacy():
+    """Tier 0 at B = 256 on k_fwd0_rows / k_inv0_rows (uniform partitioning, batch of 5, predelay in and
+    out of the current block, clamp active) against the warp-shuffle kernels."""
+    m = ca()
+    B, L, K = 256, 256 * 9 - 3, 5
+    irs = irs2x2(L, 7300)
+    n = B * 60
+    x = np.stack([np.stack([O.synth_audio(n, 7400 + 2 * s + i, rms=0.5) for i in range(2)]) for s in range(K)])
+
+    def go(flags):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, flags=flags) as e:
+            for i in range(2):
+                e.load_ir(i, 2.0 * irs[i][0], 2.0 * irs[i][1])
+            for s in range(K):
+                for i in range(2):
+                    e.set_params(s, i, select=i, predelay=(0, 7, 255, 256, 8191)[s], wet=0.9, dry=0.25, panWet=0.1 * s, panDry=-0.1 * s)
+                    e.set_glide(s, i, 0.9)
+            return e.render(x)
+
+    y_new, y_old = go(0), go(m.FLAG_LEGACY_FFT)
+    assert (np.abs(y_new) > 0.999).sum() > 50          # clamp fires
+    for s in range(K):
+        for o in range(2):
+            assert O.rel_l2(y_new[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_new[s, o], y_old[s, o]))

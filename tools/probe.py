@@ -21,7 +21,7 @@ dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
 n = torch.arange(L, device=dev, dtype=torch.float32)
 env = torch.exp(-6.91 * n / (0.8 * L))
-flags = (0 if os.environ.get('CA_NOPROFILE') else ca.FLAG_PROFILE) | (ca.FLAG_STREAMING if K >= 16 else 0)
+flags = (0 if os.environ.get('CA_NOPROFILE') else ca.FLAG_PROFILE) | (ca.FLAG_STREAMING if K >= 16 else 0) | (ca.FLAG_LEGACY_FFT if os.environ.get('CA_LEGACY_FFT') else 0)
 t0 = time.time()
 e = ca.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=flags, mac_split=split, tiers=tiers, max_voices=nvoices,
               tier_growth=int(os.environ.get('CA_TIER_GROWTH', '0')), tier_max_block=int(os.environ.get('CA_TIER_MAXBLOCK', '0')))
