@@ -183,6 +183,139 @@ def parity_check(e, ca, torch, dev, K, x_dev, y_dev, stream, periods, rank):
             "against": "fp64 FFT convolution (oracle.engine_truth), wet = dry = 0.5", "tolerance": 1e-5}
 
 
+def cfg4_streams(ca, torch, dev, rank, world, max_over_ranks, barrier, streams=1024, ir_frames=96000):
+    """configs[3]: `streams` true-stereo streams with DISTINCT 2 s IRs (and the shared-IR variant), stream s on
+    GPU s mod N, no collective; device-timed ms per period for all streams, max over ranks."""
+    mine = len(range(rank, streams, world))
+    res = {"streams": streams, "streams_per_gpu": mine, "ir_frames": ir_frames, "n_gpus": world, "sharding": "stream s -> GPU s mod N, no collective", "scaling": "strong"}
+    n = torch.arange(ir_frames, device=dev, dtype=torch.float32)
+    env = torch.exp(-6.91 * n / (0.8 * ir_frames))
+    g = torch.Generator(device=dev)
+    for name, slots in (("distinct_irs", 2 * mine), ("shared_ir", 2)):
+        e = ca.Engine(period=B, max_ir_frames=ir_frames, n_instances=mine, n_ir_slots=slots, device=dev.index,
+                      flags=ca.FLAG_STREAMING if slots > 2 else 0, sample_rate=FS, tiers="auto")
+        for sl in range(slots):
+            g.manual_seed(5000 + (rank + world * (sl // 2)) * 2 + sl % 2 if slots > 2 else 5000 + sl)
+            h = torch.randn(2, ir_frames, device=dev, generator=g) * env
+            h = h / h.pow(2).sum(dim=1, keepdim=True).sqrt()
+            e.load_ir_device(sl, h[0].data_ptr(), h[1].data_ptr(), ir_frames)
+        for s_ in range(mine):
+            for i in range(2):
+                e.set_params(s_, i, select=(2 * s_ + i) if slots > 2 else i)
+                e.set_glide(s_, i, 0.5)
+        x = (torch.randn(mine, 2, B, device=dev, generator=g) * 0.1).clamp_(-0.9, 0.9)
+        y = torch.empty(mine, 2, B, device=dev)
+        st = e.stats()
+        cycle = max(int(st.tier_block[j]) for j in range(st.n_tiers)) // B
+        for _ in range(ir_frames // B + 2 * cycle):
+            e.process_device(x.data_ptr(), y.data_ptr())
+        e.sync()
+        stream = torch.cuda.ExternalStream(e.stream, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 4 * cycle
+        barrier()
+        ev0.record(stream)
+        for _ in range(steps):
+            e.process_device(x.data_ptr(), y.data_ptr())
+        ev1.record(stream)
+        e.sync()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        # through ca_process with pinned host buffers: p50 / p99 of the host wall time per period
+        pin, pout = ca.PinnedArray((mine, 2, B)), ca.PinnedArray((mine, 2, B))
+        pin.array[...] = x.cpu().numpy()
+        for _ in range(cycle):
+            e.process_raw(pin.ptr, pout.ptr)
+        e.reset_stats()
+        for _ in range(8 * cycle):
+            e.process_raw(pin.ptr, pout.ptr)
+        s2 = e.stats()
+        res[name] = {"ms_per_period_device": round(ms, 4), "frac_of_deadline": round(ms / DEADLINE_MS, 4),
+                     "e2e_p50_us": round(max_over_ranks(s2.p50_us), 1), "e2e_p99_us": round(max_over_ranks(s2.p99_us), 1),
+                     "meets_deadline": bool(max_over_ranks(s2.p99_us) < DEADLINE_MS * 1e3),
+                     "tiers": tier_desc(st)}
+        e.close()
+        pin.free()
+        pout.free()
+        torch.cuda.empty_cache()
+    return res
+
+
+def host_copy_ceiling(torch, dev, nbytes, max_over_ranks, barrier, world, steps=50):
+    """The e2e path's copies alone (pinned host <-> device, H2D and D2H of `nbytes` each per step on two
+    streams, every rank at once, no kernels): the ceiling the host side puts on e2e at N GPUs."""
+    h_in = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    d_out = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def step():
+        with torch.cuda.stream(s_in):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_out, non_blocking=True)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+        s_in.synchronize()
+        s_out.synchronize()
+    barrier()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    return {"bytes_each_way_per_gpu": nbytes, "ms_per_step": round(ms, 4), "aggregate_gbs": round(world * 2 * nbytes / (ms * 1e-3) / 1e9, 1),
+            "rt_channels_ceiling": round(world * (nbytes // (2 * B * 4)) * (B / FS) / (ms * 1e-3), 1),
+            "note": "H2D || D2H (full duplex) of the e2e step's buffers on every rank at once, no kernels"}
+
+
+def irsplit_group(ca, n_dev, seconds, periods):
+    """configs[4] through the C ABI group object (one process drives all GPUs): per-period host wall time of
+    ca_group_process, steady state (every delay-line slot in use)."""
+    import numpy as np
+    L = int(seconds * FS)
+    P = (L + B - 1) // B
+    rng = np.random.default_rng(1000)
+    env = np.exp(-6.91 * np.arange(L) / (0.8 * L)).astype(np.float32)
+    irs = []
+    for i in range(2):
+        h = rng.standard_normal((2, L)).astype(np.float32) * env
+        h /= np.sqrt((h ** 2).sum(axis=1, keepdims=True))
+        irs.append(h)
+    out = {"ir_seconds": seconds, "partitions": P, "n_gpus": n_dev, "deadline_us": round(DEADLINE_MS * 1e3, 1), "periods": periods}
+    for name, ex in (("p2p_fused", ca.EXCHANGE_P2P), ("nccl_reduce", ca.EXCHANGE_NCCL)):
+        if n_dev == 1 and name != "p2p_fused":
+            continue
+        try:
+            with ca.Group(list(range(n_dev)), period=B, max_ir_frames=L, exchange=ex, sample_rate=FS) as g:
+                for i in range(2):
+                    g.load_ir(i, irs[i][0], irs[i][1])
+                    g.set_params(i, select=i)
+                    g.set_glide(i, 0.5)
+                a, b = ca.PinnedArray((2, B)), ca.PinnedArray((2, B))
+                a.array[...] = (rng.standard_normal((2, B)) * 0.1).astype(np.float32)
+                for _ in range(P + 64):
+                    g.process_raw(a.ptr, b.ptr)
+                g.reset_stats()
+                for _ in range(periods):
+                    g.process_raw(a.ptr, b.ptr)
+                st = g.stats()
+                out[name] = {"p50_us": round(st.p50_us, 1), "p99_us": round(st.p99_us, 1), "max_us": round(st.max_us, 1),
+                             "partitions_per_gpu": [int(st.part_count[i]) for i in range(n_dev)], "mac_split_per_gpu": [int(st.mac_split[i]) for i in range(n_dev)],
+                             "mac_bytes_per_gpu": int(st.mac_bytes[0]), "nvlink_bytes_per_peer_per_period": int(st.exchange_bytes_per_peer),
+                             "peer_timeout": int(st.peer_timeout), "output_rms": round(float(np.sqrt((b.array.astype(np.float64) ** 2).mean())), 5)}
+                a.free()
+                b.free()
+        except ca.CaError as ex_:
+            out[name] = {"error": str(ex_)[:200]}
+    out["variant"] = "p2p_fused: last CTA of each peer's MAC stores its spectrum into the root over NVLink + flag, root inverse waits; nccl_reduce: ncclReduce(sum) of the spectra, then the inverse"
+    out["bound_by"] = "host launch of one graph per GPU + kernel dependency latency; the exchange itself is 4 KB per peer"
+    return out
+
+
 def tier_desc(st):
     return [{"block": int(st.tier_block[j]), "partitions": int(st.tier_parts[j]), "ir_offset": int(st.tier_offset[j])} for j in range(st.n_tiers)]
 
@@ -400,7 +533,8 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     # ---- latency of ONE instance through the public call (p50/p99) ----
-    if rank == 0 and world == 1 and not args.no_latency:
+    if not args.no_latency and (world == 1 or not args.no_multi_extras):
+        # at N > 1 every rank measures its own GPU at the same time (one instance per GPU): rank 0 reports all
         lat = {}
         # non_uniform: long tiers with two periods of slack on a low-priority stream (CA_FLAG_ASYNC_TIERS);
         # non_uniform_sync_tiers: the same partitioning with the tiers queued in front of the next period
@@ -432,7 +566,32 @@ def run_ours(args):
             a.free()
             b.free()
         lat["deadline_us"] = round(DEADLINE_MS * 1e3, 1)
+        if world > 1:
+            allr = [None] * world
+            dist.all_gather_object(allr, lat)
+            lat = dict(allr[0])
+            lat["per_gpu"] = [{k: {"p50_us": v["p50_us"], "p99_us": v["p99_us"], "paced_p99_us": v["paced"]["p99_us"]} for k, v in r.items() if isinstance(v, dict)} for r in allr]
         extras["latency_1_instance"] = lat
+
+    # ---- BASELINE configs[3]: 1024 independent stereo streams x 2 s IRs, stream-sharded over the GPUs (strong scaling) ----
+    if not args.no_cfg4:
+        c4 = cfg4_streams(ca, torch, dev, rank, world, max_over_ranks, barrier)
+        if rank == 0:
+            extras["cfg4_1024_streams_2s"] = c4
+
+    # ---- host copy ceiling of the e2e path: the same 2 x (instances x 2 KB) per step, no kernels ----
+    if not args.no_host_ceiling:
+        hc = host_copy_ceiling(torch, dev, K * 2 * B * 4, max_over_ranks, barrier, world)
+        if rank == 0:
+            extras["e2e_host_ceiling"] = hc
+
+    # ---- BASELINE configs[4]: one 60 s IR split by partition range over all N GPUs (ca_group, one process) ----
+    if not args.no_irsplit:
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            extras["irsplit_60s"] = irsplit_group(ca, world, args.irsplit_seconds, args.irsplit_periods)
+        barrier()
 
     # ---- CPU baseline (oracle port) on the host cores, rank 0, N = 1 only ----
     cpu = None
@@ -665,6 +824,11 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-host-ceiling", action="store_true")
+    ap.add_argument("--no-irsplit", action="store_true")
+    ap.add_argument("--no-multi-extras", action="store_true", help="N > 1: skip the per-GPU latency lines")
+    ap.add_argument("--irsplit-periods", type=int, default=2000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -136,6 +137,62 @@ uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l
 // period; tier j >= 1 has block S_j = m * period, covers IR frames [off, off + P*S) and runs after
 // the output of every m-th period has been produced (its result is first needed one period later
 // because off >= S).
+// Parameter hand-off: ca_set_params / ca_set_glide may be called from ANY thread (MIDI thread, UI, the
+// real-time thread itself) and never take a lock: commands go through a bounded multi-producer /
+// single-consumer ring (Vyukov's sequence-numbered slots) that the processing thread drains at the top of
+// the next period ("set_params lock-free from any thread").
+struct ParamCmd {
+    uint32_t item = 0, kind = 0;  // kind 0: parameter block, 1: glide jump
+    ca_params p{};
+    float glide = 0.f;
+};
+
+class ParamQueue {
+public:
+    ParamQueue() { resize(1u << 13); }
+    ~ParamQueue() { delete[] slots_; }
+    // before the engine is shared: room for a full set-up pass (parameters + glide of every item, twice)
+    void resize(uint64_t min_slots)
+    {
+        delete[] slots_;
+        kSlots = 1u << 13;
+        while (kSlots < min_slots) kSlots <<= 1;
+        slots_ = new Slot[kSlots];
+        for (uint64_t i = 0; i < kSlots; i++) slots_[i].seq.store(i, std::memory_order_relaxed);
+        enq_.store(0, std::memory_order_relaxed);
+        deq_ = 0;
+    }
+    bool push(const ParamCmd &c)
+    {
+        uint64_t pos = enq_.load(std::memory_order_relaxed);
+        for (;;) {
+            Slot &s = slots_[pos & (kSlots - 1)];
+            const int64_t dif = (int64_t)s.seq.load(std::memory_order_acquire) - (int64_t)pos;
+            if (dif == 0) {
+                if (enq_.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) { s.cmd = c; s.seq.store(pos + 1, std::memory_order_release); return true; }
+            } else if (dif < 0) return false;  // full
+            else pos = enq_.load(std::memory_order_relaxed);
+        }
+    }
+    bool pop(ParamCmd *c)  // single consumer
+    {
+        Slot &s = slots_[deq_ & (kSlots - 1)];
+        if (s.seq.load(std::memory_order_acquire) != deq_ + 1) return false;
+        *c = s.cmd;
+        s.seq.store(deq_ + kSlots, std::memory_order_release);
+        deq_++;
+        return true;
+    }
+    bool empty() const { return slots_[deq_ & (kSlots - 1)].seq.load(std::memory_order_acquire) != deq_ + 1; }
+
+private:
+    struct Slot { std::atomic<uint64_t> seq; ParamCmd cmd; };
+    uint64_t kSlots = 0;
+    Slot *slots_ = nullptr;
+    std::atomic<uint64_t> enq_{0};
+    uint64_t deq_ = 0;
+};
+
 constexpr uint32_t kIoChunks = 16;  // upper bound; the count used is io_chunks (default 2, env CA_IO_CHUNKS)
 
 struct Tier {
@@ -199,13 +256,28 @@ struct ca_engine {
     bool tracing = false;
     uint32_t io_chunks = 2;  // measured at 12 288 instances: 2 chunks 1.178 ms, 3: 1.206, 4: 1.237, 8: 1.316 (device-resident 1.124)
     int upload_idx = 0;
-    // parameters (host shadow)
-    std::mutex par_mutex;
+    // parameters: `par` (host shadow of the device blocks) belongs to the processing thread; setters reach it
+    // through the lock-free command ring; `user` (what ca_get_params returns) is seqlock-guarded per item
+    ParamQueue par_queue;
     std::vector<InParamDev> par;
     std::vector<ca_params> user;
-    std::atomic<bool> par_dirty{true};
+    std::unique_ptr<std::atomic<uint32_t>[]> user_seq;
+    bool par_dirty = true;  // processing thread only
     std::vector<uint8_t> ir_loaded;
     FftFns fft{};
+    // member of a ca_group (one IR split by partition range across GPUs, csrc/group.cuh)
+    struct Link {
+        float2 *gather = nullptr;             // MAC epilogue: this device's slot of the root's gather buffer
+        unsigned long long *gflag = nullptr;  // ... and its flag (root memory)
+        uint32_t *gcount = nullptr;           // local CTA counter of the MAC launch
+        bool skip_inverse = false;            // peers stop after the MAC (the root transforms the sum)
+        bool defer_inverse = false;           // NCCL variant, root: the inverse is launched after the reduce (launch_inverse_phase)
+        const float2 *inv_src = nullptr;      // root: inverse reads the gather buffer ...
+        uint32_t inv_split = 0;               // ... of this many spectra
+        const unsigned long long *wait_flags = nullptr;
+        uint32_t n_wait = 0;
+        int *gerr = nullptr;
+    } link;
     float2 *d_rowtw = nullptr;  // [W_256^n | W_512^k]: twiddles of the 256-point row FFT
     bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
     bool fused = false;       // tier 0 runs as one fused kernel (k_fused0)
@@ -254,18 +326,33 @@ void fill_dev_param(InParamDev &d, const ca_params &u)
     d.predelay = u.predelay; d.select = u.select;
 }
 
+// processing thread: drain the command ring into the host shadow; true when anything changed
+bool drain_params(ca_engine *e)
+{
+    ParamCmd c;
+    while (e->par_queue.pop(&c)) {
+        InParamDev &d = e->par[c.item];
+        if (c.kind == 0) {
+            fill_dev_param(d, c.p);
+            if (c.p.vsteps >= 0) { d.vsteps_cmd = (uint32_t)c.p.vsteps; d.vsteps_seq++; }
+        } else {
+            d.glide_cmd = c.glide;
+            d.glide_seq++;
+        }
+        e->par_dirty = true;
+    }
+    return e->par_dirty;
+}
+
 int flush_params(ca_engine *e)
 {
-    if (!e->par_dirty.load(std::memory_order_acquire)) return CA_OK;
-    std::unique_lock<std::mutex> lk(e->par_mutex, std::try_to_lock);
-    if (!lk.owns_lock()) return CA_OK;  // a setter is mid-update: pick it up next period (never block the RT thread)
+    if (!drain_params(e)) return CA_OK;
     const int b = e->upload_idx;
     e->upload_idx ^= 1;
-    CA_CUDA(cudaEventSynchronize(e->upload_done[b]));
+    CA_CUDA(cudaEventSynchronize(e->upload_done[b]));  // the upload two changes ago: long finished
     const size_t bytes = e->par.size() * sizeof(InParamDev);
     memcpy(e->h_upload[b], e->par.data(), bytes);
-    e->par_dirty.store(false, std::memory_order_release);
-    lk.unlock();
+    e->par_dirty = false;
     CA_CUDA(cudaMemcpyAsync(e->d_par, e->h_upload[b], bytes, cudaMemcpyHostToDevice, e->stream));
     CA_CUDA(cudaEventRecord(e->upload_done[b], e->stream));
     return CA_OK;
@@ -388,8 +475,10 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
                n_items, n_alloc, e->n_in, e->nv, t0.Lring, e->ring_len, e->ring_out, i0 * e->n_in, tp1};
     MacArgs ma = mac_args(e, t0, 1u);
     ma.inst0 = i0; ma.tend_host = tp1;
+    ma.gather = e->link.gather; ma.gflag = e->link.gflag; ma.gcount = e->link.gcount;
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
                t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, tp1};
+    if (e->link.inv_src) { ia.Ypart = e->link.inv_src; ia.n_split = e->link.inv_split; ia.wait_flags = e->link.wait_flags; ia.n_wait = e->link.n_wait; ia.gerr = e->link.gerr; }
     if (e->fused) {
         // tiered throughput schedule: forward + MAC + inverse of tier 0 in one CTA per instance
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
@@ -409,8 +498,23 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
     launch_mac(t0, ma, i1 - i0, e->stream, pdl);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    launch_inv0(e, pdl, ia, e->stream);
+    if (e->link.skip_inverse) { if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl); }  // group peer: only the period counter advances
+    else if (!e->link.defer_inverse) launch_inv0(e, pdl, ia, e->stream);
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
+    CA_CUDA(cudaGetLastError());
+    return CA_OK;
+}
+
+// ca_group, NCCL variant, root: the inverse transform of the period whose forward + MAC were launched by
+// launch_period (link.defer_inverse), after the reduce has delivered the summed spectrum into link.inv_src
+int launch_inverse_phase(ca_engine *e, const float *d_in, float *d_out)
+{
+    const Tier &t0 = e->tiers[0];
+    const unsigned long long tp1 = e->t_host + 1ull;
+    InvArgs ia{e->link.inv_src, d_in, d_out, nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
+               e->link.inv_split, e->n_in, e->n_out, e->acc_len, e->n_active * e->n_out, 0u, 1u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, tp1};
+    launch_inv0(e, false, ia, e->stream);
+    e->launches += 1;
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -516,7 +620,7 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
         // asynchronous tiers: this period (t_end = t_host + 1) needs the tiers that fired at t_end - 2 (their
         // results start in this period's output block, and their state buffer is the one fwd0 rewrites now);
         // the tiers of t_end - 1 keep running beside this period
-        if (e->par_dirty.load(std::memory_order_acquire)) CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[e->t_host & 1], 0));  // they read the parameters
+        if (drain_params(e)) CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[e->t_host & 1], 0));  // they read the parameters
         CA_CUDA(cudaStreamWaitEvent(e->stream, e->ev_def[(e->t_host + 1) & 1], 0));
     }
     rc = flush_params(e);
@@ -705,7 +809,7 @@ int drain_all(ca_engine *e)
 // one period of a batch; h_src / h_dst: pinned host buffers (ca_process) or nullptr (device-resident)
 int run_pipelined(ca_engine *e, const float *d_in, float *d_out, uint32_t chunks, const float *h_src, float *h_dst)
 {
-    if (e->par_dirty.load(std::memory_order_acquire)) {  // parameters change: lane M still reads the old ones
+    if (drain_params(e)) {  // parameters change: lane M still reads the old ones
         const int rc = pipe_drain(e);
         if (rc) return rc;
     }
@@ -1173,6 +1277,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     // parameter defaults == Convolution::CC::value defaults (conv.h:42-50)
     e->par.assign(n_items, InParamDev{});
     e->user.assign(n_items, ca_params{});
+    e->par_queue.resize(4 * n_items);
+    e->user_seq.reset(new std::atomic<uint32_t>[n_items]);
+    for (size_t i = 0; i < n_items; i++) e->user_seq[i].store(0, std::memory_order_relaxed);
     for (size_t i = 0; i < n_items; i++) {
         ca_params &u = e->user[i];
         u.select = 0; u.predelay = 0; u.speed = 100; u.vsteps = -1;
@@ -1303,33 +1410,35 @@ int ca_set_params(ca_engine *e, uint32_t instance, uint32_t input, const ca_para
     if (!e || !p || instance >= e->n_inst || input >= e->n_in) return CA_ERR_INVALID;
     if (p->select >= e->cfg.n_ir_slots || p->predelay >= CA_MAX_PREDELAY) return CA_ERR_INVALID;
     if (!e->ir_loaded[p->select]) return CA_ERR_STATE;  // the reference would dereference nullptr (conv.cu:340)
-    std::lock_guard<std::mutex> lk(e->par_mutex);
-    const size_t i = (size_t)instance * e->n_in + input;
-    e->user[i] = *p;
-    e->user[i].vsteps = -1;
-    InParamDev &d = e->par[i];
-    fill_dev_param(d, *p);
-    if (p->vsteps >= 0) { d.vsteps_cmd = (uint32_t)p->vsteps; d.vsteps_seq++; }
-    e->par_dirty.store(true, std::memory_order_release);
+    ParamCmd c;
+    c.item = instance * e->n_in + input; c.kind = 0; c.p = *p;
+    if (!e->par_queue.push(c)) { g_last_error = "parameter queue full (no ca_process call is draining it)"; return CA_ERR_STATE; }
+    std::atomic<uint32_t> &sq = e->user_seq[c.item];  // seqlock: odd while the block is being written
+    sq.fetch_add(1, std::memory_order_acq_rel);
+    e->user[c.item] = *p;
+    e->user[c.item].vsteps = -1;
+    sq.fetch_add(1, std::memory_order_release);
     return CA_OK;
 }
 
 int ca_get_params(ca_engine *e, uint32_t instance, uint32_t input, ca_params *p)
 {
     if (!e || !p || instance >= e->n_inst || input >= e->n_in) return CA_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->par_mutex);
-    *p = e->user[(size_t)instance * e->n_in + input];
-    return CA_OK;
+    const size_t i = (size_t)instance * e->n_in + input;
+    for (;;) {
+        const uint32_t a = e->user_seq[i].load(std::memory_order_acquire);
+        *p = e->user[i];
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (!(a & 1u) && e->user_seq[i].load(std::memory_order_relaxed) == a) return CA_OK;
+    }
 }
 
 int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g)
 {
     if (!e || instance >= e->n_inst || input >= e->n_in) return CA_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->par_mutex);
-    InParamDev &d = e->par[(size_t)instance * e->n_in + input];
-    d.glide_cmd = g;
-    d.glide_seq++;
-    e->par_dirty.store(true, std::memory_order_release);
+    ParamCmd c;
+    c.item = instance * e->n_in + input; c.kind = 1; c.glide = g;
+    if (!e->par_queue.push(c)) { g_last_error = "parameter queue full (no ca_process call is draining it)"; return CA_ERR_STATE; }
     return CA_OK;
 }
 
@@ -1551,3 +1660,5 @@ int ca_host_free(void *p)
 }
 
 }  // extern "C"
+
+#include "group.cuh"

@@ -392,7 +392,39 @@ struct MacArgs {
     // the period count itself (0: read ctl->t + t_bias)
     unsigned long long tend_host;
     uint32_t t_sel;  // see ctl_tend()
+    // One IR split by partition range across GPUs (ca_group): the last CTA of the launch to finish
+    // sums the launch's n_split partial spectra in fixed order and stores the ONE resulting spectrum
+    // (n_out x S complex, 4 KB at B = 256) into `gather` -- this device's slot of the root GPU's gather
+    // buffer, i.e. a peer store over NVLink when this GPU is not the root -- then publishes the period
+    // count in *gflag (system-scope release).  The root's inverse kernel waits on the flags: compute and
+    // exchange are one kernel, no collective launch.  nullptr: off.
+    float2 *gather;
+    unsigned long long *gflag;
+    uint32_t *gcount;
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// root side of the fused exchange: wait until every peer has published period count `epoch`.  Bounded
+// (~2 s at 2 GHz): a peer that died must not hang this GPU; *gerr reports it.
+__device__ __forceinline__ void group_wait(const unsigned long long *flags, uint32_t n_wait, unsigned long long epoch, int *gerr, int idx)
+{
+    if ((uint32_t)idx < n_wait) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + idx) < epoch) {
+            if (clock64() - t0 > (4ll << 30)) { if (gerr) *gerr = 1; break; }
+        }
+    }
+}
 
 constexpr int kMacConsumers = 256;
 constexpr int kMacThreads = kMacConsumers + 32;
@@ -593,6 +625,29 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
         if (q == 0 && tile == 0) { sum.x = s0.x; sum.y = s0.y; }
         float2 *dst = a.Ypart + (((size_t)(a.yp_local ? blockIdx.z : inst) * a.n_split + split) * NOUT + o) * a.S + tile * BT + 2 * q;
         *reinterpret_cast<float4 *>(dst) = sum;
+    }
+    if (a.gather) {  // ca_group: one instance; see MacArgs
+        __shared__ uint32_t s_last;
+        __threadfence();  // this CTA's partial is visible device-wide before it is counted
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(a.gcount, 1u) + 1u == gridDim.x * gridDim.y * gridDim.z) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const float4 *src = reinterpret_cast<const float4 *>(a.Ypart);  // [n_split][NOUT][S]
+            const uint32_t n4 = NOUT * a.S / 2;
+            for (uint32_t idx = tid; idx < n4; idx += kMacThreads) {
+                float4 sum = __ldcg(src + idx);
+                for (uint32_t sp = 1; sp < a.n_split; sp++) {
+                    const float4 v = __ldcg(src + (size_t)sp * n4 + idx);
+                    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                }
+                reinterpret_cast<float4 *>(a.gather)[idx] = sum;
+            }
+            __threadfence_system();  // the spectrum has landed (in the root's memory) before the flag does
+            __syncthreads();
+            if (tid == 0) { *a.gcount = 0u; st_release_sys(a.gflag, tend); }
+        }
     }
 }
 
@@ -879,6 +934,11 @@ struct InvArgs {
     uint32_t raw_wet;  // 1: store the unclamped wet block only (partition-range shards: clamp + dry after the reduce)
     unsigned long long t_host_p1;  // see FwdArgs
     const float2 *rowtw;           // see FwdArgs
+    // ca_group root: Ypart is the gather buffer [n_wait + 1][n_out][B]; slots 1.. are written by the peers'
+    // MAC kernels over NVLink: wait for their flags to reach this period's count first (see MacArgs)
+    const unsigned long long *wait_flags;
+    uint32_t n_wait;
+    int *gerr;
 };
 
 #ifndef CA_INV_THREADS
@@ -902,6 +962,10 @@ __global__ void __launch_bounds__(kInvThreads) k_inverse(const InvArgs a)
     const uint32_t item = a.item0 + local;
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t_next - 1ull;
+    if (a.n_wait) {
+        group_wait(a.wait_flags, a.n_wait, t + 1ull, a.gerr, PACKED ? (tid & 31) : tid);
+        if constexpr (PACKED) __syncwarp(); else __syncthreads();
+    }
 
     if constexpr (!PACKED) {
         // --- sum the partial spectra of the MAC splits (fixed order) ---

@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_inv0_rows(const InvArgs a)
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t_next - 1ull;
     float2 *row = sm + warp * kRowSlots;
+    if (a.n_wait) {  // ca_group root: the peers' spectra arrive over NVLink (see InvArgs)
+        group_wait(a.wait_flags, a.n_wait, t + 1ull, a.gerr, lane);
+        __syncwarp();
+    }
 
     // partial spectra of the MAC's row-range splits, fixed order
     {

@@ -26,7 +26,10 @@ EXPORTS = [
     "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
     "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs",
+    "ca_group_config_init", "ca_group_create", "ca_group_destroy", "ca_group_load_ir", "ca_group_set_params", "ca_group_set_glide",
+    "ca_group_process", "ca_group_get_stats", "ca_group_reset_stats",
 ]
+EXCHANGE_P2P, EXCHANGE_NCCL = 0, 1
 
 
 class CaError(RuntimeError):
@@ -63,6 +66,19 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class GroupConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_devices", C.c_uint32), ("devices", C.c_int32 * 8), ("period", C.c_uint32),
+                ("n_in", C.c_uint32), ("n_out", C.c_uint32), ("max_ir_frames", C.c_uint32), ("n_ir_slots", C.c_uint32),
+                ("flags", C.c_uint32), ("exchange", C.c_uint32), ("max_voices", C.c_uint32), ("sample_rate", C.c_float)]
+
+
+class GroupStats(C.Structure):
+    _fields_ = [("periods", C.c_uint64), ("mean_us", C.c_double), ("p50_us", C.c_double), ("p99_us", C.c_double), ("max_us", C.c_double),
+                ("n_devices", C.c_uint32), ("exchange", C.c_uint32), ("part_begin", C.c_uint32 * 8), ("part_count", C.c_uint32 * 8),
+                ("mac_split", C.c_uint32 * 8), ("mac_bytes", C.c_uint64 * 8), ("exchange_bytes_per_peer", C.c_uint64),
+                ("gpu_launches", C.c_uint64), ("peer_timeout", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -111,6 +127,15 @@ def lib():
         L.ca_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.ca_host_free.argtypes = [vp]
         L.ca_measure_read_gbs.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        L.ca_group_config_init.argtypes = [C.POINTER(GroupConfig)]
+        L.ca_group_create.argtypes = [C.POINTER(GroupConfig), C.POINTER(vp)]
+        L.ca_group_destroy.argtypes = [vp]
+        L.ca_group_load_ir.argtypes = [vp, C.c_uint32, f32p, f32p, C.c_uint32]
+        L.ca_group_set_params.argtypes = [vp, C.c_uint32, C.POINTER(Params)]
+        L.ca_group_set_glide.argtypes = [vp, C.c_uint32, C.c_float]
+        L.ca_group_process.argtypes = [vp, vp, vp, C.c_uint32]
+        L.ca_group_get_stats.argtypes = [vp, C.POINTER(GroupStats)]
+        L.ca_group_reset_stats.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -266,3 +291,80 @@ class Engine:
 
     def reset_stats(self):
         _check(lib().ca_reset_stats(self._h), "ca_reset_stats")
+
+
+class Group:
+    """One very long IR split by partition range across the GPUs of one node (ca_group, BASELINE configs[4])."""
+
+    def __init__(self, devices, period=256, max_ir_frames=2880000, n_in=2, n_out=2, n_ir_slots=2, flags=0, exchange=EXCHANGE_P2P,
+                 max_voices=0, sample_rate=48000.0):
+        cfg = GroupConfig()
+        lib().ca_group_config_init(C.byref(cfg))
+        devices = list(devices)
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        cfg.period, cfg.n_in, cfg.n_out, cfg.max_ir_frames, cfg.n_ir_slots = period, n_in, n_out, max_ir_frames, n_ir_slots
+        cfg.flags, cfg.exchange, cfg.max_voices, cfg.sample_rate = flags, exchange, max_voices, sample_rate
+        self.cfg = cfg
+        h = C.c_void_p()
+        _check(lib().ca_group_create(C.byref(cfg), C.byref(h)), "ca_group_create")
+        self._h = h
+        self.B, self.n_in, self.n_out = period, n_in, n_out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ca_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def load_ir(self, slot, left, right=None):
+        left = np.ascontiguousarray(left, np.float32)
+        right = left if right is None else np.ascontiguousarray(right, np.float32)
+        f32p = C.POINTER(C.c_float)
+        _check(lib().ca_group_load_ir(self._h, slot, left.ctypes.data_as(f32p), right.ctypes.data_as(f32p), len(left)), "ca_group_load_ir")
+
+    def set_params(self, inp, select=0, predelay=0, speed=100, vsteps=-1, dry=0.5, wet=0.5, panDry=0.0, panWet=0.0, level=1.0):
+        p = Params(select, predelay, speed, vsteps, dry, wet, panDry, panWet, level)
+        _check(lib().ca_group_set_params(self._h, inp, C.byref(p)), "ca_group_set_params")
+
+    def set_glide(self, inp, g):
+        _check(lib().ca_group_set_glide(self._h, inp, g), "ca_group_set_glide")
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        """x: [n_in][B] float32 -> [n_out][B]"""
+        x = np.ascontiguousarray(x, np.float32)
+        assert x.shape == (self.n_in, self.B), x.shape
+        out = np.empty((self.n_out, self.B), np.float32)
+        _check(lib().ca_group_process(self._h, x.ctypes.data, out.ctypes.data, self.B), "ca_group_process")
+        return out
+
+    def process_raw(self, in_ptr: int, out_ptr: int):
+        _check(lib().ca_group_process(self._h, in_ptr, out_ptr, self.B), "ca_group_process")
+
+    def render(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        n = (x.shape[-1] // self.B) * self.B
+        out = np.empty((self.n_out, n), np.float32)
+        for t in range(n // self.B):
+            out[:, t * self.B:(t + 1) * self.B] = self.process(x[:, t * self.B:(t + 1) * self.B])
+        return out
+
+    def stats(self) -> GroupStats:
+        s = GroupStats()
+        _check(lib().ca_group_get_stats(self._h, C.byref(s)), "ca_group_get_stats")
+        return s
+
+    def reset_stats(self):
+        _check(lib().ca_group_reset_stats(self._h), "ca_group_reset_stats")

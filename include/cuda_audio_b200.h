@@ -180,6 +180,56 @@ int ca_reset_stats(ca_engine *e);
  * L2-resident for small sizes, HBM for large ones; the roofline denominator of the single-instance MAC. */
 int ca_measure_read_gbs(int device, size_t bytes, int iters, double *gbs);
 
+/* ---- One very long IR split by partition range across the GPUs of one node (BASELINE configs[4]).
+ * The reference's only long-IR mechanism is a bigger fftSize on one GPU (conv.cu:239, conv.h:63); here GPU g
+ * convolves the same input with partitions [begin_g, begin_g + count_g) (delay-line offset by ring
+ * indexing) and the n_out x B partial spectra (4 KB at B = 256) are summed on the first device, which runs
+ * the one inverse transform, clamp and dry mix.  Exchange variants:
+ *   CA_EXCHANGE_P2P   fused: the last CTA of each peer's MAC kernel stores its summed spectrum into the root's
+ *                     memory over NVLink peer access and publishes a flag; the root's inverse kernel waits on
+ *                     the flags.  No collective launch; one CUDA graph per GPU per period.
+ *   CA_EXCHANGE_NCCL  ncclReduce(sum) of the spectra onto the root, then the inverse (libnccl resolved at run
+ *                     time with dlopen; CA_ERR_UNSUPPORTED when it is not installed).
+ * One process drives all GPUs; same call sequence and semantics as a 1-instance engine. */
+enum ca_exchange { CA_EXCHANGE_P2P = 0, CA_EXCHANGE_NCCL = 1 };
+
+typedef struct ca_group ca_group;
+
+typedef struct ca_group_config {
+    uint32_t struct_size;   /* sizeof(ca_group_config) */
+    uint32_t n_devices;     /* 1..8; devices[0] is the root (input fan-out, inverse, output) */
+    int32_t devices[8];
+    uint32_t period, n_in, n_out;
+    uint32_t max_ir_frames, n_ir_slots;
+    uint32_t flags;         /* ca_flags for the member engines (CA_FLAG_L2_PERSIST, ...); graphs are always used with P2P */
+    uint32_t exchange;      /* ca_exchange */
+    uint32_t max_voices;
+    float sample_rate;
+} ca_group_config;
+
+typedef struct ca_group_stats {
+    uint64_t periods;
+    double mean_us, p50_us, p99_us, max_us;   /* host wall time per ca_group_process call */
+    uint32_t n_devices, exchange;
+    uint32_t part_begin[8], part_count[8];    /* partition range per device */
+    uint32_t mac_split[8];
+    uint64_t mac_bytes[8];                    /* algorithmic bytes each device's MAC streams per period */
+    uint64_t exchange_bytes_per_peer;         /* bytes each peer sends to the root per period */
+    uint64_t gpu_launches;
+    int32_t peer_timeout;                     /* 1: the root gave up waiting for a peer's flag */
+} ca_group_stats;
+
+void ca_group_config_init(ca_group_config *cfg);
+int ca_group_create(const ca_group_config *cfg, ca_group **out);
+int ca_group_destroy(ca_group *g);
+int ca_group_load_ir(ca_group *g, uint32_t slot, const float *left, const float *right, uint32_t frames);
+int ca_group_set_params(ca_group *g, uint32_t input, const ca_params *p);
+int ca_group_set_glide(ca_group *g, uint32_t input, float glide);
+/* One period: in = planar [n_in][nframes], out = planar [n_out][nframes], host memory; synchronous. */
+int ca_group_process(ca_group *g, const float *in, float *out, uint32_t nframes);
+int ca_group_get_stats(ca_group *g, ca_group_stats *s);
+int ca_group_reset_stats(ca_group *g);
+
 /* Pinned host memory helpers for callers that want zero staging copies. */
 int ca_host_alloc(void **p, size_t bytes);
 int ca_host_free(void *p);
