@@ -18,6 +18,8 @@
 #include <cstddef>
 #include <cstdint>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,6 +37,33 @@
 #ifndef CONV_MAX_PREDELAY
 #define CONV_MAX_PREDELAY CA_MAX_PREDELAY
 #endif
+
+class Settings;
+class SharedEngine;
+
+// How a Convolution object maps onto the B200 engine (not in the reference: its engine IS conv.cu).
+// Settings-file keys (all optional, read by EngineOptions::fromSettings; ca_live / ca_render pass them on):
+//   engine.device <n>            CUDA device ordinal
+//   engine.tiers uniform|auto    uniform partitions (default) or non-uniform tiers (ca_config_auto_tiers)
+//   engine.tier_growth <n>, engine.tier_max_block <n>
+//   engine.async_tiers true      long tiers on a low-priority stream, two periods of slack (CA_FLAG_ASYNC_TIERS)
+//   engine.graph false           host-driven launches instead of one CUDA graph per period
+//   engine.l2_persist true       pin IR spectra + delay lines in L2 (CA_FLAG_L2_PERSIST)
+//   engine.period <frames>       build the engine at prepare()/onStart() time for this period (default: JACK's buffer size)
+//   engine.shared <N>            every N consecutive Convolution objects of the process are the N instances of
+//                                ONE batched engine (one set of kernel launches per JACK cycle for all of them)
+// The same options can come from the environment (CA_ENGINE_TIERS, CA_ENGINE_SHARED, CA_ENGINE_PERIOD,
+// CA_ENGINE_DEVICE, CA_ENGINE_ASYNC_TIERS) for drivers that construct Convolution objects themselves.
+struct EngineOptions {
+    int device = 0;
+    uint32_t flags = CA_FLAG_GRAPH;
+    bool autoTiers = false;
+    uint32_t tierGrowth = 0, tierMaxBlock = 0;
+    uint32_t period = 0;
+    uint32_t shared = 0;
+    static EngineOptions fromEnv();
+    static EngineOptions fromSettings(Settings &settings);
+};
 
 class Convolution : public JackClient, public RawMidi::MessageHandler {
 public:
@@ -70,29 +99,42 @@ public:
     // --- additions (not in the reference) ---
     int lastError() const { return _lastError; }          // ca_error of the last failing call, 0 = none
     const std::string &lastErrorText() const { return _lastErrorText; }
-    ca_engine *engine() const { return _engine; }          // null until the first onProcess()
-    void setDevice(int device) { _device = device; }       // before the first onProcess()
-    void setFlags(uint32_t flags) { _flags = flags; }      // ca_flags, before the first onProcess()
+    ca_engine *engine() const { return _engine; }          // null until the engine is built (buildNow / onStart / first onProcess)
+    void setDevice(int device) { _opt.device = device; }   // before the engine is built
+    void setFlags(uint32_t flags) { _opt.flags = flags; }  // ca_flags, before the engine is built
     void setSampleRate(float fs) { _sampleRate = fs; }
+    void setOptions(const EngineOptions &o);               // before the engine is built
+    const EngineOptions &options() const { return _opt; }
+    static void setDefaultOptions(const EngineOptions &o); // options of Convolution objects constructed from now on
+    // Build the engine NOW, outside the real-time thread (allocation, graph capture, IR transforms, one silent
+    // warm-up period).  onStart() calls it with JACK's buffer size; harnesses that know the period call it after
+    // the last prepare().  Without it the first onProcess() builds the engine (not real-time safe).
+    bool buildNow(size_t period);
     size_t numIRs() const { return _irs.size(); }
+    uint64_t skippedPeriods() const { return _skipped; }   // periods answered with silence because prepare() held the engine
 
 private:
+    friend class SharedEngine;
     struct HostIR { std::vector<float> left, right; };
     bool buildEngine(size_t period);
     void pushParams(bool force);
+    void pushParamsTo(ca_engine *e, uint32_t instance, size_t slotBase, bool force);
     void fail(int code, const char *what);
 
     size_t _fftSize;
     std::map<size_t, HostIR> _irs;  // time-domain IRs kept on the host so the engine can be (re)built
     size_t _minPrepareFrames = 1024;
     ca_engine *_engine = nullptr;
+    std::mutex _engineMutex;  // prepare() on a live engine vs onProcess(): the RT thread only try_locks (silence on contention)
     size_t _period = 0, _engineSlots = 0, _engineCapFrames = 0;
-    int _device = 0;
-    uint32_t _flags = CA_FLAG_GRAPH;
+    EngineOptions _opt;
+    std::shared_ptr<SharedEngine> _shared;  // engine.shared: this object is instance _sharedIdx of a batched engine
+    int _sharedIdx = -1;
     float _sampleRate = 48000.f;
     CC::Value _pushed[2];
     bool _havePushed = false;
-    std::vector<float> _in, _out;  // planar staging [2][period]
+    float *_in = nullptr, *_out = nullptr;  // pinned planar staging [2][period] (ca_host_alloc): no copy inside ca_process
+    uint64_t _skipped = 0;
     double _runtimeMs = 0;
     int _nruns = -10;  // conv.h:80: discard the first couple of runs
     int _lastError = 0;
