@@ -593,6 +593,10 @@ def run_ours(args):
             extras["irsplit_60s"] = irsplit_group(ca, world, args.irsplit_seconds, args.irsplit_periods)
         barrier()
 
+    # ---- the reference's class API on this engine (N = 1 only: one process per K) ----
+    if rank == 0 and world == 1 and not args.no_class_api and os.path.exists(os.path.join(ROOT, "tests", "dropin", "libdropin_conv.so")):
+        extras["dropin_class_api"] = class_api_extra()
+
     # ---- CPU baseline (oracle port) on the host cores, rank 0, N = 1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -798,13 +802,70 @@ def run_reference(args):
     print(json.dumps(base), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# the reference's CLASS API on this engine: K mirror `Convolution` objects on K host threads through the
+# same harness code the reference arm runs (oracle/ref_harness/harness.cu::ref_bench, built against the
+# host mirror as tests/dropin/libdropin_conv.so), sharing ONE batched engine (engine.shared)
+# ------------------------------------------------------------------------------------------------
+def run_class_api(args):
+    import numpy as np
+
+    from oracle import refgpu
+
+    K = args.class_k
+    lib = os.path.join(ROOT, "tests", "dropin", "libdropin_conv.so")
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)                      # the mirror logs IR loads like the reference does
+    rng = np.random.default_rng(0)
+    env = np.exp(-6.91 * np.arange(IR_FRAMES) / (0.8 * IR_FRAMES)).astype(np.float32)
+    insts = []
+    for _ in range(K):
+        r = refgpu.RefGpu(262144, 0, lib)
+        for i in range(2):
+            h = rng.standard_normal((2, IR_FRAMES)).astype(np.float32) * env
+            h /= np.sqrt((h ** 2).sum(axis=1, keepdims=True))
+            r.prepare(i, h[0], h[1], B)
+            r.set_cc(i, select=i)
+        insts.append(r)
+    wall = refgpu.bench(insts, B, STEADY + 200, args.class_periods)
+    os.dup2(saved, 1)
+    os.close(devnull)
+    mean_ms = float(wall.mean()) * 1e-3
+    print(json.dumps({"objects": K, "host_threads": K, "p50_us": round(float(np.percentile(wall, 50)), 1), "p99_us": round(float(np.percentile(wall, 99)), 1),
+                      "ms_per_period": round(mean_ms, 4), "rt_channels": round(K * (B / FS) / (mean_ms * 1e-3), 1),
+                      "meets_deadline_p99": bool(np.percentile(wall, 99) < DEADLINE_MS * 1e3)}), flush=True)
+
+
+def class_api_extra(ks=(8, 32, 128), periods=1000):
+    """Spawn one process per K (the engine options are process-wide defaults read at the first construction)."""
+    res = {"how": "K mirror Convolution objects (conv.h surface) on K host threads, lock-stepped per period by the reference harness's ref_bench; "
+                  "engine.shared = K: one batched, tiered engine behind all of them", "sweep": {}}
+    for k in ks:
+        env = dict(os.environ, CA_ENGINE_SHARED=str(k), CA_ENGINE_TIERS="auto", CA_ENGINE_PERIOD=str(B))
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", "class-api", "--class-k", str(k), "--class-periods", str(periods)],
+                                 env=env, capture_output=True, text=True, timeout=600)
+            res["sweep"][str(k)] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": out.stderr[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            res["sweep"][str(k)] = {"error": str(ex)[:300]}
+    ok = [v for v in res["sweep"].values() if "rt_channels" in v]
+    if ok:
+        res["best_rt_channels"] = max(v["rt_channels"] for v in ok)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="channels", choices=["channels", "irsplit"],
+    ap.add_argument("--class-k", type=int, default=8)
+    ap.add_argument("--class-periods", type=int, default=1000)
+    ap.add_argument("--no-class-api", action="store_true")
+    ap.add_argument("--mode", default="channels", choices=["channels", "irsplit", "class-api"],
                     help="channels: the headline (independent instances, no collective); irsplit: configs[4], one long IR split across the GPUs")
     ap.add_argument("--irsplit-seconds", type=float, default=60.0)
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU in the throughput run (0 = as many as the GPU's HBM holds)")
@@ -832,6 +893,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "class-api":
+        run_class_api(args)
     elif args.mode == "irsplit":
         run_irsplit(args)
     else:

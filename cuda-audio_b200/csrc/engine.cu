@@ -183,7 +183,6 @@ public:
         deq_++;
         return true;
     }
-    bool empty() const { return slots_[deq_ & (kSlots - 1)].seq.load(std::memory_order_acquire) != deq_ + 1; }
 
 private:
     struct Slot { std::atomic<uint64_t> seq; ParamCmd cmd; };

@@ -2,15 +2,75 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_runtime.h>
 
-Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize) {}
+#include "settings_file.h"
+#include "shared_engine.h"
+
+// ---- engine options -------------------------------------------------------------------------
+static bool truthy(const char *v) { return v && (v[0] == '1' || v[0] == 't' || v[0] == 'T' || v[0] == 'y' || v[0] == 'Y'); }
+
+EngineOptions EngineOptions::fromEnv()
+{
+    EngineOptions o;
+    if (const char *v = getenv("CA_ENGINE_DEVICE")) o.device = atoi(v);
+    if (const char *v = getenv("CA_ENGINE_TIERS")) o.autoTiers = std::string(v) == "auto";
+    if (const char *v = getenv("CA_ENGINE_PERIOD")) o.period = (uint32_t)atoi(v);
+    if (const char *v = getenv("CA_ENGINE_SHARED")) o.shared = (uint32_t)atoi(v);
+    if (truthy(getenv("CA_ENGINE_ASYNC_TIERS"))) o.flags |= CA_FLAG_ASYNC_TIERS;
+    if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;  // batches: host-driven launches + PDL
+    return o;
+}
+
+EngineOptions EngineOptions::fromSettings(Settings &st)
+{
+    EngineOptions o = fromEnv();
+    if (st.has("engine.device")) o.device = (int)st.u32("engine.device");
+    if (st.has("engine.tiers")) o.autoTiers = st.str("engine.tiers") == "auto";
+    if (st.has("engine.tier_growth")) o.tierGrowth = st.u32("engine.tier_growth");
+    if (st.has("engine.tier_max_block")) o.tierMaxBlock = st.u32("engine.tier_max_block");
+    if (st.has("engine.period")) o.period = st.u32("engine.period");
+    if (st.has("engine.shared")) o.shared = st.u32("engine.shared");
+    auto flag = [&](const char *key, uint32_t bit, bool dflt) {
+        const bool on = st.has(key) ? truthy(st.str(key).c_str()) : dflt;
+        o.flags = on ? (o.flags | bit) : (o.flags & ~bit);
+    };
+    flag("engine.graph", CA_FLAG_GRAPH, (o.flags & CA_FLAG_GRAPH) != 0);
+    flag("engine.async_tiers", CA_FLAG_ASYNC_TIERS, (o.flags & CA_FLAG_ASYNC_TIERS) != 0);
+    flag("engine.l2_persist", CA_FLAG_L2_PERSIST, (o.flags & CA_FLAG_L2_PERSIST) != 0);
+    if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;
+    return o;
+}
+
+static EngineOptions &defaultOptions()
+{
+    static EngineOptions o = EngineOptions::fromEnv();
+    return o;
+}
+
+void Convolution::setDefaultOptions(const EngineOptions &o) { defaultOptions() = o; }
+
+void Convolution::setOptions(const EngineOptions &o)
+{
+    if (_engine || _shared) { fail(CA_ERR_STATE, "setOptions: the engine is already built"); return; }
+    _opt = o;
+    if (_opt.shared > 1) _shared = SharedEngine::join(this, _opt, &_sharedIdx);
+}
+
+Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize), _opt(defaultOptions())
+{
+    if (_opt.shared > 1) _shared = SharedEngine::join(this, _opt, &_sharedIdx);
+}
 
 Convolution::~Convolution()
 {
+    if (_shared) _shared->leave(this);
     if (_engine) ca_destroy(_engine);
+    if (_in) ca_host_free(_in);
+    if (_out) ca_host_free(_out);
 }
 
 void Convolution::fail(int code, const char *what)
@@ -20,14 +80,32 @@ void Convolution::fail(int code, const char *what)
     Log::error(name, "%s", _lastErrorText.c_str());
 }
 
-// conv.cu:197-204
+// conv.cu:197-204.  The engine is built HERE (allocation, graph capture, IR transforms, warm-up), before the
+// client is activated, so the first real-time callback finds it ready.
 void Convolution::onStart()
 {
+    const size_t period = _opt.period ? _opt.period : (handle ? (size_t)jack_get_buffer_size(handle) : 0);
+    if (period && !_irs.empty() && !_shared) buildNow(period);
     activate();
     playback[0] = addOutput("playback_1");
     playback[1] = addOutput("playback_2");
     capture[0] = addInput("capture_1");
     capture[1] = addInput("capture_2");
+}
+
+bool Convolution::buildNow(size_t period)
+{
+    if (_shared) return _shared->buildNow(period, samplerate ? (float)samplerate : _sampleRate);
+    std::lock_guard<std::mutex> lk(_engineMutex);
+    if (_engine && _period == period) return true;
+    if (_engine) { ca_destroy(_engine); _engine = nullptr; }
+    if (!buildEngine(period)) return false;
+    pushParams(true);
+    // one silent period: first-launch costs (module load, graph upload) are paid here, not in the callback
+    memset(_in, 0, 2 * period * sizeof(float));
+    const int rc = ca_process(_engine, _in, _out, (uint32_t)period);
+    if (rc) { fail(rc, "ca_process (warm-up)"); return false; }
+    return true;
 }
 
 // conv.cu:207-253: the stereo IR `wav` (device float2 frames, half scale) becomes bank entry idx,
@@ -39,7 +117,7 @@ void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
     const size_t n = std::min(wav.numFrames, cap);
     if (!n) { fail(CA_ERR_INVALID, "prepare: fftSize too small"); return; }
     std::vector<float2> host(n);
-    cudaSetDevice(_device);
+    cudaSetDevice(_opt.device);
     if (cudaMemcpy(host.data(), wav.buffer, n * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) {
         (void)cudaGetLastError();
         fail(CA_ERR_CUDA, "prepare: cannot read the wav buffer");
@@ -50,11 +128,20 @@ void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
     ir.right.resize(n);
     for (size_t i = 0; i < n; i++) { ir.left[i] = host[i].x; ir.right[i] = host[i].y; }
     _minPrepareFrames = std::min(_minPrepareFrames, nframes);
+    if (_shared) { _shared->irChanged(this); return; }
+    // A running engine: the load (or the rebuild) happens here, on the caller's thread, under the engine lock;
+    // the real-time thread only try_locks and answers the periods it loses with silence (skippedPeriods()).
+    // The reference's prepare() is not thread safe at all (conv.cu:206 "TODO make thread safe").
+    std::lock_guard<std::mutex> lk(_engineMutex);
     if (_engine) {
-        // running engine: load in place when the slot and the length fit, else rebuild lazily
         if (idx < _engineSlots && n <= _engineCapFrames && ca_load_ir(_engine, (uint32_t)idx, ir.left.data(), ir.right.data(), (uint32_t)n) == CA_OK) return;
+        const size_t period = _period;
         ca_destroy(_engine);
         _engine = nullptr;
+        if (buildEngine(period)) pushParams(true);
+    } else if (_opt.period) {
+        // period known up front (engine.period): build as soon as there is an IR, rebuild above when the bank grows
+        if (buildEngine(_opt.period)) pushParams(true);
     }
 }
 
@@ -63,7 +150,7 @@ bool Convolution::buildEngine(size_t period)
     if (_irs.empty()) { fail(CA_ERR_STATE, "onProcess: no IR prepared"); return false; }
     ca_config cfg;
     ca_config_init(&cfg);
-    cfg.device = _device;
+    cfg.device = _opt.device;
     cfg.period = (uint32_t)period;
     cfg.n_instances = 1;
     cfg.n_in = cfg.n_out = 2;
@@ -71,9 +158,10 @@ bool Convolution::buildEngine(size_t period)
     for (auto &kv : _irs) longest = std::max(longest, kv.second.left.size());
     cfg.max_ir_frames = (uint32_t)longest;
     cfg.n_ir_slots = (uint32_t)(_irs.rbegin()->first + 1);
-    cfg.flags = _flags;
+    cfg.flags = _opt.flags;
     cfg.max_voices = 3;  // old IR + new IR + one more switch in flight during a cross-fade
     cfg.sample_rate = samplerate ? (float)samplerate : _sampleRate;
+    if (_opt.autoTiers && ca_config_auto_tiers(&cfg, _opt.tierGrowth, _opt.tierMaxBlock) != CA_OK) { fail(CA_ERR_INVALID, "ca_config_auto_tiers"); return false; }
     int rc = ca_create(&cfg, &_engine);
     if (rc) { _engine = nullptr; fail(rc, "ca_create"); return false; }
     for (auto &kv : _irs) {
@@ -83,15 +171,22 @@ bool Convolution::buildEngine(size_t period)
     _period = period;
     _engineSlots = cfg.n_ir_slots;
     _engineCapFrames = cfg.max_ir_frames;
-    _in.assign(2 * period, 0.f);
-    _out.assign(2 * period, 0.f);
+    if (_in) ca_host_free(_in);
+    if (_out) ca_host_free(_out);
+    _in = _out = nullptr;
+    if (ca_host_alloc((void **)&_in, 2 * period * sizeof(float)) || ca_host_alloc((void **)&_out, 2 * period * sizeof(float))) { fail(CA_ERR_NOMEM, "ca_host_alloc"); ca_destroy(_engine); _engine = nullptr; return false; }
+    memset(_in, 0, 2 * period * sizeof(float));
+    memset(_out, 0, 2 * period * sizeof(float));
     _havePushed = false;
     return true;
 }
 
 // cc[i].value is plain shared state like in the reference (conv.cu:339-427 reads it every period):
 // whatever changed since the last period is forwarded to the engine.
-void Convolution::pushParams(bool force)
+void Convolution::pushParams(bool force) { pushParamsTo(_engine, 0, 0, force); }
+
+// instance / slotBase: position of this object inside a shared batched engine (0, 0 for its own engine)
+void Convolution::pushParamsTo(ca_engine *e, uint32_t instance, size_t slotBase, bool force)
 {
     for (int i = 0; i < 2; i++) {
         CC::Value &v = cc[i].value;
@@ -107,12 +202,12 @@ void Convolution::pushParams(bool force)
                 v.select = _havePushed ? p.select : _irs.begin()->first;
             }
             ca_params q;
-            q.select = (uint32_t)v.select;
+            q.select = (uint32_t)(slotBase + v.select);
             q.predelay = (uint32_t)std::min<size_t>(v.predelay, CA_MAX_PREDELAY - 1);
             q.speed = (uint32_t)v.speed;
             q.vsteps = (vstepsChanged || !_havePushed) ? (int32_t)v.vsteps : -1;
             q.dry = v.dry; q.wet = v.wet; q.panDry = v.panDry; q.panWet = v.panWet; q.level = v.level;
-            const int rc = ca_set_params(_engine, 0, (uint32_t)i, &q);
+            const int rc = ca_set_params(e, instance, (uint32_t)i, &q);
             if (rc) fail(rc, "ca_set_params");
             p = v;
         }
@@ -133,17 +228,25 @@ void Convolution::onProcess(size_t nframes)
     if (!IN1 || !IN2 || !L || !R) return;  // conv.cu:297
 
     const auto t0 = std::chrono::steady_clock::now();
-    if (!_engine || _period != nframes) {
-        if (_engine) { ca_destroy(_engine); _engine = nullptr; }
-        if (!buildEngine(nframes)) { memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); return; }
+    auto silence = [&] { memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); };
+    if (_shared) {
+        if (!_shared->process(this, _sharedIdx, IN1, IN2, L, R, nframes)) { silence(); _skipped++; }
+    } else {
+        std::unique_lock<std::mutex> lk(_engineMutex, std::try_to_lock);
+        if (!lk.owns_lock()) { silence(); _skipped++; return; }  // prepare() is loading an IR: never block the RT thread
+        if (!_engine || _period != nframes) {
+            // no buildNow() / onStart() with a known buffer size came first (plain harness): build here
+            if (_engine) { ca_destroy(_engine); _engine = nullptr; }
+            if (!buildEngine(nframes)) { silence(); return; }
+        }
+        pushParams(false);
+        memcpy(_in, IN1, nframes * sizeof(float));
+        memcpy(_in + nframes, IN2, nframes * sizeof(float));
+        const int rc = ca_process(_engine, _in, _out, (uint32_t)nframes);  // pinned staging: used in place
+        if (rc) { fail(rc, "ca_process"); silence(); return; }
+        memcpy(L, _out, nframes * sizeof(float));
+        memcpy(R, _out + nframes, nframes * sizeof(float));
     }
-    pushParams(false);
-    memcpy(_in.data(), IN1, nframes * sizeof(float));
-    memcpy(_in.data() + nframes, IN2, nframes * sizeof(float));
-    const int rc = ca_process(_engine, _in.data(), _out.data(), (uint32_t)nframes);
-    if (rc) { fail(rc, "ca_process"); memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); return; }
-    memcpy(L, _out.data(), nframes * sizeof(float));
-    memcpy(R, _out.data() + nframes, nframes * sizeof(float));
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (++_nruns > 0) _runtimeMs += ms;  // conv.cu:462
 }

@@ -24,10 +24,12 @@ struct _jack_client {
 };
 
 static unsigned g_rate = 48000;
+static unsigned g_buffer = 0;  // 0: unknown until the first cycle
 
 extern "C" {
 
 void hj_set_sample_rate(unsigned rate) { g_rate = rate; }
+void hj_set_buffer_size(unsigned frames) { g_buffer = frames; }
 
 int hj_cycle(jack_client_t *c, jack_nframes_t nframes)
 {
@@ -75,6 +77,7 @@ jack_client_t *jack_client_open(const char *client_name, jack_options_t, jack_st
 int jack_set_process_callback(jack_client_t *c, JackProcessCallback cb, void *arg) { c->process = cb; c->processArg = arg; return 0; }
 void jack_on_shutdown(jack_client_t *c, JackShutdownCallback cb, void *arg) { c->shutdown = cb; c->shutdownArg = arg; }
 jack_nframes_t jack_get_sample_rate(jack_client_t *) { return g_rate; }
+jack_nframes_t jack_get_buffer_size(jack_client_t *) { return g_buffer; }
 
 int jack_client_close(jack_client_t *c)
 {

@@ -9,6 +9,7 @@
 extern "C" {
 #endif
 void hj_set_sample_rate(unsigned rate);
+void hj_set_buffer_size(unsigned frames);  /* what jack_get_buffer_size() reports (0 = unknown) */
 /* run one period: invokes the client's process callback with nframes */
 int hj_cycle(jack_client_t *client, jack_nframes_t nframes);
 /* point a port at caller-owned memory for the next cycles (NULL = internal buffer) */

@@ -66,6 +66,12 @@ jack_nframes_t jack_get_sample_rate(jack_client_t *c)
     static auto f = sym<jack_nframes_t (*)(jack_client_t *)>("jack_get_sample_rate");
     return f ? f(c) : 0;
 }
+
+jack_nframes_t jack_get_buffer_size(jack_client_t *c)
+{
+    static auto f = sym<jack_nframes_t (*)(jack_client_t *)>("jack_get_buffer_size");
+    return f ? f(c) : 0;
+}
 int jack_client_close(jack_client_t *c)
 {
     static auto f = sym<int (*)(jack_client_t *)>("jack_client_close");

@@ -25,6 +25,7 @@ int main(int argc, char **argv)
     uint32_t count = 0;
     try { count = settings.u32("conv.count"); } catch (std::exception &) { fprintf(stderr, "ca_live: conv.count missing\n"); return 1; }
     if (count % 2) { fprintf(stderr, "ca_live: conv.count must be a multiple of 2\n"); return 1; }
+    Convolution::setDefaultOptions(EngineOptions::fromSettings(settings));  // engine.* keys (convolution.h)
     // `resample <Hz>`: convert IRs recorded at another rate (the shipped library is 44.1 kHz) to the JACK
     // server's rate on load; absent / 0 keeps the reference's behaviour (IR played at the server's rate)
     const uint32_t irRate = settings.has("resample") ? settings.u32("resample") : 0;

@@ -23,6 +23,7 @@
 #include <memory>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "convolution.h"
@@ -165,6 +166,7 @@ int main(int argc, char **argv)
     }
     const unsigned rate = o.rate ? o.rate : input.sampleRate;
     hj_set_sample_rate(rate);
+    hj_set_buffer_size((unsigned)o.period);  // JackClient::start() -> Convolution::onStart() builds the engine for it
 
     // ---- instances (main.cu:25-93) ----
     Settings settings;
@@ -174,6 +176,7 @@ int main(int argc, char **argv)
         const uint32_t count = settings.u32("conv.count");
         if (count % 2) { fprintf(stderr, "ca_render: conv.count must be a multiple of 2\n"); return 1; }
         numInstances = count / 2;
+        Convolution::setDefaultOptions(EngineOptions::fromSettings(settings));  // engine.* keys
     }
     // optional IR sample-rate conversion: --resample (to the run's rate) or `resample <Hz>` in the settings file
     unsigned irRate = o.resample ? rate : 0;
@@ -269,7 +272,7 @@ int main(int argc, char **argv)
     const size_t periods = (input.frames + B - 1) / B;
     const size_t outChannels = o.mono ? 1 : 2 * numInstances;
     std::vector<std::vector<float>> out(outChannels, std::vector<float>(periods * B, 0.f));
-    std::vector<float> silence(B, 0.f), scratch(B, 0.f);
+    std::vector<float> silence(B, 0.f), scratch(B, 0.f), scratch2(B, 0.f);
     std::vector<std::vector<float>> inPadded(input.channels);
     for (int c = 0; c < input.channels; c++) { inPadded[c] = input.ch[c]; inPadded[c].resize(periods * B, 0.f); }
     auto channelOf = [](const char *peer, const char *prefix) -> int {
@@ -279,11 +282,20 @@ int main(int argc, char **argv)
     };
     std::vector<double> wall;
     wall.reserve(periods);
-    for (int w = 0; w < o.warmup; w++)  // silent warm-up periods (lets the wet glide converge)
-        for (auto &c : inst) {
-            for (int i = 0; i < 2; i++) { hj_port_set_buffer(c->capture[i], silence.data()); hj_port_set_buffer(c->playback[i], scratch.data()); }
-            hj_cycle(c->handle, (jack_nframes_t)B);
-        }
+    // one JACK cycle for every client.  With `engine.shared` the clients are instances of one batched engine
+    // and meet at a rendezvous inside onProcess(): their callbacks must run on separate threads, as JACK's do.
+    const bool threaded = inst.size() > 1 && inst[0]->options().shared > 1;
+    auto cycle_all = [&] {
+        if (!threaded) { for (auto &c : inst) hj_cycle(c->handle, (jack_nframes_t)B); return; }
+        std::vector<std::thread> th;
+        for (auto &c : inst) th.emplace_back([&c, B] { hj_cycle(c->handle, (jack_nframes_t)B); });
+        for (auto &t : th) t.join();
+    };
+    for (int w = 0; w < o.warmup; w++) {  // silent warm-up periods (lets the wet glide converge)
+        for (auto &c : inst)
+            for (int i = 0; i < 2; i++) { hj_port_set_buffer(c->capture[i], silence.data()); hj_port_set_buffer(c->playback[i], i == 0 ? scratch.data() : scratch2.data()); }
+        cycle_all();
+    }
     for (size_t t = 0; t < periods; t++) {
         const auto t0 = std::chrono::steady_clock::now();
         for (auto &c : inst) {
@@ -296,8 +308,8 @@ int main(int argc, char **argv)
                 if (o.mono) oc = (i == 0) ? 0 : -1;
                 hj_port_set_buffer(c->playback[i], (oc >= 0 && oc < (int)outChannels) ? out[oc].data() + t * B : scratch.data());
             }
-            hj_cycle(c->handle, (jack_nframes_t)B);
         }
+        cycle_all();
         wall.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
     }
     int rc = 0;

@@ -36,6 +36,7 @@ jack_client_t *jack_client_open(const char *, jack_options_t, jack_status_t *sta
 int jack_set_process_callback(jack_client_t *, JackProcessCallback, void *) { return 0; }
 void jack_on_shutdown(jack_client_t *, JackShutdownCallback, void *) {}
 jack_nframes_t jack_get_sample_rate(jack_client_t *) { return 48000; }
+jack_nframes_t jack_get_buffer_size(jack_client_t *) { return 0; }  /* unknown: the harness never calls start() */
 int jack_client_close(jack_client_t *c) { delete c; return 0; }
 int jack_connect(jack_client_t *, const char *, const char *) { return 0; }
 const char *jack_port_name(const jack_port_t *) { return "fake"; }

@@ -26,6 +26,7 @@ jack_client_t *jack_client_open(const char *client_name, jack_options_t options,
 int jack_set_process_callback(jack_client_t *client, JackProcessCallback cb, void *arg);
 void jack_on_shutdown(jack_client_t *client, JackShutdownCallback cb, void *arg);
 jack_nframes_t jack_get_sample_rate(jack_client_t *client);
+jack_nframes_t jack_get_buffer_size(jack_client_t *client);
 int jack_client_close(jack_client_t *client);
 int jack_connect(jack_client_t *client, const char *source_port, const char *destination_port);
 const char *jack_port_name(const jack_port_t *port);

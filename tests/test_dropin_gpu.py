@@ -171,3 +171,47 @@ def test_settings_driven_render_two_instances(tmp_path):
         truth = O.engine_truth(x[2 * n:2 * n + 2], [stereo[pr[0]["select"]], stereo[pr[1]["select"]]], pr)
         for o in range(2):
             assert O.rel_l2(y[2 * n + o], truth[o]) < 5e-6, (n, o)
+
+
+@needs_libs
+def test_shared_batched_engine_through_the_class_api():
+    """`engine.shared` / CA_ENGINE_SHARED: three mirror Convolution objects on three host threads are the three
+    instances of ONE batched, tiered engine (one set of launches per cycle); same driver code as the
+    reference arm (harness.cu), results against fp64."""
+    import sys
+    env = dict(os.environ, CA_ENGINE_SHARED="3", CA_ENGINE_TIERS="auto")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_shared_worker.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("SHARED_RESULT ")][-1].split(" ", 1)[1])
+    assert res["K"] == 3 and max(res["rel_l2"]) < 5e-6, res
+
+
+def test_render_with_engine_keys_shared_and_tiers(tmp_path):
+    """settings.txt `engine.*` keys reach the engine: two instances as ONE shared, tiered, batched engine give
+    the same audio as two private uniform engines."""
+    fs, B, L = 48000, 64, 64 * 8 + 512 * 5 + 11
+    irs = [O.synth_ir(L, fs, 330 + i) for i in range(4)]
+    for j in range(2):
+        write_f32_wav(tmp_path / f"ir{j}.wav", np.stack([irs[2 * j], irs[2 * j + 1]]), fs)
+    (tmp_path / "all.index").write_text(f"{tmp_path}/ir0.wav\n{tmp_path}/ir1.wav\n")
+    x = np.stack([O.synth_audio(B * 200, 430 + c) for c in range(4)])
+    write_f32_wav(tmp_path / "in.wav", x, fs)
+
+    def render(extra, name):
+        lines = ["conv.count 4"] + extra
+        for i in range(4):
+            lines += [f"conv[{i}].fftSize 8192", f"conv[{i}].index {tmp_path}/all.index", f"conv[{i}].input system:capture_{i + 1}",
+                      f"conv[{i}].output system:playback_{i + 1}", f"conv[{i}].cc.message 176"]
+            lines += [f"conv[{i}].cc.{k} {20 + n}" for n, k in enumerate(["select", "predelay", "dry", "wet", "speed", "panDry", "panWet", "level"])]
+            lines += [f"conv[{i}].value.select {i % 2}", f"conv[{i}].value.predelay {7 * i}", f"conv[{i}].value.dry 0.25", f"conv[{i}].value.wet 0.75",
+                      f"conv[{i}].value.speed 100", f"conv[{i}].value.panDry 0.0", f"conv[{i}].value.panWet {0.25 * i - 0.25}", f"conv[{i}].value.level 1.0"]
+        (tmp_path / f"{name}.txt").write_text("\n".join(lines) + "\n")
+        subprocess.check_call([RENDER, "--settings", str(tmp_path / f"{name}.txt"), "--in", str(tmp_path / "in.wav"), "--out", str(tmp_path / f"{name}.wav"),
+                               "--period", str(B), "--warmup", "100"], stdout=subprocess.DEVNULL)
+        return read_f32_wav(tmp_path / f"{name}.wav")
+
+    ya = render([], "private")
+    yb = render(["engine.shared 2", "engine.tiers auto", "engine.period 64"], "shared")
+    assert ya.shape == yb.shape == (4, B * 200)
+    for c in range(4):
+        assert O.rel_l2(yb[c], ya[c]) < 2e-6, (c, O.rel_l2(yb[c], ya[c]))
