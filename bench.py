@@ -332,13 +332,22 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- this engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_pg = dist.new_group(backend="gloo")   # host-side rendezvous that leaves the GPUs idle (see cpu_barrier)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def cpu_barrier():
+        # an NCCL barrier parks a spinning kernel on every waiting rank's GPU; while rank 0 drives ALL GPUs from
+        # one process (ca_group) the other ranks must wait on the host instead
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_pg)
 
     def max_over_ranks(x):
         if world == 1:
@@ -588,10 +597,10 @@ def run_ours(args):
     # ---- BASELINE configs[4]: one 60 s IR split by partition range over all N GPUs (ca_group, one process) ----
     if not args.no_irsplit:
         torch.cuda.empty_cache()
-        barrier()
+        cpu_barrier()
         if rank == 0:
             extras["irsplit_60s"] = irsplit_group(ca, world, args.irsplit_seconds, args.irsplit_periods)
-        barrier()
+        cpu_barrier()
 
     # ---- the reference's class API on this engine (N = 1 only: one process per K) ----
     if rank == 0 and world == 1 and not args.no_class_api and os.path.exists(os.path.join(ROOT, "tests", "dropin", "libdropin_conv.so")):

@@ -278,6 +278,8 @@ struct ca_engine {
         int *gerr = nullptr;
     } link;
     float2 *d_rowtw = nullptr;  // [W_256^n | W_512^k]: twiddles of the 256-point row FFT
+    uint32_t *d_vpool = nullptr;  // bitmap of the shared cross-fade voice entries
+    uint32_t n_voices = 0, n_extra = 0;  // voice pool: n_items homes + n_extra shared entries
     bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
     bool fused = false;       // tier 0 runs as one fused kernel (k_fused0)
     uint32_t fused_smem = 0;
@@ -357,6 +359,11 @@ int flush_params(ca_engine *e)
     return CA_OK;
 }
 
+VoicePool voice_pool(const ca_engine *e)
+{
+    return VoicePool{e->d_vpool, (e->n_extra + 31u) / 32u, e->n_inst * e->n_in, e->n_extra};
+}
+
 MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
 {
     return MacArgs{t.X, t.H, t.Ypart, e->d_par, e->d_st, e->d_ctl, e->n_inst * e->n_in, e->n_in, e->nv, t.Lring, t.P, t.S,
@@ -380,6 +387,7 @@ void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t s
 void launch_fwd0(ca_engine *e, bool pdl, FwdArgs fa, cudaStream_t st)
 {
     fa.rowtw = e->d_rowtw;
+    fa.vp = voice_pool(e);
     if (e->rows0) launch_k(pdl, k_fwd0_rows, dim3((fa.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, fa);
     else launch_k(pdl, e->fft.fwd, dim3((fa.n_items + kFwdWarps - 1) / kFwdWarps), dim3(kFwdWarps * 32), 0, st, fa);
 }
@@ -483,7 +491,7 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
         FusedArgs ga{d_in, d_out, e->d_ring, t0.X, t0.H, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
                      n_alloc, e->n_in, e->nv, t0.Lring, t0.P, e->ring_len, e->ring_out, e->acc_len, i0,
-                     (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u};
+                     (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, voice_pool(e)};
         if (profile) { CA_CUDA(cudaEventRecord(e->ev[0], e->stream)); CA_CUDA(cudaEventRecord(e->ev[1], e->stream)); }
         fn<<<i1 - i0, kFusedThreads, e->fused_smem, e->stream>>>(ga);
         if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl);
@@ -1036,7 +1044,7 @@ int ca_destroy(ca_engine *e)
     for (auto &ev : e->ptinv_ev) if (ev) cudaEventDestroy(ev);
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw); cudaFree(e->d_vpool);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1129,6 +1137,15 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     if (const char *tr = getenv("CA_PIPE_TRACE")) e->trace_at = (uint64_t)atoll(tr);
 
     const size_t n_items = (size_t)e->n_inst * e->n_in;
+    // voice pool: one home entry per (instance, input) + shared entries for the second (third ...) voice of
+    // inputs that are cross-fading.  Small engines get every voice resident (n_items * (nv - 1)); batches share
+    // n_items / 8 (at least 64), or what ca_config.voice_pool asks for.
+    {
+        const uint64_t all = (uint64_t)n_items * (e->nv - 1u);
+        uint64_t extra = cfg->voice_pool ? cfg->voice_pool : std::max<uint64_t>(64, n_items / 8);
+        e->n_extra = (uint32_t)std::min<uint64_t>(all, extra);
+        e->n_voices = (uint32_t)n_items + e->n_extra;
+    }
     uint32_t s_max = e->B, reach = e->B;
     e->arena_bytes = 0;
     const bool legacy_fft = (cfg->flags & CA_FLAG_LEGACY_FFT) != 0;
@@ -1176,7 +1193,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         const uint32_t rows = t.P * e->n_in;  // steady state: one voice per input
         t.n_split = std::max<uint32_t>(1, std::min(split, std::max<uint32_t>(1, rows / (uint32_t)t.mac.kc)));
         t.h_bytes = (size_t)cfg->n_ir_slots * e->n_out * t.P * t.S * sizeof(float2);
-        t.x_bytes = n_items * e->nv * t.Lring * t.S * sizeof(float2);
+        t.x_bytes = (size_t)e->n_voices * t.Lring * t.S * sizeof(float2);
         e->arena_bytes += t.h_bytes + t.x_bytes;
         s_max = std::max(s_max, t.S);
         reach = std::max(reach, t.off + t.S);
@@ -1239,7 +1256,12 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         CA_CUDA(cudaMalloc(&t.tw, tw.size() * sizeof(float2)));
         CA_CUDA(cudaMemcpyAsync(t.tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));  // pageable: staged before return
     }
-    const size_t ring_bytes = n_items * e->nv * e->ring_len * sizeof(float);
+    const size_t ring_bytes = (size_t)e->n_voices * e->ring_len * sizeof(float);
+    {
+        const size_t words = std::max<size_t>(1, (e->n_extra + 31u) / 32u);
+        CA_CUDA(cudaMalloc(&e->d_vpool, words * sizeof(uint32_t)));
+        CA_CUDA(cudaMemsetAsync(e->d_vpool, 0, words * sizeof(uint32_t), e->stream));
+    }
     CA_CUDA(cudaMalloc(&e->d_ring, ring_bytes));
     CA_CUDA(cudaMemsetAsync(e->d_ring, 0, ring_bytes, e->stream));
     size_t acc_bytes = 0;
@@ -1454,6 +1476,8 @@ int ca_set_active(ca_engine *e, uint32_t n)
         // delay-line block is skipped, and the voice's first forward clears its time ring) instead of
         // replaying pre-deactivation audio as a tail
         const size_t i0 = (size_t)e->n_active * e->n_in, cnt = (size_t)(n - e->n_active) * e->n_in, n_alloc = (size_t)e->n_inst * e->n_in;
+        // shared cross-fade voices the parked items still hold go back to the pool first
+        k_release_voices<<<(unsigned)((cnt + 127) / 128), 128, 0, e->stream>>>(e->d_st + (e->t_host & 1) * n_alloc + i0, (uint32_t)cnt, voice_pool(e));
         for (int b = 0; b < 2; b++) CA_CUDA(cudaMemsetAsync(e->d_st + b * n_alloc + i0, 0, cnt * sizeof(ItemState), e->stream));
         if (e->d_acc) CA_CUDA(cudaMemsetAsync(e->d_acc + (size_t)e->n_active * e->n_out * e->acc_len, 0, (size_t)(n - e->n_active) * e->n_out * e->acc_len * sizeof(float), e->stream));
         CA_CUDA(cudaStreamSynchronize(e->stream));

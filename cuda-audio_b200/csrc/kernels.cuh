@@ -52,7 +52,80 @@ struct ItemState {
     uint32_t fresh;                        // bit v: voice v was (re)allocated in this period
     uint32_t vsteps;
     uint32_t vsteps_seq_seen, glide_seq_seen, pad;
+    // storage of voice v (time ring + one delay line per tier): 1 + index into the voice pool, 0 = none.
+    // Item i owns pool entry i for good (its "home"); entries >= n_home are shared by all items and only
+    // held while a second voice is audible or ringing out (an IR cross-fade), see voice_storage_update().
+    uint32_t pool[kMaxVoices];
 };
+
+// Shared pool of cross-fade voices.  Outside cross-fades an input needs ONE voice; a resident second delay
+// line per input was 22 % of an instance's memory (and HBM capacity, not time, bounds the channel count).
+struct VoicePool {
+    uint32_t *bitmap;   // bit b of word w: pool entry n_home + 32 w + b is in use
+    uint32_t n_words;
+    uint32_t n_home;    // = allocated (instance, input) items
+    uint32_t n_extra;   // shared entries
+};
+
+__device__ __forceinline__ uint32_t voice_pool_alloc(const VoicePool &vp, uint32_t hint)
+{
+    for (uint32_t i = 0; i < vp.n_words; i++) {
+        const uint32_t w = (hint + i) % vp.n_words;
+        uint32_t cur = vp.bitmap[w];
+        while (~cur) {
+            const uint32_t bit = (uint32_t)__ffs((int)~cur) - 1u;
+            if (32u * w + bit >= vp.n_extra) break;
+            const uint32_t prev = atomicOr(&vp.bitmap[w], 1u << bit);
+            if (!(prev & (1u << bit))) return vp.n_home + 32u * w + bit + 1u;
+            cur = prev | (1u << bit);
+        }
+    }
+    return 0u;  // pool exhausted
+}
+
+__device__ __forceinline__ void voice_pool_free(const VoicePool &vp, uint32_t entry_p1)
+{
+    if (entry_p1 > vp.n_home) {  // homes are never returned
+        const uint32_t e = entry_p1 - 1u - vp.n_home;
+        atomicAnd(&vp.bitmap[e >> 5], ~(1u << (e & 31u)));
+    }
+}
+
+// ONE lane per item, after step_item_state(): release the storage of voices that went silent in this step,
+// give every fresh voice storage (the item's home entry when no other voice of the item holds it, else a
+// shared entry).  When the shared pool is exhausted the new voice takes over the storage of the item's
+// quietest other voice, which is cut off: the IR switch degrades to a hard switch instead of failing.
+__device__ __forceinline__ void voice_storage_update(ItemState &s, uint32_t old_active, uint32_t item, int nv, const VoicePool &vp)
+{
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++)
+        if (v < nv && ((old_active >> v) & 1u) && !((s.active >> v) & 1u)) { voice_pool_free(vp, s.pool[v]); s.pool[v] = 0u; }
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++) {
+        if (!(v < nv && ((s.active >> v) & 1u) && s.pool[v] == 0u)) continue;
+        bool home_used = false;
+#pragma unroll
+        for (int u = 0; u < kMaxVoices; u++) home_used |= (u < nv && s.pool[u] == item + 1u);
+        uint32_t got = home_used ? voice_pool_alloc(vp, item) : item + 1u;
+        if (!got) {
+            int q = -1;
+            float best = 3.0e38f;
+#pragma unroll
+            for (int u = 0; u < kMaxVoices; u++)
+                if (u < nv && u != v && ((s.active >> u) & 1u) && s.pool[u] && fabsf(s.c[u]) < best) { best = fabsf(s.c[u]); q = u; }
+#pragma unroll
+            for (int u = 0; u < kMaxVoices; u++)
+                if (u == q) { got = s.pool[u]; s.pool[u] = 0u; s.active &= ~(1u << u); }
+        }
+        s.pool[v] = got;
+        s.fresh |= 1u << v;  // whatever the entry held belongs to another voice's past
+    }
+}
+
+// the whole per-period voice step of one (instance, input) item, warp-wide: every lane computes the pure
+// step, lane 0 updates the storage, the result is broadcast and stored for the period's other kernels
+__device__ __forceinline__ ItemState item_step_warp(ItemState *st, uint32_t n_items_alloc, uint32_t item, const InParamDev &p, unsigned long long t,
+                                                    int nv, uint32_t ring_out, const VoicePool &vp, int lane);
 struct Ctl {
     // period counter.  k_forward and k_mac read t; k_forward publishes t_next = t + 1; k_inverse reads
     // only t_next and finally sets t = t_next, so no kernel reads a field another CTA of it writes.
@@ -130,13 +203,44 @@ __device__ __forceinline__ ItemState step_item_state(ItemState s, const InParamD
     return s;
 }
 
+__device__ __forceinline__ ItemState item_step_warp(ItemState *st, uint32_t n_items_alloc, uint32_t item, const InParamDev &p, unsigned long long t,
+                                                    int nv, uint32_t ring_out, const VoicePool &vp, int lane)
+{
+    const ItemState old = st[(t & 1ull) * n_items_alloc + item];
+    ItemState s = step_item_state(old, p, t, nv, ring_out);
+    if (lane == 0) voice_storage_update(s, old.active, item, nv, vp);
+    s.active = __shfl_sync(0xffffffffu, s.active, 0);
+    s.fresh = __shfl_sync(0xffffffffu, s.fresh, 0);
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++) s.pool[v] = __shfl_sync(0xffffffffu, s.pool[v], 0);
+    if (lane == 0) st[((t + 1ull) & 1ull) * n_items_alloc + item] = s;
+    return s;
+}
+
+// ca_set_active: items that are about to be reset hand their shared voice entries back
+__global__ void k_release_voices(const ItemState *st, uint32_t n, const VoicePool vp)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int v = 0; v < kMaxVoices; v++) voice_pool_free(vp, st[i].pool[v]);
+}
+
+// pool entry (0-based) of voice v; only called for voices that are active (they always have storage)
+__device__ __forceinline__ uint32_t voice_entry(const ItemState &s, uint32_t v)
+{
+    uint32_t e = 0;
+#pragma unroll
+    for (int q = 0; q < kMaxVoices; q++) e = (q == (int)v) ? s.pool[q] : e;
+    return e - 1u;
+}
+
 // ------------------------------------------------------------------------------------------
 // forward (tier 0): one warp per (instance, input, voice)
 // ------------------------------------------------------------------------------------------
 struct FwdArgs {
     const float *in;   // [inst][n_in][B]
-    float *ring;       // [(inst*n_in + i)*nv + v][ring_len]: predelayed, gain-scaled input stream
-    float2 *X;         // FDL [(inst*n_in + i)*nv + v][Lring][B]
+    float *ring;       // [voice pool entry][ring_len]: predelayed, gain-scaled input stream
+    float2 *X;         // FDL [voice pool entry][Lring][B]
     const InParamDev *par;
     ItemState *st;     // [2][inst*n_in]
     Ctl *ctl;
@@ -149,6 +253,7 @@ struct FwdArgs {
     // ctl->t round trip off the head of every warp's chain of dependent loads (0: read ctl->t)
     unsigned long long t_host_p1;
     const float2 *rowtw;  // [W_256^n | W_512^k] for the row-FFT kernels (kernels_rows.cuh)
+    VoicePool vp;
 };
 
 // One warp per (instance, input); it steps the voice state once and then runs every audible voice
@@ -168,8 +273,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 20 / kFwdWarps) k_forward(cons
 
     const InParamDev p = a.par[item];
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
-    const ItemState s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
-    if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+    const ItemState s = item_step_warp(a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
 
     WarpFft<R> f;
     f.init(a.twM);
@@ -188,7 +292,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 20 / kFwdWarps) k_forward(cons
 #pragma unroll
         for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
         const float gain = cv * p.level;
-        float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
+        const uint32_t entry = voice_entry(s, v);
+        float *ring = a.ring + (size_t)entry * a.ring_len;
         if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
             for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
@@ -248,7 +353,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 20 / kFwdWarps) k_forward(cons
         }
         f.forward(z);
         f.split_r2c(z, a.tw2M);
-        float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot) * B;
+        float2 *dst = a.X + ((size_t)entry * a.Lring + slot) * B;
 #pragma unroll
         for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
     }
@@ -369,7 +474,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uin
 // contiguous ranges (one CTA each) so few instances still cover all SMs; bins are cut into tiles
 // of BT complex.
 struct MacArgs {
-    const float2 *X;   // FDL [(inst*n_in + i)*nv + v][Lring][S]
+    const float2 *X;   // FDL [voice pool entry][Lring][S]
     const float2 *H;   // IR bank [slot][n_out][P][S]
     float2 *Ypart;     // [inst][n_split][n_out][S]
     const InParamDev *par;
@@ -455,6 +560,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
     uint64_t *empty = full + NSTAGE;
     __shared__ uint32_t s_rowstart[kMaxStreams + 1];  // prefix sum of rows per stream
     __shared__ uint32_t s_slot[kMaxStreams];
+    __shared__ uint32_t s_entry[kMaxStreams];  // voice pool entry of every stream
     __shared__ float s_pan[2][NOUT];
 
     const uint32_t split = blockIdx.x, tile = blockIdx.y, inst = a.inst0 + blockIdx.z * a.inst_stride;
@@ -471,11 +577,12 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
         mbar_fence_init();
     } else if (warp == 0) {
         // lane s: rows of stream s = (input s / nv, voice s % nv); exclusive prefix sum by shuffles
-        uint32_t nk = 0, slot = 0;
+        uint32_t nk = 0, slot = 0, entry = 0;
         if ((uint32_t)lane < ns) {
             const uint32_t i = lane / a.nv, v = lane % a.nv;
             const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + inst * a.n_in + i];
             if ((st.active >> v) & 1u) {
+                entry = st.pool[v] - 1u;
                 // partition k reads the block fired at index n_fire - k_off - k; it is valid when that
                 // block was built after the voice's (re)start: fire * m - 1 >= start
                 const long long first_fire = (long long)((st.start[v] + phase + a.m) / a.m);  // ceil((start + 1 + phase) / m)
@@ -491,7 +598,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
             if (lane >= d) incl += up;
         }
         const uint32_t total_rows = __shfl_sync(kFull, incl, kMaxStreams - 1);  // all 32 lanes take part
-        if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; }
+        if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; s_entry[lane] = entry; }
         else if (lane == kMaxStreams) s_rowstart[kMaxStreams] = total_rows;
     } else if (warp == 2 && lane < 2 * NOUT) {
         const uint32_t i = lane / NOUT;
@@ -537,7 +644,7 @@ __global__ void __launch_bounds__(kMacThreads) k_mac(const MacArgs a)
                 const float2 *src;
                 if (w == 0) {
                     const uint32_t slot = (head + a.k_off + k) % a.Lring;
-                    src = a.X + ((size_t)(inst * ns + s) * a.Lring + slot) * a.S + tile * BT;
+                    src = a.X + ((size_t)s_entry[s] * a.Lring + slot) * a.S + tile * BT;
                 } else {
                     src = a.H + (((size_t)s_slot[s] * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
                 }
@@ -693,7 +800,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
     MacStageMeta *meta = reinterpret_cast<MacStageMeta *>(smem + PCfg::RING_BYTES + PCfg::BAR_BYTES);
     float4 *red = reinterpret_cast<float4 *>(smem + PCfg::RING_BYTES + PCfg::BAR_BYTES + PCfg::META_BYTES);  // [G-1][NOUT][LR]
     float2 *red0 = reinterpret_cast<float2 *>(red + (G - 1) * NOUT * LR);                                     // [G][NOUT]
-    __shared__ uint32_t s_rs[kMaxStreams], s_sl[kMaxStreams];  // producer-private: first row / IR slot of every stream
+    __shared__ uint32_t s_rs[kMaxStreams], s_sl[kMaxStreams], s_en[kMaxStreams];  // producer-private: first row / IR slot / voice pool entry of every stream
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t ns = a.n_in * a.nv;
@@ -715,9 +822,9 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
         const uint64_t pol = a.stream_hint ? l2_policy_evict_first() : l2_policy_evict_last();
         // raw descriptor of a work item, one stream (lane < ns) / one pan gain (lane < 2 NOUT) per lane;
         // the loads of item j + 1 are issued before item j is streamed so their latency is hidden
-        struct Raw { uint32_t active, slot; unsigned long long start; float pan; };
+        struct Raw { uint32_t active, slot, entry; unsigned long long start; float pan; };
         auto load_raw = [&](uint32_t j) {
-            Raw r{0u, 0u, 0ull, 0.f};
+            Raw r{0u, 0u, 0u, 0ull, 0.f};
             const uint32_t inst = a.inst0 + (j >> t_log) * a.inst_stride;
             if ((uint32_t)lane < ns) {
                 const uint32_t i = lane / a.nv, v = lane % a.nv;
@@ -725,6 +832,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                 r.active = (st.active >> v) & 1u;
                 r.start = st.start[v];
                 r.slot = st.slot[v];
+                r.entry = st.pool[v] - 1u;
             }
             if (lane < 2 * NOUT) {
                 const uint32_t i = lane / NOUT;
@@ -753,7 +861,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
             }
             const uint32_t excl = incl - nk;
             __syncwarp();  // every lane has issued the previous item's copies: the row table may change
-            if (lane < kMaxStreams) { s_rs[lane] = excl; s_sl[lane] = cur.slot; }
+            if (lane < kMaxStreams) { s_rs[lane] = excl; s_sl[lane] = cur.slot; s_en[lane] = cur.entry; }
             __syncwarp();
             const uint32_t total = __shfl_sync(kFull, incl, kMaxStreams - 1);
             const uint32_t boundary = a.nv < kMaxStreams ? __shfl_sync(kFull, excl, a.nv) : total;
@@ -788,7 +896,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                     if (w == 0) {
                         uint32_t pos = head0 + k;  // k < P <= Lring
                         if (pos >= a.Lring) pos -= a.Lring;
-                        src = a.X + ((size_t)(inst * ns + s) * a.Lring + pos) * a.S + tile * BT;
+                        src = a.X + ((size_t)s_en[s] * a.Lring + pos) * a.S + tile * BT;
                     } else {
                         src = a.H + (((size_t)slot * NOUT + (w - 1)) * a.P + k) * a.S + tile * BT;
                     }
@@ -1086,6 +1194,7 @@ struct FusedArgs {
     const float2 *twM, *tw2M;
     uint32_t n_items_alloc, n_in, nv, Lring, P, ring_len, ring_out, acc_len;
     uint32_t inst0, stream_hint, raw_wet;
+    VoicePool vp;
 };
 
 constexpr int kFusedThreads = kMacConsumers + 32 + 64;  // 8 consumer warps, 1 producer warp, 2 FFT warps
@@ -1115,7 +1224,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + NSTAGE * Cfg::STAGE_BYTES + Cfg::XNEW_BYTES + Cfg::YS_BYTES);
     uint64_t *empty = full + NSTAGE;
     uint64_t *xready = empty + NSTAGE;
-    __shared__ uint32_t s_nk[4], s_slot[4], s_rowstart[5];
+    __shared__ uint32_t s_nk[4], s_slot[4], s_entry[4], s_rowstart[5];
     __shared__ float s_pan[2][NOUT];
 
     const uint32_t inst = a.inst0 + blockIdx.x;
@@ -1139,12 +1248,12 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
         if ((uint32_t)fw < a.n_in) {
             const uint32_t item = inst * a.n_in + fw;
             p = a.par[item];
-            s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
-            if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+            s = item_step_warp(a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
             if ((uint32_t)lane < a.nv) {
                 uint32_t nk = 0, sl = 0;
                 if ((s.active >> lane) & 1u) {
                     unsigned long long st0 = 0;
+                    s_entry[fw * a.nv + lane] = voice_entry(s, (uint32_t)lane);
 #pragma unroll
                     for (int q = 0; q < kMaxVoices; q++) { if (q == lane) { st0 = s.start[q]; sl = s.slot[q]; } }
                     const long long cnt = (long long)(t + 1ull) - (long long)(st0 + 1ull) + 1;
@@ -1186,7 +1295,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
 #pragma unroll
                 for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
                 const float gain = cv * p.level;
-                float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
+                const uint32_t entry = voice_entry(s, v);
+                float *ring = a.ring + (size_t)entry * a.ring_len;
                 if ((s.fresh >> v) & 1u) {
                     for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncwarp();
@@ -1238,7 +1348,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
                 }
                 f.forward(z);
                 f.split_r2c(z, a.tw2M);
-                float2 *dst = a.X + (((size_t)item * a.nv + v) * a.Lring + slot_new) * B;
+                float2 *dst = a.X + ((size_t)entry * a.Lring + slot_new) * B;
                 float2 *xs = xnew + (size_t)(fw * a.nv + v) * B;
 #pragma unroll
                 for (int d = 0; d < R; d++) { dst[f.c + 32 * d] = z[d]; xs[f.c + 32 * d] = z[d]; }
@@ -1278,7 +1388,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
                 const float2 *src;
                 if (w == 0) {
                     if (k == 0) continue;
-                    src = a.X + ((size_t)(inst * ns + sidx) * a.Lring + (slot_new + k) % a.Lring) * B;
+                    src = a.X + ((size_t)s_entry[sidx] * a.Lring + (slot_new + k) % a.Lring) * B;
                 } else {
                     src = a.H + (((size_t)s_slot[sidx] * NOUT + (w - 1)) * a.P + k) * B;
                 }
@@ -1449,8 +1559,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_fused0(const FusedArgs a)
 constexpr int kTierThreads = 512;  // launch bound; the host launches S/16 threads clamped to [128, 512] (engine.cu: tier_div)
 
 struct TierFwdArgs {
-    const float *ring;    // [(item*nv + v)][ring_len]
-    float2 *X;            // FDL of this tier [(item*nv + v)][Lring][S]
+    const float *ring;    // [voice pool entry][ring_len]
+    float2 *X;            // FDL of this tier [voice pool entry][Lring][S]
     const ItemState *st;  // [2][n_items_alloc]
     const Ctl *ctl;
     const float2 *twM, *tw2M;
@@ -1472,10 +1582,10 @@ __global__ void __launch_bounds__(kTierThreads, 2) k_tier_forward(const TierFwdA
     const uint32_t v = blockIdx.x;
     const uint32_t inst = a.inst0 + blockIdx.z * a.inst_stride;
     const uint32_t item = inst * a.n_in + blockIdx.y;
-    const uint32_t w = item * a.nv + v;
     const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     const ItemState &st = a.st[(tend & 1ull) * a.n_items_alloc + item];
     if (!((st.active >> v) & 1u)) return;
+    const uint32_t w = st.pool[v] - 1u;  // voice pool entry
     __shared__ uint32_t s_slot;
     if (threadIdx.x == 0) {  // m is a power of two; the 64-bit modulo runs once per CTA
         const unsigned long long n_fire = (tend + (inst & (a.m - 1u))) >> (31 - __clz((int)a.m));

@@ -40,8 +40,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
 
     const InParamDev p = a.par[item];
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
-    const ItemState s = step_item_state(a.st[(t & 1ull) * a.n_items_alloc + item], p, t, (int)a.nv, a.ring_out);
-    if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+    const ItemState s = item_step_warp(a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
 
     float2 *row = sm + warp * kRowSlots;
     const uint32_t mask = a.ring_len - 1;
@@ -57,7 +56,8 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
 #pragma unroll
         for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
         const float gain = cv * p.level;
-        float *ring = a.ring + ((size_t)item * a.nv + v) * a.ring_len;
+        const uint32_t entry = voice_entry(s, v);
+        float *ring = a.ring + (size_t)entry * a.ring_len;
         if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
             for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
         row_fft256<false>(z, row, tb, lane, NoPostTw{});
         rows_split<false>(row, row, true, make_float2(1.f, 0.f), tb, lane);
         __syncwarp();
-        row_store_global(row, a.X + (((size_t)item * a.nv + v) * a.Lring + slot) * B, lane);
+        row_store_global(row, a.X + ((size_t)entry * a.Lring + slot) * B, lane);
         __syncwarp();
     }
 }
@@ -207,10 +207,10 @@ __device__ __forceinline__ TierCommon tier_fwd_common(const TierFwdArgs &a, uint
     TierCommon c;
     c.inst = a.inst0 + z * a.inst_stride;
     c.item = c.inst * a.n_in + i;
-    c.w = c.item * a.nv + v;
     c.tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     const ItemState &st = a.st[(c.tend & 1ull) * a.n_items_alloc + c.item];
     c.active = ((st.active >> v) & 1u) != 0;
+    c.w = st.pool[v] - 1u;  // voice pool entry (meaningful when active)
     const unsigned long long n_fire = (c.tend + (c.inst & (a.m - 1u))) >> (31 - __clz((int)a.m));  // m is a power of two
     c.slot = (a.Lring - 1u) - (uint32_t)(n_fire % a.Lring);
     return c;

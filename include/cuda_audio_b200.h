@@ -96,6 +96,11 @@ typedef struct ca_config {
     uint32_t tier_block[CA_MAX_TIERS];
     uint32_t tier_parts[CA_MAX_TIERS];
     float sample_rate;      /* only for deadline / xrun accounting; 0 = off */
+    /* Cross-fade voices shared by all inputs of the engine (each input owns one voice for good; a second one
+     * is only needed while an IR switch glides, conv.cu:15-32).  0 = auto: every voice resident for small
+     * engines, n_inputs / 8 shared voices for batches.  When the pool runs dry an IR switch of that input
+     * degrades to a hard switch. */
+    uint32_t voice_pool;
 } ca_config;
 
 /* Per-input parameter block == Convolution::CC::value (conv.h:40-50). */

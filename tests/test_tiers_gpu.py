@@ -498,3 +498,58 @@ def test_row_fft_tier0_uniform_matches_legacy():
     for s in range(K):
         for o in range(2):
             assert O.rel_l2(y_new[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_new[s, o], y_old[s, o]))
+
+
+def test_shared_voice_pool_crossfades_and_exhaustion():
+    """Cross-fade voices come from a pool shared by all inputs of the engine (ca_config.voice_pool).  40 instances
+    switch IR at once with only 6 shared voices: six inputs glide, the others fall back to a hard switch; the
+    instances that do not switch are untouched, everybody ends up on the new IR exactly, the pool is handed
+    back (a second wave of switches finds voices again), and with a big enough pool the batch equals
+    per-instance engines that have every voice resident."""
+    m = ca()
+    B, K = 64, 40
+    L = 64 * 8 + 512 * 3 - 7
+    tiers = [(64, 8), (512, 0)]
+    irs = irs2x2(L, 7700) + irs2x2(L, 7750)          # bank slots 0..3
+    nper = 260
+    x = np.stack([np.stack([O.synth_audio(B * nper, 7800 + 2 * s + i) for i in range(2)]) for s in range(K)])
+    switchers = [s for s in range(K) if s % 4 != 3]   # 30 instances switch input 0 from IR 0 to IR 2
+
+    def go(pool, k_inst, xs, which):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=k_inst, n_ir_slots=4, tiers=tiers, voice_pool=pool) as e:
+            for j in range(4):
+                e.load_ir(j, irs[j][0], irs[j][1])
+            for s in range(k_inst):
+                for i in range(2):
+                    e.set_params(s, i, select=i, wet=1.0, dry=0.0)
+                    e.set_glide(s, i, 1.0)
+            out = np.zeros((k_inst, 2, B * nper), np.float32)
+            for t in range(nper):
+                if t == 60:
+                    for s in which:
+                        e.set_params(s, 0, select=2, wet=1.0, dry=0.0, vsteps=10)
+                if t == 160:                           # second wave: back to IR 0 (needs pool entries again)
+                    for s in which:
+                        e.set_params(s, 0, select=0, wet=1.0, dry=0.0, vsteps=10)
+                out[:, :, t * B:(t + 1) * B] = e.process(xs[:, :, t * B:(t + 1) * B])
+            return out
+
+    y_small = go(6, K, x, switchers)
+    y_big = go(2 * K, K, x, switchers)
+    # (1) instances that never switch: identical whatever the others do, and equal to the truth
+    for s in (3, 39):
+        assert np.array_equal(y_small[s], y_big[s])
+        truth = O.engine_truth(x[s], [irs[0], irs[1]], [dict(wet=1.0)] * 2)
+        assert O.rel_l2(y_small[s, 0], truth[0]) < 5e-6
+    # (2) with every voice available the batch equals single-instance engines (all voices resident there)
+    for s in (0, 17):
+        one = go(0, 1, x[s:s + 1], [0])
+        assert O.rel_l2(y_big[s, 0], one[0, 0]) < 1e-6, (s, O.rel_l2(y_big[s, 0], one[0, 0]))
+    # (3) exhausted pool: once the old IR has rung out (IR length + glide) everybody is exactly on the new IR
+    settle = 60 + 10 + 60 + (L + B - 1) // B + 4
+    for s in switchers:
+        seg = slice(settle * B, 160 * B)   # only input fed after the switch is still audible here
+        assert O.rel_l2(y_small[s, 0, seg], y_big[s, 0, seg]) < 1e-5, s
+    # (4) the second wave found pool entries again for some inputs: at least six of them glide exactly like the big pool
+    same = sum(np.array_equal(y_small[s, 0, 160 * B:200 * B], y_big[s, 0, 160 * B:200 * B]) for s in switchers)
+    assert same >= 6, same
