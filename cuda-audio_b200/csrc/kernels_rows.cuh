@@ -41,6 +41,11 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
     const InParamDev p = a.par[item];
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
     const ItemState s = item_step_warp(a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
+    // per-voice coefficient and storage are re-read from the state lane 0 just stored (same warp, L1-hot):
+    // keeping eight more values alive across the transform spills at 64 registers
+    const ItemState *sn = a.st + ((t + 1ull) & 1ull) * a.n_items_alloc + item;
+    const uint32_t active = s.active, fresh = s.fresh;
+    __syncwarp();
 
     float2 *row = sm + warp * kRowSlots;
     const uint32_t mask = a.ring_len - 1;
@@ -51,14 +56,11 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
 
 #pragma unroll 1
     for (uint32_t v = 0; v < a.nv; v++) {
-        if (!((s.active >> v) & 1u)) continue;
-        float cv = 0.f;
-#pragma unroll
-        for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
-        const float gain = cv * p.level;
-        const uint32_t entry = voice_entry(s, v);
+        if (!((active >> v) & 1u)) continue;
+        const float gain = sn->c[v] * p.level;
+        const uint32_t entry = sn->pool[v] - 1u;
         float *ring = a.ring + (size_t)entry * a.ring_len;
-        if ((s.fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
+        if ((fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
             for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
         }

@@ -499,3 +499,21 @@ def test_edge_cases_tiny_truncated_and_zero_irs_silence(tiers):
         else:
             for o in range(2):
                 assert O.rel_l2(y[o], truth[o]) < 5e-6, (name, o, O.rel_l2(y[o], truth[o]))
+
+
+def test_l2_persist_window_flag_is_bit_identical():
+    """CA_FLAG_L2_PERSIST only changes cache policy (access-policy window over [IR spectra | delay lines])."""
+    m = ca()
+    fs, B, L = 48000, 256, 256 * 120 + 9
+    irs = make_irs(L, fs)
+    x = np.stack([O.synth_audio(B * 150, 2100 + i) for i in range(2)])
+
+    def go(flags):
+        with m.Engine(period=B, max_ir_frames=L, flags=flags) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, select=i, wet=0.8, dry=0.1)
+                e.set_glide(0, i, 0.8)
+            return e.render(x[None])[0]
+
+    assert np.array_equal(go(m.FLAG_GRAPH), go(m.FLAG_GRAPH | m.FLAG_L2_PERSIST))
