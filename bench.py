@@ -623,7 +623,7 @@ def run_ours(args):
             allr = [None] * world
             dist.all_gather_object(allr, lat)
             lat = dict(allr[0])
-            lat["per_gpu"] = [{k: {"p50_us": v["p50_us"], "p99_us": v["p99_us"], "paced_p99_us": v["paced"]["p99_us"]} for k, v in r.items() if isinstance(v, dict)} for r in allr]
+            lat["per_gpu"] = [{k: {"p50_us": v["p50_us"], "p99_us": v["p99_us"], "paced_p99_us": v["paced"]["p99_us"]} for k, v in r.items() if isinstance(v, dict) and "paced" in v} for r in allr]
         extras["latency_1_instance"] = lat
 
     # ---- BASELINE configs[3]: 1024 independent stereo streams x 2 s IRs, stream-sharded over the GPUs (strong scaling) ----
