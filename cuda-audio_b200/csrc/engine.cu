@@ -1096,6 +1096,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     e->B = cfg->period; e->R = cfg->period / 32;
     e->n_inst = e->n_active = cfg->n_instances; e->n_in = cfg->n_in; e->n_out = cfg->n_out;
     e->nv = cfg->max_voices ? cfg->max_voices : 2u;
+    if (cfg->io_chunks) e->io_chunks = std::min<uint32_t>(kIoChunks, cfg->io_chunks);
     if (const char *c = getenv("CA_IO_CHUNKS")) e->io_chunks = std::max(1, std::min<int>(kIoChunks, atoi(c)));
     int rc = plan_tiers(cfg, e);
     if (rc) return rc;
@@ -1127,12 +1128,13 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     for (auto &row : e->ptm_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CA_CUDA(cudaEventCreateWithFlags(&e->pm_tail, cudaEventDisableTiming));
     for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->pipe_mode = (cfg->schedule & CA_SCHED_PIPELINED) ? 1 : 0;
     if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
     e->async_tiers = (cfg->flags & CA_FLAG_ASYNC_TIERS) && e->tiers.size() > 1 && !(cfg->flags & CA_FLAG_PROFILE);
     CA_CUDA(cudaStreamCreateWithPriority(&e->s_def, cudaStreamNonBlocking, prio_lo));
     CA_CUDA(cudaEventCreateWithFlags(&e->ev_period, cudaEventDisableTiming));
     for (auto &ev : e->ev_def) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    e->pdl = !(cfg->flags & CA_FLAG_GRAPH);
+    e->pdl = !(cfg->flags & CA_FLAG_GRAPH) && !(cfg->schedule & CA_SCHED_NO_PDL);
     if (const char *pd = getenv("CA_PDL")) e->pdl = atoi(pd) != 0;
     if (const char *tr = getenv("CA_PIPE_TRACE")) e->trace_at = (uint64_t)atoll(tr);
 
@@ -1169,8 +1171,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
             // persistent schedule: resident CTA slots of the device (CA_MAC_PERSIST=0 off, =1 always when
             // n_split == 1, and forces n_split = 1; CA_MAC_SLOTS=n overrides the slot count -- tests force several items per CTA)
             const char *pe = getenv("CA_MAC_PERSIST");
-            t.p_slots = 0; t.p_force = pe && pe[0] == '1';
-            if (!(pe && pe[0] == '0')) {
+            const bool p_off = pe ? pe[0] == '0' : (cfg->schedule & CA_SCHED_MAC_PER_ITEM) != 0;
+            t.p_slots = 0; t.p_force = pe ? pe[0] == '1' : (cfg->schedule & CA_SCHED_MAC_PERSISTENT) != 0;
+            if (!p_off) {
                 CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.pfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.psmem));
                 int per_sm = 0;
                 CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)t.mac.pfn, kMacThreads, t.mac.psmem));
@@ -1200,6 +1203,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     }
     {
         const char *fz = getenv("CA_FUSE");
+        if (!fz && (cfg->schedule & CA_SCHED_FUSED_TIER0)) fz = "1";
+        if (!fz && (cfg->schedule & CA_SCHED_NO_FUSED_TIER0)) fz = "0";
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
         e->fused = e->tiers.size() > 1 && fn && e->tiers[0].n_split == 1 && e->tiers[0].tiles == 1 && e->n_in * e->nv <= 4 &&
                    (fz ? fz[0] == '1' : e->n_inst <= 16);  // measured: -2 us p50 for one instance, but 178 vs 132 us at 4096 instances

@@ -69,6 +69,15 @@ enum ca_flags {
                                    * to fp32 rounding) */
 };
 
+enum ca_schedule {
+    CA_SCHED_MAC_PERSISTENT = 1u << 0,   /* FDL MAC of every tier on the persistent work-list schedule (n_split = 1) */
+    CA_SCHED_MAC_PER_ITEM = 1u << 1,     /* never: one CTA per (instance, split, bin tile) */
+    CA_SCHED_FUSED_TIER0 = 1u << 2,      /* tier 0 as ONE kernel per instance (forward + MAC + inverse) */
+    CA_SCHED_NO_FUSED_TIER0 = 1u << 3,
+    CA_SCHED_PIPELINED = 1u << 4,        /* two-lane batch schedule: FFT lanes beside the MAC lane (measured slower end to end) */
+    CA_SCHED_NO_PDL = 1u << 5            /* no programmatic dependent launch between the period's kernels */
+};
+
 typedef struct ca_engine ca_engine;
 
 typedef struct ca_config {
@@ -101,6 +110,10 @@ typedef struct ca_config {
      * engines, n_inputs / 8 shared voices for batches.  When the pool runs dry an IR switch of that input
      * degrades to a hard switch. */
     uint32_t voice_pool;
+    /* Schedule choices that change which kernels run (ca_schedule bits; 0 = the engine picks).  The CA_*
+     * environment variables of DESIGN.md section 9 override them and exist for development sweeps only. */
+    uint32_t schedule;
+    uint32_t io_chunks;     /* instance chunks of ca_process's H2D | kernels | D2H pipeline for batches; 0 = 2 */
 } ca_config;
 
 /* Per-input parameter block == Convolution::CC::value (conv.h:40-50). */

@@ -553,3 +553,33 @@ def test_shared_voice_pool_crossfades_and_exhaustion():
     # (4) the second wave found pool entries again for some inputs: at least six of them glide exactly like the big pool
     same = sum(np.array_equal(y_small[s, 0, 160 * B:200 * B], y_big[s, 0, 160 * B:200 * B]) for s in switchers)
     assert same >= 6, same
+
+
+def test_schedule_bits_in_the_config_select_the_same_kernels_as_the_env_knobs():
+    """ca_config.schedule (CA_SCHED_*) instead of environment variables: persistent vs per-item MAC, fused vs
+    three-kernel tier 0, pipelined lanes vs sequential -- all bit-identical on the same input."""
+    m = ca()
+    B, K = 64, 6
+    tiers = [(64, 8), (512, 3), (2048, 0)]
+    L = 64 * 8 + 512 * 3 + 2048 * 2 - 33
+    irs = [irs2x2(L, 9100 + 8 * s) for s in range(K)]
+    n = B * 120
+    x = np.stack([np.stack([O.synth_audio(n, 9600 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(schedule):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, mac_split=1, schedule=schedule) as e:
+            for s in range(K):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+                    e.set_params(s, i, select=2 * s + i, wet=0.8, dry=0.1, predelay=3 * s)
+                    e.set_glide(s, i, 0.8)
+            st = e.stats()
+            return e.render(x), st.tier0_fused
+
+    y_item, f0 = go(m.SCHED_MAC_PER_ITEM | m.SCHED_NO_FUSED_TIER0)
+    y_pers, f1 = go(m.SCHED_MAC_PERSISTENT | m.SCHED_NO_FUSED_TIER0)
+    y_pipe, _ = go(m.SCHED_MAC_PERSISTENT | m.SCHED_NO_FUSED_TIER0 | m.SCHED_PIPELINED)
+    y_fused, f2 = go(m.SCHED_FUSED_TIER0)
+    assert (f0, f1, f2) == (0, 0, 1)
+    assert np.array_equal(y_item, y_pers) and np.array_equal(y_pers, y_pipe)
+    assert O.rel_l2(y_fused, y_item) < 2e-6
