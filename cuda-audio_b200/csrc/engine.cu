@@ -200,6 +200,7 @@ struct Tier {
     size_t h_bytes = 0, x_bytes = 0;
     MacVariant mac{};
     uint32_t p_slots = 0;  // resident CTA slots of the persistent MAC (0: schedule disabled)
+    uint32_t *workctr = nullptr;  // persistent MAC: [next work item, finished CTAs]
     bool p_force = false;
     // FFT family of this tier's transforms: 0 = fft_warp / fft_cta (general), 1 = row FFTs, one CTA per
     // transform (M1 = S / 256 <= 16), 2 = row FFTs, columns and rows as two launches (M1 = 32, 64)
@@ -370,6 +371,8 @@ MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
                    e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u, t.m > 1 ? 1u : 0u};
 }
 
+MacArgs with_workctr(MacArgs ma, const Tier &t) { ma.work_ctr = t.workctr; return ma; }
+
 // One MAC launch over `count` instances of tier t.  Batches (n_split == 1 and more work items than
 // resident CTA slots) take the persistent schedule: every CTA gets the same number of work items.
 void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st, bool pdl = false)
@@ -377,7 +380,7 @@ void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t s
     const uint32_t n_work = count * t.tiles;
     if (t.p_slots && t.n_split == 1 && (t.p_force || n_work > t.p_slots)) {
         const uint32_t per = (n_work + t.p_slots - 1) / t.p_slots;
-        launch_k(pdl, t.mac.pfn, dim3((n_work + per - 1) / per), dim3(kMacThreads), t.mac.psmem, st, ma, n_work, t.tiles);
+        launch_k(pdl, t.mac.pfn, dim3((n_work + per - 1) / per), dim3(kMacThreads), t.mac.psmem, st, with_workctr(ma, t), n_work, t.tiles);
     } else {
         launch_k(pdl, t.mac.fn, dim3(t.n_split, t.tiles, count), dim3(kMacThreads), t.mac.smem, st, ma);
     }
@@ -1042,7 +1045,7 @@ int ca_destroy(ca_engine *e)
     for (auto &row : e->ptm_ev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
     if (e->pm_tail) cudaEventDestroy(e->pm_tail);
     for (auto &ev : e->ptinv_ev) if (ev) cudaEventDestroy(ev);
-    for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); }
+    for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); cudaFree(t.workctr); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw); cudaFree(e->d_vpool);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
@@ -1251,6 +1254,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
             CA_CUDA(cudaMemsetAsync(t.Ypart2, 0, yp_bytes, e->stream));
             e->device_bytes += yp_bytes;
         }
+        CA_CUDA(cudaMalloc(&t.workctr, 2 * sizeof(uint32_t)));
+        CA_CUDA(cudaMemsetAsync(t.workctr, 0, 2 * sizeof(uint32_t), e->stream));
         // twiddles, fp64 -> fp32: [W_S^n, n < S | W_2S^k, k < S]
         std::vector<float2> tw(2 * (size_t)t.S);
         for (uint32_t n = 0; n < t.S; n++) {

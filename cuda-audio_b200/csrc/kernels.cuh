@@ -506,6 +506,9 @@ struct MacArgs {
     float2 *gather;
     unsigned long long *gflag;
     uint32_t *gcount;
+    // persistent schedule: [0] next work item to hand out (beyond the first gridDim.x, which are static),
+    // [1] CTAs that have finished; the last one to finish zeroes both for the next launch of this tier
+    uint32_t *work_ctr;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
@@ -771,7 +774,10 @@ struct MacStageMeta {
     uint32_t boundary;  // first row of input 1
     uint32_t last;      // 1: last stage of the item
     float pan[4];       // [input][output] wet pan gains
+    uint32_t item;      // work item (instance * tiles + tile) this stage belongs to; kMacNoItem ends the CTA's list
+    uint32_t pad[3];
 };
+constexpr uint32_t kMacNoItem = 0xffffffffu;
 
 template <int BT, int NOUT, int KC, int NSTAGE>
 struct MacPCfg {
@@ -840,10 +846,19 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
             }
             return r;
         };
+        // Work items are handed out dynamically (an atomic counter; the first gridDim.x statically): CTAs on SMs
+        // that happen to stream faster take more items, so the launch has no tail of a few late CTAs
+        // (ncu r02: 7-10 % of the SM cycles of a MAC launch were idle with the static stride).
+        auto grab = [&]() {
+            uint32_t v = 0;
+            if (lane == 0) v = gridDim.x + atomicAdd(a.work_ctr, 1u);
+            return __shfl_sync(kFull, v, 0);
+        };
         uint32_t it = 0;
-        Raw cur = load_raw(blockIdx.x), nxt = cur;
-        for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
-            if (j + gridDim.x < n_work) nxt = load_raw(j + gridDim.x);
+        uint32_t j = blockIdx.x, jn = j < n_work ? grab() : kMacNoItem;
+        Raw cur = load_raw(min(j, n_work - 1u)), nxt = cur;
+        for (; j < n_work; j = jn, jn = (jn < n_work) ? grab() : kMacNoItem) {
+            if (jn < n_work) nxt = load_raw(jn);
             const uint32_t tile = j & t_mask, inst = a.inst0 + (j >> t_log) * a.inst_stride;
             const uint32_t phase = inst & m_mask;
             const unsigned long long n_fire = (tend + phase) >> m_log;
@@ -881,6 +896,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                     MacStageMeta &m = meta[st];
                     m.rows = rows; m.rho0 = i * KC; m.boundary = boundary; m.last = (i + 1 == n_iter) ? 1u : 0u;
                     m.pan[0] = pan[0]; m.pan[1] = pan[1]; m.pan[2] = pan[2]; m.pan[3] = pan[3];
+                    m.item = j;
                     if (rows) mbar_arrive_expect_tx(&full[st], rows * NARR * Cfg::ARR_BYTES);
                     else mbar_arrive(&full[st]);
                 }
@@ -906,6 +922,15 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
             }
             cur = nxt;
         }
+        {   // end of this CTA's list: one empty stage tells the consumers
+            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+            if (it >= NSTAGE) mbar_wait(&empty[st], ph ^ 1u);
+            if (lane == 0) {
+                MacStageMeta &m = meta[st];
+                m.rows = 0u; m.rho0 = 0u; m.boundary = 0u; m.last = 1u; m.item = kMacNoItem;
+                mbar_arrive(&full[st]);
+            }
+        }
     } else {
         // ===== consumers: thread (g, q) owns bins (2q, 2q+1).  Row groups g take every G-th row and their
         // sums are added through shared memory at the end of the item -- except when there are as many
@@ -917,9 +942,9 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
         const int q = tid % LR, g = tid / LR;
         const int r_first = OSPLIT ? 0 : g, o_base = OSPLIT ? g : 0;
         uint32_t it = 0;
-        for (uint32_t j = blockIdx.x; j < n_work; j += gridDim.x) {
-            const uint32_t tile = j & t_mask, z = j >> t_log;
-            const bool bin0 = (q == 0) && (tile == 0);
+        for (;;) {
+            uint32_t tile = 0, z = 0;
+            bool bin0 = false, first = true, done = false;
             float4 acc[NO], y[NO];
             float2 e0[NO], y0[NO];
 #pragma unroll
@@ -937,6 +962,13 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                 const MacStageMeta &m = meta[st];
                 const uint32_t rows = m.rows, rho0 = m.rho0, boundary = m.boundary;
                 last = m.last;
+                if (first) {  // first stage of an item: which one it is
+                    first = false;
+                    const uint32_t j = m.item;
+                    done = j == kMacNoItem;
+                    tile = j & t_mask; z = j >> t_log;
+                    bin0 = (q == 0) && (tile == 0);
+                }
 #pragma unroll
                 for (int o = 0; o < NO; o++) { pan0[o] = m.pan[o_base + o]; pan1[o] = m.pan[NOUT + o_base + o]; }
 #pragma unroll
@@ -974,6 +1006,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                 if (lane == 0) mbar_arrive(&empty[st]);
                 it++;
             } while (!last);
+            if (done) break;
 #pragma unroll
             for (int o = 0; o < NO; o++) {  // fold the last input's sum with its pan (conv.cu:392-401)
                 const float pan = second ? pan1[o] : pan0[o];
@@ -1022,6 +1055,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
         }
     }
     __syncthreads();  // the producer warp stays resident until every copy it issued has been consumed
+    if (tid == 0 && atomicAdd(a.work_ctr + 1, 1u) + 1u == gridDim.x) { a.work_ctr[0] = 0u; a.work_ctr[1] = 0u; }  // nobody hands out items any more
 }
 
 // ------------------------------------------------------------------------------------------
