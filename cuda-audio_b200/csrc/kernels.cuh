@@ -849,16 +849,23 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
         // Work items are handed out dynamically (an atomic counter; the first gridDim.x statically): CTAs on SMs
         // that happen to stream faster take more items, so the launch has no tail of a few late CTAs
         // (ncu r02: 7-10 % of the SM cycles of a MAC launch were idle with the static stride).
-        auto grab = [&]() {
-            uint32_t v = 0;
-            if (lane == 0) v = gridDim.x + atomicAdd(a.work_ctr, 1u);
-            return __shfl_sync(kFull, v, 0);
-        };
+        // The atomic that hands out the item AFTER the next one is issued at the top of an item and its result is
+        // first touched when the item has been streamed, so its round trip to L2 never sits on the critical path.
+        // With few items per CTA (work_ctr == nullptr) the static stride j, j + gridDim.x, ... is kept: every CTA
+        // gets the same count and the launch is ~3 % faster than with the counter (measured r02, 7 items per CTA).
+        const bool dyn = a.work_ctr != nullptr;
         uint32_t it = 0;
-        uint32_t j = blockIdx.x, jn = j < n_work ? grab() : kMacNoItem;
+        uint32_t j = blockIdx.x;
+        uint32_t grabbed = j + gridDim.x;
+        if (dyn && lane == 0) grabbed = gridDim.x + atomicAdd(a.work_ctr, 1u);
         Raw cur = load_raw(min(j, n_work - 1u)), nxt = cur;
-        for (; j < n_work; j = jn, jn = (jn < n_work) ? grab() : kMacNoItem) {
-            if (jn < n_work) nxt = load_raw(jn);
+        uint32_t jn = __shfl_sync(kFull, grabbed, 0);
+        while (j < n_work) {
+            if (jn < n_work) {
+                nxt = load_raw(jn);
+                grabbed = jn + gridDim.x;
+                if (dyn && lane == 0) grabbed = gridDim.x + atomicAdd(a.work_ctr, 1u);
+            }
             const uint32_t tile = j & t_mask, inst = a.inst0 + (j >> t_log) * a.inst_stride;
             const uint32_t phase = inst & m_mask;
             const unsigned long long n_fire = (tend + phase) >> m_log;
@@ -921,6 +928,8 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
                 }
             }
             cur = nxt;
+            j = jn;
+            jn = (jn < n_work) ? __shfl_sync(kFull, grabbed, 0) : kMacNoItem;
         }
         {   // end of this CTA's list: one empty stage tells the consumers
             const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
@@ -1055,7 +1064,7 @@ __global__ void __launch_bounds__(kMacThreads, 4) k_mac_p(const MacArgs a, const
         }
     }
     __syncthreads();  // the producer warp stays resident until every copy it issued has been consumed
-    if (tid == 0 && atomicAdd(a.work_ctr + 1, 1u) + 1u == gridDim.x) { a.work_ctr[0] = 0u; a.work_ctr[1] = 0u; }  // nobody hands out items any more
+    if (a.work_ctr && tid == 0 && atomicAdd(a.work_ctr + 1, 1u) + 1u == gridDim.x) { a.work_ctr[0] = 0u; a.work_ctr[1] = 0u; }  // nobody hands out items any more
 }
 
 // ------------------------------------------------------------------------------------------
