@@ -923,7 +923,7 @@ def main():
                     help="channels: the headline (independent instances, no collective); irsplit: configs[4], one long IR split across the GPUs")
     ap.add_argument("--irsplit-seconds", type=float, default=60.0)
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU in the throughput run (0 = as many as the GPU's HBM holds)")
-    ap.add_argument("--reserve-gb", type=float, default=14.0, help="HBM left free when --instances 0 sizes the batch")
+    ap.add_argument("--reserve-gb", type=float, default=11.0, help="HBM left free when --instances 0 sizes the batch")
     ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
     ap.add_argument("--uniform-instances", type=int, default=2048)
     ap.add_argument("--profile-instances", type=int, default=4096)
