@@ -565,8 +565,11 @@ def run_ours(args):
         lat = {}
         # non_uniform: long tiers with two periods of slack on a low-priority stream (CA_FLAG_ASYNC_TIERS);
         # non_uniform_sync_tiers: the same partitioning with the tiers queued in front of the next period
-        for name, tr, fl in (("non_uniform", "auto", ca.FLAG_ASYNC_TIERS), ("non_uniform_sync_tiers", "auto", 0), ("uniform", None, 0)):
-            e1 = build_engine(ca, torch, dev, 1, ca.FLAG_GRAPH | fl, tiers=tr)
+        # uniform_persistent_kernel: no launches at all -- one resident cooperative kernel polls a mailbox in mapped
+        # host memory (CA_FLAG_PERSISTENT, SURVEY 7.5 launch mode (b)); the others replay one CUDA graph per period
+        for name, tr, fl in (("non_uniform", "auto", ca.FLAG_GRAPH | ca.FLAG_ASYNC_TIERS), ("non_uniform_sync_tiers", "auto", ca.FLAG_GRAPH),
+                             ("uniform", None, ca.FLAG_GRAPH), ("uniform_persistent_kernel", None, ca.FLAG_PERSISTENT)):
+            e1 = build_engine(ca, torch, dev, 1, fl, tiers=tr)
             a, b = ca.PinnedArray((1, 2, B)), ca.PinnedArray((1, 2, B))
             a.array[...] = 0.05
             for _ in range(STEADY + 200):

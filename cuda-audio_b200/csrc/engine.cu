@@ -6,6 +6,7 @@
 #include "../../include/cuda_audio_b200.h"
 #include "kernels.cuh"
 #include "kernels_rows.cuh"
+#include "kernels_persist.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -279,6 +280,14 @@ struct ca_engine {
         int *gerr = nullptr;
     } link;
     float2 *d_rowtw = nullptr;  // [W_256^n | W_512^k]: twiddles of the 256-point row FFT
+    // CA_FLAG_PERSISTENT (kernels_persist.cuh)
+    bool persistent = false, p_running = false;
+    PersistBox *pbox = nullptr;            // mapped pinned host memory
+    unsigned long long *d_go = nullptr;
+    unsigned int *d_arrive = nullptr;
+    InParamDev *d_ppar = nullptr;
+    float2 *d_pY = nullptr;
+    uint32_t p_ctas = 0, p_gen = 0;
     uint32_t *d_vpool = nullptr;  // bitmap of the shared cross-fade voice entries
     uint32_t n_voices = 0, n_extra = 0;  // voice pool: n_items homes + n_extra shared entries
     bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
@@ -944,6 +953,93 @@ int prewarm_graphs(ca_engine *e)
     return CA_OK;
 }
 
+// ---- CA_FLAG_PERSISTENT: the resident kernel and its mailbox ----
+typedef void (*persist_fn)(const PersistArgs);
+persist_fn persist_pick(uint32_t R, uint32_t n_out)
+{
+    switch (R) {
+    case 1: return n_out == 1 ? k_persist<1, 1> : k_persist<1, 2>;
+    case 2: return n_out == 1 ? k_persist<2, 1> : k_persist<2, 2>;
+    case 4: return n_out == 1 ? k_persist<4, 1> : k_persist<4, 2>;
+    case 8: return n_out == 1 ? k_persist<8, 1> : k_persist<8, 2>;
+    default: return nullptr;
+    }
+}
+
+int persist_stop(ca_engine *e)
+{
+    if (!e->persistent || !e->p_running) return CA_OK;
+    e->pbox->seq_in = kPersistExit;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    CA_CUDA(cudaStreamSynchronize(e->stream));
+    e->p_running = false;
+    e->pbox->seq_in = e->t_host;
+    return CA_OK;
+}
+
+int persist_launch(ca_engine *e)
+{
+    const Tier &t0 = e->tiers[0];
+    e->p_gen++;
+    e->pbox->exited = 0;
+    e->pbox->seq_in = e->t_host;       // nothing to do yet
+    e->pbox->seq_out = e->t_host;
+    e->pbox->pad[0] = (unsigned int)(e->t_host & 0xffffffffu);
+    e->pbox->pad[1] = (unsigned int)(e->t_host >> 32);
+    CA_CUDA(cudaMemsetAsync(e->d_arrive, 0, sizeof(unsigned int), e->stream));
+    CA_CUDA(cudaMemcpyAsync(e->d_go, e->pbox->pad, sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));  // pinned source
+    PersistArgs pa{};
+    pa.box = e->pbox; pa.ring = e->d_ring; pa.X = t0.X; pa.H = t0.H; pa.Ypart = e->d_pY; pa.st = e->d_st; pa.par_dev = e->d_ppar;
+    pa.twM = t0.tw; pa.tw2M = t0.tw + e->B; pa.go = e->d_go; pa.arrive = e->d_arrive; pa.t0 = e->t_host;
+    pa.n_in = e->n_in; pa.n_out = e->n_out; pa.nv = e->nv; pa.Lring = t0.Lring; pa.P = t0.P; pa.ring_len = e->ring_len; pa.ring_out = e->ring_out;
+    pa.k_off = e->k_off; pa.raw_wet = (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u; pa.gen = e->p_gen; pa.n_items_alloc = e->n_inst * e->n_in;
+    pa.vp = voice_pool(e);
+    void *kargs[] = {&pa};
+    CA_CUDA(cudaLaunchCooperativeKernel((const void *)persist_pick(e->R, e->n_out), dim3(e->p_ctas), dim3(kPersistThreads), kargs, 0, e->stream));
+    e->p_running = true;
+    e->launches += 1;
+    return CA_OK;
+}
+
+// one period through the mailbox; in / out: host memory of any kind
+int process_persistent(ca_engine *e, const float *in, float *out)
+{
+    PersistBox *b = e->pbox;
+    drain_params(e);
+    e->par_dirty = false;
+    memcpy(b->par, e->par.data(), e->n_in * sizeof(InParamDev));
+    memcpy(b->in, in, (size_t)e->n_in * e->B * sizeof(float));
+    if (e->p_running && b->exited == e->p_gen) {  // the kernel left (idle): collect it
+        CA_CUDA(cudaStreamSynchronize(e->stream));
+        e->p_running = false;
+    }
+    if (!e->p_running) {
+        const int rc = persist_launch(e);
+        if (rc) return rc;
+    }
+    const unsigned long long want = e->t_host + 1ull;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    b->seq_in = want;
+    const double t0 = now_us();
+    for (unsigned spins = 0; b->seq_out < want; spins++) {
+        if ((spins & 0xfff) == 0xfff) {
+            if (b->exited == e->p_gen) {  // it left between our check and the signal: relaunch, the request stands
+                CA_CUDA(cudaStreamSynchronize(e->stream));
+                e->p_running = false;
+                const int rc = persist_launch(e);
+                if (rc) return rc;
+                b->seq_in = want;
+            }
+            if (now_us() - t0 > 4e6) { g_last_error = "persistent kernel does not answer"; return CA_ERR_CUDA; }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(out, b->out, (size_t)e->n_out * e->B * sizeof(float));
+    if (b->err) { g_last_error = "persistent kernel: grid barrier timed out"; return CA_ERR_CUDA; }
+    e->t_host = want;
+    return CA_OK;
+}
+
 void record_wall(ca_engine *e, double us)
 {
     e->wall[e->periods % e->wall.size()] = (float)us;
@@ -1023,6 +1119,7 @@ int ca_destroy(ca_engine *e)
 {
     if (!e) return CA_OK;
     cudaSetDevice(e->device);
+    persist_stop(e);
     if (e->s_mac) cudaStreamSynchronize(e->s_mac);
     if (e->s_def) cudaStreamSynchronize(e->s_def);
     for (auto &st : e->s_tier) if (st) cudaStreamSynchronize(st);
@@ -1052,6 +1149,8 @@ int ca_destroy(ca_engine *e)
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); cudaFree(t.workctr); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw); cudaFree(e->d_vpool);
+    cudaFree(e->d_go); cudaFree(e->d_arrive); cudaFree(e->d_ppar); cudaFree(e->d_pY);
+    if (e->pbox) cudaFreeHost(e->pbox);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -1341,6 +1440,25 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
             if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
         }
     }
+    if (cfg->flags & CA_FLAG_PERSISTENT) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        if (e->n_inst != 1 || e->tiers.size() != 1 || e->B > 256 || !coop || !persist_pick(e->R, e->n_out) ||
+            (cfg->flags & (CA_FLAG_GRAPH | CA_FLAG_PROFILE | CA_FLAG_ASYNC_TIERS))) {
+            g_last_error = "CA_FLAG_PERSISTENT: one instance, uniform partitioning, period <= 256, no graph / profile / async-tier flags";
+            return CA_ERR_UNSUPPORTED;
+        }
+        e->persistent = true;
+        const uint32_t rows = e->tiers[0].P * e->n_in;
+        e->p_ctas = (uint32_t)std::max(1, std::min<int>(sms - 4, (int)(rows / 12)));  // <= 8-row batches x 1..2 per CTA; a few SMs stay free
+        CA_CUDA(cudaHostAlloc(&e->pbox, sizeof(PersistBox), cudaHostAllocMapped));
+        memset((void *)e->pbox, 0, sizeof(PersistBox));
+        CA_CUDA(cudaMalloc(&e->d_go, sizeof(unsigned long long)));
+        CA_CUDA(cudaMalloc(&e->d_arrive, sizeof(unsigned int)));
+        CA_CUDA(cudaMalloc(&e->d_ppar, 2 * sizeof(InParamDev)));
+        CA_CUDA(cudaMemsetAsync(e->d_ppar, 0, 2 * sizeof(InParamDev), e->stream));
+        CA_CUDA(cudaMalloc(&e->d_pY, (size_t)e->p_ctas * e->n_out * e->B * sizeof(float2)));
+    }
     CA_CUDA(cudaStreamSynchronize(e->stream));
     return prewarm_graphs(e);
 }
@@ -1376,6 +1494,10 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
     // caller-produced device data (e.g. WavFile::buffer, filled by copies/kernels on the legacy or
     // another stream) must be complete before this engine's non-blocking stream reads it;
     // the reference's prepare() does the same (conv.cu:237)
+    {
+        const int rc = persist_stop(e);  // the resident kernel reads the IR bank: it is relaunched by the next period
+        if (rc) return rc;
+    }
     if (foreign) CA_CUDA(cudaDeviceSynchronize());
     {
         const int rc = drain_all(e);  // lane M / the asynchronous tiers may still read the IR bank
@@ -1481,6 +1603,7 @@ int ca_set_active(ca_engine *e, uint32_t n)
 {
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
     if (n == e->n_active) return CA_OK;
+    if (e->persistent) return CA_ERR_UNSUPPORTED;
     const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
@@ -1504,6 +1627,7 @@ int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nf
 {
     if (!e || !d_in || !d_out) return CA_ERR_INVALID;
     if (nframes != e->B) return CA_ERR_PERIOD;
+    if (e->persistent) { g_last_error = "CA_FLAG_PERSISTENT engines are driven through ca_process"; return CA_ERR_UNSUPPORTED; }
     const double t0 = now_us();
     int rc;
     if (use_pipeline(e)) {
@@ -1524,6 +1648,12 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     if (!e || !in || !out) return CA_ERR_INVALID;  // the reference silently returns on null ports (conv.cu:297)
     if (nframes != e->B) return CA_ERR_PERIOD;
     const double t0 = now_us();
+    if (e->persistent) {
+        const int rc = process_persistent(e, in, out);
+        if (rc) return rc;
+        record_wall(e, now_us() - t0);
+        return CA_OK;
+    }
     const size_t in_stride = (size_t)e->n_in * e->B, out_stride = (size_t)e->n_out * e->B;  // floats per instance
     const size_t in_bytes = e->n_active * in_stride * sizeof(float), out_bytes = e->n_active * out_stride * sizeof(float);
     const float *src = in;
@@ -1581,6 +1711,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
 int ca_sync(ca_engine *e)
 {
     if (!e) return CA_ERR_INVALID;
+    if (e->persistent) return CA_OK;  // ca_process is synchronous; the resident kernel keeps the stream busy by design
     const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));

@@ -1,0 +1,360 @@
+// kernels_persist.cuh -- CA_FLAG_PERSISTENT: ONE resident cooperative kernel processes every period of a
+// single uniform-partitioned instance; the host talks to it through a mailbox in mapped pinned memory
+// instead of launching anything (SURVEY 7.5 "per-period launch (b)": lowest latency, monopolises some SMs).
+//
+//   host   : writes the period's parameters + input block into the mailbox, then seq_in = t + 1
+//   CTA 0  : polls seq_in over PCIe; forward R2C of every input (voice step, predelay ring, FDL slot)
+//   grid   : released by a device flag (`go`); every CTA multiply-accumulates its slice of the (stream,
+//            partition) row list straight out of L2 (9.2 MB for a 4 s IR: L2-resident), partial spectrum out
+//   CTA 0  : waits for the arrival counter, sums the partials in fixed order, C2R + overlap discard + clamp +
+//            dry mix, stores the block into the mailbox, __threadfence_system, seq_out = t + 1
+//   host   : spins on seq_out
+// Every wait is bounded: the kernel leaves by itself after ~1 s without a new period (the next ca_process
+// relaunches it), on an exit request (IR load, destroy, ...), or when a grid barrier times out (`err`).
+// Everything the kernel itself modifies in global memory is read back with ld.global.cg: L1 lines of a
+// resident kernel are never invalidated by a launch boundary.
+// Same arithmetic as k_forward / k_mac / k_inverse (conv.cu:287-466 replaced), checked against them and fp64.
+#pragma once
+#include "kernels.cuh"
+
+namespace ca {
+
+constexpr unsigned long long kPersistExit = ~0ull;
+constexpr int kPersistThreads = 256;
+
+struct PersistBox {
+    volatile unsigned long long seq_in;   // host -> device: period count that may be processed; kPersistExit: leave
+    volatile unsigned long long seq_out;  // device -> host: periods completed
+    volatile unsigned int exited;         // device -> host: launch generation that has returned
+    volatile int err;                     // device -> host: 1 = a grid barrier timed out
+    unsigned int pad[10];
+    InParamDev par[2];                    // this period's parameters (input 0, 1)
+    float in[2 * 256];                    // [n_in][B]
+    float out[2 * 256];                   // [n_out][B]
+};
+
+struct PersistArgs {
+    PersistBox *box;
+    float *ring;           // [voice entry][ring_len]
+    float2 *X;             // FDL [voice entry][Lring][B]
+    const float2 *H;       // [slot][n_out][P][B]
+    float2 *Ypart;         // [CTA][n_out][B]
+    ItemState *st;         // [2][n_items_alloc]
+    InParamDev *par_dev;   // [n_in]: CTA 0 republishes the period's parameters for the other CTAs (pan gains)
+    const float2 *twM, *tw2M;
+    unsigned long long *go;  // device flag: period count the grid may work on; kPersistExit: leave
+    unsigned int *arrive;    // device counter, monotonic since launch
+    unsigned long long t0;   // periods completed at launch
+    uint32_t n_in, n_out, nv, Lring, P, ring_len, ring_out, k_off, raw_wet, gen, n_items_alloc;
+    VoicePool vp;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// struct copy through L2 (see the header: nothing invalidates this kernel's L1)
+template <class T>
+__device__ __forceinline__ T ld_cg_struct(const T *p)
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized struct");
+    T v;
+    const unsigned int *src = reinterpret_cast<const unsigned int *>(p);
+    unsigned int *dst = reinterpret_cast<unsigned int *>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); i++) dst[i] = __ldcg(src + i);
+    return v;
+}
+
+constexpr long long kPersistIdleCycles = 1ll << 31;     // ~1.1 s at 1.965 GHz without a new period: leave
+constexpr long long kPersistBarrierCycles = 1ll << 30;  // a grid barrier that takes this long is broken
+
+template <int R, int NOUT>
+__global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArgs a)
+{
+    constexpr int B = 32 * R;
+    constexpr int G2 = kPersistThreads / B;  // row groups of the MAC phase (B = 256: 1)
+    static_assert(B <= kPersistThreads, "period <= 256");
+    __shared__ __align__(16) float s_in[2][B];          // CTA 0: this period's input (dry mix reads it again)
+    __shared__ __align__(16) float2 s_Y[NOUT][B];       // CTA 0: summed spectrum; every CTA: cross-group reduction
+    __shared__ float2 s_red[G2 > 1 ? (G2 - 1) * NOUT * B : 1];
+    __shared__ InParamDev s_par[2];
+    __shared__ uint32_t s_rowstart[kMaxStreams + 1], s_slot[kMaxStreams], s_entry[kMaxStreams];
+    __shared__ float s_panwet[2];
+    __shared__ int s_cmd;  // 0 = run the period, 1 = leave
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ns = a.n_in * a.nv;
+    const uint32_t nctas = gridDim.x;
+    PersistBox *box = a.box;
+    WarpFft<R> f;
+    f.init(a.twM);
+
+    for (unsigned long long t = a.t0;; t++) {
+        // ---------------- wait for the host / for CTA 0 ----------------
+        if (blockIdx.x == 0) {
+            if (tid == 0) {
+                int cmd = 0;
+                const long long c0 = clock64();
+                for (;;) {
+                    const unsigned long long s = ld_acquire_sys(const_cast<const unsigned long long *>(&box->seq_in));
+                    if (s == kPersistExit) { cmd = 1; break; }
+                    if (s >= t + 1ull) break;
+                    if (clock64() - c0 > kPersistIdleCycles) { cmd = 1; break; }
+                }
+                s_cmd = cmd;
+            }
+            __syncthreads();
+            if (s_cmd == 0) {
+                // parameters + input out of the mailbox (mapped host memory: read once, kept in shared memory)
+                if (tid < (int)(a.n_in * (sizeof(InParamDev) / 4))) reinterpret_cast<unsigned int *>(s_par)[tid] = __ldcv(reinterpret_cast<const unsigned int *>(box->par) + tid);
+                for (int i = tid; i < (int)a.n_in * B; i += kPersistThreads) s_in[i / B][i % B] = __ldcv(&box->in[i]);
+                __syncthreads();
+                if (tid < (int)(a.n_in * (sizeof(InParamDev) / 4))) reinterpret_cast<unsigned int *>(a.par_dev)[tid] = reinterpret_cast<const unsigned int *>(s_par)[tid];
+                // ---- forward: warp i = input i (same steps as k_forward<R>) ----
+                if ((uint32_t)warp < a.n_in) {
+                    const uint32_t item = warp;
+                    const InParamDev p = s_par[item];
+                    const uint32_t pd = s_par[0].predelay;  // input 0's, conv.cu:412,415
+                    const ItemState old = ld_cg_struct(&a.st[(t & 1ull) * a.n_items_alloc + item]);
+                    ItemState s = step_item_state(old, p, t, (int)a.nv, a.ring_out);
+                    if (lane == 0) voice_storage_update(s, old.active, item, (int)a.nv, a.vp);
+                    s.active = __shfl_sync(kFull, s.active, 0);
+                    s.fresh = __shfl_sync(kFull, s.fresh, 0);
+#pragma unroll
+                    for (int v = 0; v < kMaxVoices; v++) s.pool[v] = __shfl_sync(kFull, s.pool[v], 0);
+                    if (lane == 0) a.st[((t + 1ull) & 1ull) * a.n_items_alloc + item] = s;
+                    const uint32_t mask = a.ring_len - 1;
+                    const uint32_t base = (uint32_t)((t * (unsigned long long)B) & mask);
+                    const uint32_t prev = (base - B) & mask;
+                    const uint32_t off = ((lane < 16) ? prev : base) + 2 * R * (lane & 15);
+                    const uint32_t slot = (a.Lring - 1u) - (uint32_t)((t + 1ull) % a.Lring);
+#pragma unroll 1
+                    for (uint32_t v = 0; v < a.nv; v++) {
+                        if (!((s.active >> v) & 1u)) continue;
+                        float cv = 0.f;
+#pragma unroll
+                        for (int q = 0; q < kMaxVoices; q++) cv = (q == (int)v) ? s.c[q] : cv;
+                        const float gain = cv * p.level;
+                        const uint32_t entry = voice_entry(s, v);
+                        float *ring = a.ring + (size_t)entry * a.ring_len;
+                        if ((s.fresh >> v) & 1u) {
+                            for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < R; j++) ring[(base + kMaxPredelay + lane + 32 * j) & mask] = 0.f;
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < R; j++) {  // the whole response of this block is delayed by pd samples (conv.cu:97)
+                            const int n = lane + 32 * j;
+                            const uint32_t idx = (base + pd + n) & mask;
+                            ring[idx] = __ldcg(ring + idx) + gain * s_in[item][n];
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        float2 z[R];
+#pragma unroll
+                        for (int j = 0; j < R; j++) z[j] = __ldcg(reinterpret_cast<const float2 *>(ring + off) + j);
+                        f.forward(z);
+                        f.split_r2c(z, a.tw2M);
+                        float2 *dst = a.X + ((size_t)entry * a.Lring + slot) * B;
+#pragma unroll
+                        for (int d = 0; d < R; d++) dst[f.c + 32 * d] = z[d];
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { __threadfence(); st_release_gpu(a.go, s_cmd ? kPersistExit : t + 1ull); }
+        } else {
+            if (tid == 0) {
+                int cmd = 0;
+                const long long c0 = clock64();
+                for (;;) {
+                    const unsigned long long g = ld_acquire_gpu(a.go);
+                    if (g == kPersistExit) { cmd = 1; break; }
+                    if (g >= t + 1ull) break;
+                    if (clock64() - c0 > 2 * kPersistIdleCycles) { cmd = 1; break; }
+                }
+                s_cmd = cmd;
+            }
+            __syncthreads();
+        }
+        if (s_cmd) break;
+
+        // ---------------- FDL MAC: this CTA's slice of the row list ----------------
+        if (warp == 0) {
+            uint32_t nk = 0, slot = 0, entry = 0;
+            if ((uint32_t)lane < ns) {
+                const uint32_t i = lane / a.nv, v = lane % a.nv;
+                const ItemState st = ld_cg_struct(&a.st[((t + 1ull) & 1ull) * a.n_items_alloc + i]);
+                if ((st.active >> v) & 1u) {
+                    unsigned long long start = 0;
+#pragma unroll
+                    for (int q = 0; q < kMaxVoices; q++)
+                        if (q == (int)v) { start = st.start[q]; slot = st.slot[q]; entry = st.pool[q] - 1u; }
+                    const long long cnt = (long long)t - (long long)start + 1 - (long long)a.k_off;  // k_mac with m = 1
+                    nk = (uint32_t)max(0ll, min((long long)a.P, cnt));
+                }
+            }
+            uint32_t incl = nk;
+#pragma unroll
+            for (int d = 1; d < kMaxStreams; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const uint32_t total_rows = __shfl_sync(kFull, incl, kMaxStreams - 1);
+            if (lane < kMaxStreams) { s_rowstart[lane] = incl - nk; s_slot[lane] = slot; s_entry[lane] = entry; }
+            else if (lane == kMaxStreams) s_rowstart[kMaxStreams] = total_rows;
+        } else if (warp == 1 && (uint32_t)lane < a.n_in) {
+            s_panwet[lane] = __ldcg(&a.par_dev[lane].panWet);
+        }
+        __syncthreads();
+        {
+            const uint32_t total = s_rowstart[kMaxStreams];
+            const uint32_t boundary = a.n_in > 1 ? s_rowstart[a.nv] : total;  // first row of input 1
+            uint32_t rps = (total + nctas - 1) / nctas;
+            rps = ((rps + G2 - 1) / G2) * G2;
+            const uint32_t r_begin = min(total, blockIdx.x * rps), r_end = min(total, r_begin + rps);
+            const int q = tid % B, g = tid / B;
+            const uint32_t head = (a.Lring - 1u) - (uint32_t)((t + 1ull) % a.Lring);
+            float2 acc[2][NOUT];
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) acc[i][o] = make_float2(0.f, 0.f);
+            // rows in batches of UN: every load of a batch is in flight before the first product (the slice is
+            // L2-resident, so the loop is a chain of ~700-cycle round trips otherwise)
+            constexpr int UN = 8;
+            for (uint32_t rho0 = r_begin + g; rho0 < r_end; rho0 += UN * G2) {
+                float2 xs[UN], hs[UN][NOUT];
+                int in1[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const uint32_t rho = rho0 + u * G2;
+                    xs[u] = make_float2(0.f, 0.f);
+                    in1[u] = 0;
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) hs[u][o] = make_float2(0.f, 0.f);
+                    if (rho < r_end) {
+                        uint32_t s = 0;
+#pragma unroll
+                        for (int qq = 1; qq < kMaxStreams; qq++) s += (rho >= s_rowstart[qq]) ? 1u : 0u;
+                        const uint32_t k = rho - s_rowstart[s];
+                        const uint32_t pos = (head + a.k_off + k) % a.Lring;
+                        xs[u] = __ldcg(a.X + ((size_t)s_entry[s] * a.Lring + pos) * B + q);
+#pragma unroll
+                        for (int o = 0; o < NOUT; o++) hs[u][o] = __ldg(a.H + (((size_t)s_slot[s] * NOUT + o) * a.P + k) * B + q);
+                        in1[u] = rho >= boundary ? 1 : 0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const float2 x = xs[u];
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) {
+                        const float2 h = hs[u][o];
+                        float2 r;
+                        if (q == 0) r = make_float2(x.x * h.x, x.y * h.y);  // bin 0 = (DC, Nyquist): two real products
+                        else r = make_float2(x.x * h.x - x.y * h.y, x.x * h.y + x.y * h.x);
+                        if (in1[u] == 0) { acc[0][o].x += r.x; acc[0][o].y += r.y; }
+                        else { acc[1][o].x += r.x; acc[1][o].y += r.y; }
+                    }
+                }
+            }
+            float2 y[NOUT];
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) {  // pan per (input, output), conv.cu:392-401
+                const float p0 = pan_gain(s_panwet[0], o, NOUT);
+                const float p1 = pan_gain(s_panwet[a.n_in - 1], o, NOUT);
+                y[o] = make_float2(p0 * acc[0][o].x + p1 * acc[1][o].x, p0 * acc[0][o].y + p1 * acc[1][o].y);
+            }
+            if (G2 > 1) {
+                if (g > 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++) s_red[((g - 1) * NOUT + o) * B + q] = y[o];
+                }
+                __syncthreads();
+                if (g == 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; o++)
+                        for (int gg = 1; gg < G2; gg++) { const float2 v = s_red[((gg - 1) * NOUT + o) * B + q]; y[o].x += v.x; y[o].y += v.y; }
+                }
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) a.Ypart[((size_t)blockIdx.x * NOUT + o) * B + q] = y[o];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(a.arrive, 1u);
+
+        // ---------------- CTA 0: sum, inverse, mix, publish ----------------
+        if (blockIdx.x == 0) {
+            if (tid == 0) {
+                const unsigned int want = (unsigned int)((t - a.t0 + 1ull) * nctas);
+                const long long c0 = clock64();
+                while ((int)(ld_acquire_gpu_u32(a.arrive) - want) < 0) {
+                    if (clock64() - c0 > kPersistBarrierCycles) { box->err = 1; break; }
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < NOUT * B; idx += kPersistThreads) {
+                float2 sum = make_float2(0.f, 0.f);
+#pragma unroll 8
+                for (uint32_t c = 0; c < nctas; c++) { const float2 v = __ldcg(a.Ypart + (size_t)c * NOUT * B + idx); sum.x += v.x; sum.y += v.y; }
+                s_Y[idx / B][idx % B] = sum;
+            }
+            __syncthreads();
+            if (warp < NOUT) {
+                const int o = warp;
+                float2 v[R];
+#pragma unroll
+                for (int d = 0; d < R; d++) v[d] = s_Y[o][f.c + 32 * d];
+                f.split_c2r(v, a.tw2M);
+                f.inverse(v);
+                if (lane >= 16) {  // overlap discard: time samples [B, 2B) live in lanes 16..31
+                    const bool raw = a.raw_wet != 0;
+                    float dg0 = 0.f, dg1 = 0.f;
+                    if (!raw) {  // dry * panDry * level, conv.cu:418-427
+                        const InParamDev p0 = s_par[0], p1 = s_par[a.n_in - 1];
+                        dg0 = p0.dry * pan_gain(p0.panDry, o, NOUT) * p0.level;
+                        dg1 = a.n_in > 1 ? p1.dry * pan_gain(p1.panDry, o, NOUT) * p1.level : 0.f;
+                    }
+                    const int n0 = 2 * R * (lane & 15);
+#pragma unroll
+                    for (int j = 0; j < R; j++) {
+                        const float w0 = raw ? v[j].x : fminf(fmaxf(v[j].x, -1.0f), 1.0f);  // conv.cu:98
+                        const float w1 = raw ? v[j].y : fminf(fmaxf(v[j].y, -1.0f), 1.0f);
+                        const int n = n0 + 2 * j;
+                        box->out[o * B + n] = fmaf(dg0, s_in[0][n], fmaf(dg1, s_in[a.n_in - 1][n], w0));
+                        box->out[o * B + n + 1] = fmaf(dg0, s_in[0][n + 1], fmaf(dg1, s_in[a.n_in - 1][n + 1], w1));
+                    }
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) st_release_sys(const_cast<unsigned long long *>(&box->seq_out), t + 1ull);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        __threadfence_system();
+        box->exited = a.gen;
+    }
+}
+
+}  // namespace ca

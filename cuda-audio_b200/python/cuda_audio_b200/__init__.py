@@ -20,6 +20,7 @@ CA_MAX_TIERS = 4
 FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 4, 8, 16
 FLAG_ASYNC_TIERS = 32
 FLAG_LEGACY_FFT = 64
+FLAG_PERSISTENT = 128
 SCHED_MAC_PERSISTENT, SCHED_MAC_PER_ITEM, SCHED_FUSED_TIER0, SCHED_NO_FUSED_TIER0, SCHED_PIPELINED, SCHED_NO_PDL = 1, 2, 4, 8, 16, 32
 
 EXPORTS = [

@@ -64,6 +64,11 @@ enum ca_flags {
                                    * plans it), so its result is due two periods after its block closes and
                                    * the tier work runs on a low-priority stream BESIDE the next period's
                                    * output path instead of in front of it (flat p99) */
+    CA_FLAG_PERSISTENT = 1u << 7, /* latency schedule without launches: ONE resident cooperative kernel polls a
+                                   * mailbox in mapped host memory and processes every period of a single,
+                                   * uniformly partitioned instance (period <= 256); ca_process only writes the
+                                   * block + parameters and spins on the answer.  The kernel leaves by itself after
+                                   * ~1 s of silence and is relaunched by the next call.  ca_process only. */
     CA_FLAG_LEGACY_FFT = 1u << 6  /* A/B: transforms on the warp-shuffle / whole-transform-per-CTA FFT kernels
                                    * of round 1 instead of the row-FFT family (same layouts, same results
                                    * to fp32 rounding) */

@@ -517,3 +517,60 @@ def test_l2_persist_window_flag_is_bit_identical():
             return e.render(x[None])[0]
 
     assert np.array_equal(go(m.FLAG_GRAPH), go(m.FLAG_GRAPH | m.FLAG_L2_PERSIST))
+
+
+@pytest.mark.parametrize("B,n_in,n_out", [(256, 2, 2), (64, 2, 1), (128, 1, 2)])
+def test_persistent_kernel_mode_matches_graph_mode_and_fp64(B, n_in, n_out):
+    """CA_FLAG_PERSISTENT: one resident cooperative kernel + a mailbox in mapped host memory instead of launches.
+    Same audio as the launched pipeline (different MAC split => fp32 rounding only) and as fp64, through a
+    predelay, pans, an IR cross-fade, an IR load (stops and relaunches the kernel) and an idle gap long enough
+    for the kernel to leave by itself."""
+    import time
+    m = ca()
+    fs, L = 48000, B * 40 + 9
+    irs = make_irs(L, fs, n_in=2, n_out=2, seed0=3100)
+    extra = make_irs(L, fs, n_in=1, n_out=2, seed0=3200)[0]
+    nper = 160
+    x = np.stack([O.synth_audio(B * nper, 3300 + i) for i in range(n_in)])
+    pr = dict(wet=0.8, dry=0.3, level=0.9, panWet=0.25, panDry=-0.5)
+
+    def go(flags):
+        with m.Engine(period=B, max_ir_frames=L, n_in=n_in, n_out=n_out, n_ir_slots=3, flags=flags, max_voices=2) as e:
+            for i in range(2):
+                e.load_ir(i, irs[i][0], irs[i][1] if n_out == 2 else None)
+            for i in range(n_in):
+                e.set_params(0, i, select=i, predelay=77, **pr)
+                e.set_glide(0, i, pr["wet"])
+            out = np.zeros((n_out, B * nper), np.float32)
+            for t in range(nper):
+                if t == 50:
+                    e.load_ir(2, extra[0], extra[1] if n_out == 2 else None)
+                if t == 60:
+                    e.set_params(0, 0, select=2, predelay=77, vsteps=15, **pr)      # cross-fade input 0 to the new IR
+                if t == 100 and (flags & m.FLAG_PERSISTENT):
+                    time.sleep(1.6)                                                  # the kernel leaves after ~1.1 s of silence
+                out[:, t * B:(t + 1) * B] = e.process(x[None, :, t * B:(t + 1) * B])[0]
+            st = e.stats()
+            return out, st
+
+    yp, sp = go(m.FLAG_PERSISTENT)
+    yg, sg = go(m.FLAG_GRAPH)
+    assert sp.gpu_launches < 40 < sg.gpu_launches          # a handful of (re)launches instead of 3 per period
+    for o in range(n_out):
+        assert O.rel_l2(yp[o], yg[o]) < 2e-6, (o, O.rel_l2(yp[o], yg[o]))
+    # fp64 truth for the part before the switch (static parameters)
+    hs = [[irs[i][o] for o in range(n_out)] for i in range(n_in)]
+    truth = O.engine_truth(x[:, :60 * B], hs, [pr] * n_in, predelay=77)
+    for o in range(n_out):
+        assert O.rel_l2(yp[o, :60 * B], truth[o]) < 5e-6
+
+
+def test_persistent_kernel_mode_rejects_what_it_cannot_do():
+    m = ca()
+    for kw in (dict(n_instances=2), dict(tiers=[(64, 8), (512, 0)]), dict(period=512, max_ir_frames=4096), dict(flags_extra=m.FLAG_GRAPH)):
+        fl = m.FLAG_PERSISTENT | kw.pop("flags_extra", 0)
+        args = dict(period=64, max_ir_frames=64 * 8 + 512 * 3, flags=fl)
+        args.update(kw)
+        with pytest.raises(m.CaError) as ei:
+            m.Engine(**args)
+        assert ei.value.code == -5, kw
