@@ -286,7 +286,8 @@ struct ca_engine {
     unsigned long long *d_go = nullptr;
     unsigned int *d_arrive = nullptr;
     InParamDev *d_ppar = nullptr;
-    float2 *d_pY = nullptr;
+    float2 *d_pY = nullptr, *d_pYsum = nullptr;
+    bool p_stamp = false;
     uint32_t p_ctas = 0, p_gen = 0;
     uint32_t *d_vpool = nullptr;  // bitmap of the shared cross-fade voice entries
     uint32_t n_voices = 0, n_extra = 0;  // voice pool: n_items homes + n_extra shared entries
@@ -986,7 +987,7 @@ int persist_launch(ca_engine *e)
     e->pbox->seq_out = e->t_host;
     e->pbox->pad[0] = (unsigned int)(e->t_host & 0xffffffffu);
     e->pbox->pad[1] = (unsigned int)(e->t_host >> 32);
-    CA_CUDA(cudaMemsetAsync(e->d_arrive, 0, sizeof(unsigned int), e->stream));
+    CA_CUDA(cudaMemsetAsync(e->d_arrive, 0, 2 * sizeof(unsigned int), e->stream));
     CA_CUDA(cudaMemcpyAsync(e->d_go, e->pbox->pad, sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));  // pinned source
     PersistArgs pa{};
     pa.box = e->pbox; pa.ring = e->d_ring; pa.X = t0.X; pa.H = t0.H; pa.Ypart = e->d_pY; pa.st = e->d_st; pa.par_dev = e->d_ppar;
@@ -994,6 +995,7 @@ int persist_launch(ca_engine *e)
     pa.n_in = e->n_in; pa.n_out = e->n_out; pa.nv = e->nv; pa.Lring = t0.Lring; pa.P = t0.P; pa.ring_len = e->ring_len; pa.ring_out = e->ring_out;
     pa.k_off = e->k_off; pa.raw_wet = (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u; pa.gen = e->p_gen; pa.n_items_alloc = e->n_inst * e->n_in;
     pa.vp = voice_pool(e);
+    pa.Ysum = e->d_pYsum; pa.stamp = e->p_stamp ? 1u : 0u;
     void *kargs[] = {&pa};
     CA_CUDA(cudaLaunchCooperativeKernel((const void *)persist_pick(e->R, e->n_out), dim3(e->p_ctas), dim3(kPersistThreads), kargs, 0, e->stream));
     e->p_running = true;
@@ -1149,7 +1151,7 @@ int ca_destroy(ca_engine *e)
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); cudaFree(t.workctr); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw); cudaFree(e->d_vpool);
-    cudaFree(e->d_go); cudaFree(e->d_arrive); cudaFree(e->d_ppar); cudaFree(e->d_pY);
+    cudaFree(e->d_go); cudaFree(e->d_arrive); cudaFree(e->d_ppar); cudaFree(e->d_pY); cudaFree(e->d_pYsum);
     if (e->pbox) cudaFreeHost(e->pbox);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -1454,7 +1456,9 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         CA_CUDA(cudaHostAlloc(&e->pbox, sizeof(PersistBox), cudaHostAllocMapped));
         memset((void *)e->pbox, 0, sizeof(PersistBox));
         CA_CUDA(cudaMalloc(&e->d_go, sizeof(unsigned long long)));
-        CA_CUDA(cudaMalloc(&e->d_arrive, sizeof(unsigned int)));
+        CA_CUDA(cudaMalloc(&e->d_arrive, 2 * sizeof(unsigned int)));
+        CA_CUDA(cudaMalloc(&e->d_pYsum, (size_t)e->n_out * e->B * sizeof(float2)));
+        e->p_stamp = getenv("CA_PERSIST_STAMPS") != nullptr;  // diagnostics: phase timestamps (ca_persist_stamps)
         CA_CUDA(cudaMalloc(&e->d_ppar, 2 * sizeof(InParamDev)));
         CA_CUDA(cudaMemsetAsync(e->d_ppar, 0, 2 * sizeof(InParamDev), e->stream));
         CA_CUDA(cudaMalloc(&e->d_pY, (size_t)e->p_ctas * e->n_out * e->B * sizeof(float2)));
@@ -1811,6 +1815,13 @@ int ca_measure_read_gbs(int device, size_t bytes, int iters, double *gbs)
     *gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf); cudaFree(sink);
+    return CA_OK;
+}
+
+int ca_persist_stamps(ca_engine *e, uint64_t stamps_ns[8])
+{
+    if (!e || !stamps_ns || !e->persistent || !e->pbox) return CA_ERR_INVALID;
+    for (int i = 0; i < 8; i++) stamps_ns[i] = e->pbox->stamps[i];
     return CA_OK;
 }
 

@@ -28,6 +28,7 @@ struct PersistBox {
     volatile unsigned int exited;         // device -> host: launch generation that has returned
     volatile int err;                     // device -> host: 1 = a grid barrier timed out
     unsigned int pad[10];
+    unsigned long long stamps[8];         // device -> host: %globaltimer (ns) at the phase boundaries of the last period
     InParamDev par[2];                    // this period's parameters (input 0, 1)
     float in[2 * 256];                    // [n_in][B]
     float out[2 * 256];                   // [n_out][B]
@@ -43,7 +44,9 @@ struct PersistArgs {
     InParamDev *par_dev;   // [n_in]: CTA 0 republishes the period's parameters for the other CTAs (pan gains)
     const float2 *twM, *tw2M;
     unsigned long long *go;  // device flag: period count the grid may work on; kPersistExit: leave
-    unsigned int *arrive;    // device counter, monotonic since launch
+    unsigned int *arrive;    // device counters, monotonic since launch: [0] partial spectra written, [1] slices of the sum written
+    float2 *Ysum;            // [n_out][B]: the summed spectrum, every CTA writes its slice
+    uint32_t stamp;          // 1: record %globaltimer at the phase boundaries (diagnostics; the stores cost ~2 us)
     unsigned long long t0;   // periods completed at launch
     uint32_t n_in, n_out, nv, Lring, P, ring_len, ring_out, k_off, raw_wet, gen, n_items_alloc;
     VoicePool vp;
@@ -76,6 +79,13 @@ __device__ __forceinline__ T ld_cg_struct(const T *p)
     unsigned int *dst = reinterpret_cast<unsigned int *>(&v);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 4); i++) dst[i] = __ldcg(src + i);
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
     return v;
 }
 
@@ -116,6 +126,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArg
                     if (clock64() - c0 > kPersistIdleCycles) { cmd = 1; break; }
                 }
                 s_cmd = cmd;
+                if (a.stamp) box->stamps[0] = globaltimer_ns();
             }
             __syncthreads();
             if (s_cmd == 0) {
@@ -123,6 +134,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArg
                 if (tid < (int)(a.n_in * (sizeof(InParamDev) / 4))) reinterpret_cast<unsigned int *>(s_par)[tid] = __ldcv(reinterpret_cast<const unsigned int *>(box->par) + tid);
                 for (int i = tid; i < (int)a.n_in * B; i += kPersistThreads) s_in[i / B][i % B] = __ldcv(&box->in[i]);
                 __syncthreads();
+                if (tid == 0 && a.stamp) box->stamps[1] = globaltimer_ns();
                 if (tid < (int)(a.n_in * (sizeof(InParamDev) / 4))) reinterpret_cast<unsigned int *>(a.par_dev)[tid] = reinterpret_cast<const unsigned int *>(s_par)[tid];
                 // ---- forward: warp i = input i (same steps as k_forward<R>) ----
                 if ((uint32_t)warp < a.n_in) {
@@ -178,7 +190,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArg
                 }
             }
             __syncthreads();
-            if (tid == 0) { __threadfence(); st_release_gpu(a.go, s_cmd ? kPersistExit : t + 1ull); }
+            if (tid == 0) { __threadfence(); st_release_gpu(a.go, s_cmd ? kPersistExit : t + 1ull); if (a.stamp) box->stamps[2] = globaltimer_ns(); }
         } else {
             if (tid == 0) {
                 int cmd = 0;
@@ -301,25 +313,48 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArg
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(a.arrive, 1u);
+        if (tid == 0) { atomicAdd(a.arrive, 1u); if (blockIdx.x == 0 && a.stamp) box->stamps[3] = globaltimer_ns(); }
 
-        // ---------------- CTA 0: sum, inverse, mix, publish ----------------
-        if (blockIdx.x == 0) {
+        // ---------------- every CTA: its slice of the sum over the partial spectra ----------------
+        // (one CTA summing nctas x 4 KB alone is a chain of L2 round trips: 11 us of a 29 us period, measured)
+        {
             if (tid == 0) {
                 const unsigned int want = (unsigned int)((t - a.t0 + 1ull) * nctas);
                 const long long c0 = clock64();
                 while ((int)(ld_acquire_gpu_u32(a.arrive) - want) < 0) {
                     if (clock64() - c0 > kPersistBarrierCycles) { box->err = 1; break; }
                 }
+                if (blockIdx.x == 0 && a.stamp) box->stamps[4] = globaltimer_ns();
             }
             __syncthreads();
-            for (int idx = tid; idx < NOUT * B; idx += kPersistThreads) {
+            const uint32_t n_val = NOUT * B, per_cta = (n_val + nctas - 1) / nctas;
+            for (uint32_t vi = warp; vi < per_cta; vi += kPersistThreads / 32) {  // one warp per value, lanes over the partials
+                const uint32_t idx = blockIdx.x * per_cta + vi;
+                if (idx >= n_val) break;
                 float2 sum = make_float2(0.f, 0.f);
-#pragma unroll 8
-                for (uint32_t c = 0; c < nctas; c++) { const float2 v = __ldcg(a.Ypart + (size_t)c * NOUT * B + idx); sum.x += v.x; sum.y += v.y; }
-                s_Y[idx / B][idx % B] = sum;
+                for (uint32_t c = lane; c < nctas; c += 32) { const float2 v = __ldcg(a.Ypart + (size_t)c * n_val + idx); sum.x += v.x; sum.y += v.y; }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) { sum.x += __shfl_xor_sync(kFull, sum.x, d); sum.y += __shfl_xor_sync(kFull, sum.y, d); }
+                if (lane == 0) a.Ysum[idx] = sum;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(a.arrive + 1, 1u);
+        }
+
+        // ---------------- CTA 0: inverse, mix, publish ----------------
+        if (blockIdx.x == 0) {
+            if (tid == 0) {
+                const unsigned int want = (unsigned int)((t - a.t0 + 1ull) * nctas);
+                const long long c0 = clock64();
+                while ((int)(ld_acquire_gpu_u32(a.arrive + 1) - want) < 0) {
+                    if (clock64() - c0 > kPersistBarrierCycles) { box->err = 1; break; }
+                }
             }
             __syncthreads();
+            for (int idx = tid; idx < NOUT * B; idx += kPersistThreads) s_Y[idx / B][idx % B] = __ldcg(a.Ysum + idx);
+            __syncthreads();
+            if (tid == 0 && a.stamp) box->stamps[5] = globaltimer_ns();
             if (warp < NOUT) {
                 const int o = warp;
                 float2 v[R];
@@ -346,9 +381,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persist(const PersistArg
                     }
                 }
             }
+            if (tid == 0 && a.stamp) box->stamps[6] = globaltimer_ns();
             __threadfence_system();
             __syncthreads();
-            if (tid == 0) st_release_sys(const_cast<unsigned long long *>(&box->seq_out), t + 1ull);
+            if (tid == 0) { if (a.stamp) box->stamps[7] = globaltimer_ns(); st_release_sys(const_cast<unsigned long long *>(&box->seq_out), t + 1ull); }
         }
     }
     if (blockIdx.x == 0 && tid == 0) {

@@ -27,7 +27,7 @@ EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",
     "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
-    "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs",
+    "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs", "ca_persist_stamps",
     "ca_group_config_init", "ca_group_create", "ca_group_destroy", "ca_group_load_ir", "ca_group_set_params", "ca_group_set_glide",
     "ca_group_process", "ca_group_get_stats", "ca_group_reset_stats",
 ]
@@ -129,6 +129,7 @@ def lib():
         L.ca_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.ca_host_free.argtypes = [vp]
         L.ca_measure_read_gbs.argtypes = [C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        L.ca_persist_stamps.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.ca_group_config_init.argtypes = [C.POINTER(GroupConfig)]
         L.ca_group_create.argtypes = [C.POINTER(GroupConfig), C.POINTER(vp)]
         L.ca_group_destroy.argtypes = [vp]
@@ -294,6 +295,11 @@ class Engine:
 
     def reset_stats(self):
         _check(lib().ca_reset_stats(self._h), "ca_reset_stats")
+
+    def persist_stamps(self):
+        a = (C.c_uint64 * 8)()
+        _check(lib().ca_persist_stamps(self._h, a), "ca_persist_stamps")
+        return list(a)
 
 
 class Group:

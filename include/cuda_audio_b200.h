@@ -253,6 +253,10 @@ int ca_group_process(ca_group *g, const float *in, float *out, uint32_t nframes)
 int ca_group_get_stats(ca_group *g, ca_group_stats *s);
 int ca_group_reset_stats(ca_group *g);
 
+/* Diagnostics, CA_FLAG_PERSISTENT: GPU %globaltimer (ns) at the phase boundaries of the last period: input seen,
+ * input read, forward done, first CTA's MAC done, all CTAs arrived, partials summed, inverse done, published. */
+int ca_persist_stamps(ca_engine *e, uint64_t stamps_ns[8]);
+
 /* Pinned host memory helpers for callers that want zero staging copies. */
 int ca_host_alloc(void **p, size_t bytes);
 int ca_host_free(void *p);

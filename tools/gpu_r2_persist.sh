@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_engine_gpu.py -m gpu -x -q -k "persistent_kernel" > gpurun_out/r2p_tests.log 2>&1; echo "persist tests rc=$?"; tail -30 gpurun_out/r2p_tests.log | cut -c1-400
+for ST in 0 1; do
+if [ $ST = 1 ]; then export CA_PERSIST_STAMPS=1; fi
 timeout 300 python - <<'PY'
 import sys, os, time
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "cuda-audio_b200", "python"))
@@ -18,4 +20,12 @@ for name, fl in (("graph", ca.FLAG_GRAPH), ("persistent", ca.FLAG_PERSISTENT)):
         for _ in range(3000): e.process_raw(a.ptr, b.ptr)
         s = e.stats()
         print(name, "p50 %.1f p99 %.1f max %.1f us" % (s.p50_us, s.p99_us, s.max_us), "launches", s.gpu_launches, flush=True)
+        if fl == ca.FLAG_PERSISTENT:
+            acc = np.zeros(7)
+            for _ in range(200):
+                e.process_raw(a.ptr, b.ptr)
+                st = e.persist_stamps()
+                acc += np.diff(np.array(st, dtype=np.int64))
+            print("phases ns (read input, forward, mac cta0, wait all, sum, inverse, fence+publish):", (acc / 200).round(0).tolist(), "device total", round(acc.sum() / 200))
 PY
+done
