@@ -515,7 +515,7 @@ def run_ours(args):
     roof = None
     if rank == 0 and not args.no_roofline:
         peak, peak_src = measured_peak_hbm()
-        Kp = min(K, args.profile_instances)
+        Kp = min(K, args.profile_instances) if args.profile_instances > 0 else K   # default: the headline's own batch
         ep = build_engine(ca, torch, dev, Kp, ca.FLAG_STREAMING | ca.FLAG_PROFILE, tiers=tiers)
         for _ in range(STEADY + cycle):
             ep.process_device(x_dev.data_ptr(), y_dev.data_ptr())
@@ -929,7 +929,7 @@ def main():
     ap.add_argument("--reserve-gb", type=float, default=11.0, help="HBM left free when --instances 0 sizes the batch")
     ap.add_argument("--uniform", action="store_true", help="uniform partitioning (P=750) instead of the non-uniform tiers")
     ap.add_argument("--uniform-instances", type=int, default=2048)
-    ap.add_argument("--profile-instances", type=int, default=4096)
+    ap.add_argument("--profile-instances", type=int, default=0, help="instances of the per-kernel profile / roofline run (0 = the same batch as the headline)")
     ap.add_argument("--no-round-to-cycle", action="store_true", help="time exactly --steps periods instead of rounding up to a multiple of the tier launch-pattern period (64)")
     ap.add_argument("--parity-periods", type=int, default=896, help="periods of the in-bench parity spot-check (>= 832: the 16 K tier's delay line wraps)")
     ap.add_argument("--no-parity", action="store_true")
