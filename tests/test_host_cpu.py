@@ -236,3 +236,24 @@ def test_midi_device_thread_drives_cc_mapping(tmp_path):
     proc.wait(timeout=10)
     assert out == {"predelay": 4096, "dry": 0.25, "wet": 0.75, "speed": 128, "panDry": -1.0, "panWet": 127 / 64 - 1, "level": 0.5}
     assert RENDER and subprocess.run([RENDER, "--midi-listen", str(tmp_path / "nope"), "0.1"], capture_output=True).returncode == 1
+
+
+def test_wav_with_lying_block_align_is_rejected_or_clamped(tmp_path):
+    """A header whose blockAlign is smaller than channels x bytes per sample would walk the sample loop past the
+    data chunk: rejected.  A larger blockAlign (padding per frame) is legal: the last frame must still lie inside."""
+    pcm = (np.arange(40, dtype=np.int16) * 100).tobytes()              # 20 stereo 16-bit frames = 80 bytes
+    good = wav_bytes(1, 2, 48000, 16, pcm)
+    off = good.index(b"fmt ") + 8 + 12                                  # blockAlign field
+    lying = bytearray(good)
+    lying[off:off + 2] = struct.pack("<H", 2)                           # claims 2 bytes per frame, needs 4
+    p = tmp_path / "lying.wav"
+    p.write_bytes(bytes(lying))
+    r = subprocess.run([RENDER, "--dump-wav", str(p), "1", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode == 1 and "blockAlign" in r.stderr
+    padded = bytearray(wav_bytes(1, 2, 48000, 16, pcm + b"\0\0"))      # 82 bytes of data, blockAlign 6: 13 frames ((13-1)*6 + 4 = 76 <= 82)
+    padded[off:off + 2] = struct.pack("<H", 6)
+    q = tmp_path / "padded.wav"
+    q.write_bytes(bytes(padded))
+    m, d = dump(q, 1.0, tmp_path)
+    assert m["frames"] == 13 and d.shape == (2, 13)
+    assert d[0, 1] == np.float32(300 / 32768.0)                          # frame 1 starts at byte 6 = sample 3
