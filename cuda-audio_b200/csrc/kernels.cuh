@@ -225,6 +225,20 @@ __global__ void k_release_voices(const ItemState *st, uint32_t n, const VoicePoo
     for (int v = 0; v < kMaxVoices; v++) voice_pool_free(vp, st[i].pool[v]);
 }
 
+// same with the old state already loaded by the caller (so that load can overlap other set-up work)
+__device__ __forceinline__ ItemState item_step_warp_from(const ItemState &old, ItemState *st, uint32_t n_items_alloc, uint32_t item, const InParamDev &p,
+                                                         unsigned long long t, int nv, uint32_t ring_out, const VoicePool &vp, int lane)
+{
+    ItemState s = step_item_state(old, p, t, nv, ring_out);
+    if (lane == 0) voice_storage_update(s, old.active, item, nv, vp);
+    s.active = __shfl_sync(0xffffffffu, s.active, 0);
+    s.fresh = __shfl_sync(0xffffffffu, s.fresh, 0);
+#pragma unroll
+    for (int v = 0; v < kMaxVoices; v++) s.pool[v] = __shfl_sync(0xffffffffu, s.pool[v], 0);
+    if (lane == 0) st[((t + 1ull) & 1ull) * n_items_alloc + item] = s;
+    return s;
+}
+
 // pool entry (0-based) of voice v; only called for voices that are active (they always have storage)
 __device__ __forceinline__ uint32_t voice_entry(const ItemState &s, uint32_t v)
 {

@@ -30,20 +30,31 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
     constexpr int B = 256;
     extern __shared__ __align__(16) float2 sm[];
     __shared__ RowTables tb;
-    rows_tables_init(tb, a.rowtw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t w = blockIdx.x * kRowsWarps + warp;
-    if (w >= a.n_items) return;
-    const uint32_t item = a.item0 + w;
+    const bool valid = w < a.n_items;
+    const uint32_t item = a.item0 + (valid ? w : 0u);
     const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t;
-    if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
-
+    // parameter / state loads are in flight while the twiddle tables are staged (one L2 round trip, not two)
     const InParamDev p = a.par[item];
     const uint32_t pd = a.par[(item / a.n_in) * a.n_in].predelay;  // input 0's, conv.cu:412,415
-    const ItemState s = item_step_warp(a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
-    // per-voice coefficient and storage are re-read from the state lane 0 just stored (same warp, L1-hot):
-    // keeping eight more values alive across the transform spills at 64 registers
-    const ItemState *sn = a.st + ((t + 1ull) & 1ull) * a.n_items_alloc + item;
+    const ItemState old = a.st[(t & 1ull) * a.n_items_alloc + item];
+    rows_tables_init(tb, a.rowtw);
+    if (!valid) return;
+    if (w == 0 && lane == 0) a.ctl->t_next = t + 1ull;
+    const ItemState s = item_step_warp_from(old, a.st, a.n_items_alloc, item, p, t, (int)a.nv, a.ring_out, a.vp, lane);
+    // per-voice coefficient and storage entry wait in shared memory: keeping eight more values alive across the
+    // transform spills at 64 registers, re-reading them from the stored state would be an L2 round trip per voice
+    __shared__ float s_vc[kRowsWarps][kMaxVoices];
+    __shared__ uint32_t s_ve[kRowsWarps][kMaxVoices];
+    if (lane < kMaxVoices) {
+        float cv = 0.f;
+        uint32_t ev = 0u;
+#pragma unroll
+        for (int q = 0; q < kMaxVoices; q++) { cv = (q == lane) ? s.c[q] : cv; ev = (q == lane) ? s.pool[q] : ev; }
+        s_vc[warp][lane] = cv;
+        s_ve[warp][lane] = ev;
+    }
     const uint32_t active = s.active, fresh = s.fresh;
     __syncwarp();
 
@@ -57,8 +68,8 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_fwd0_rows(const FwdArgs a)
 #pragma unroll 1
     for (uint32_t v = 0; v < a.nv; v++) {
         if (!((active >> v) & 1u)) continue;
-        const float gain = sn->c[v] * p.level;
-        const uint32_t entry = sn->pool[v] - 1u;
+        const float gain = s_vc[warp][v] * p.level;
+        const uint32_t entry = s_ve[warp][v] - 1u;
         float *ring = a.ring + (size_t)entry * a.ring_len;
         if ((fresh >> v) & 1u) {  // (re)allocated voice: its time-domain history belongs to another IR
             for (uint32_t n = 4 * lane; n < a.ring_len; n += 128) *reinterpret_cast<float4 *>(ring + n) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -118,10 +129,10 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_inv0_rows(const InvArgs a)
     constexpr int B = 256;
     extern __shared__ __align__(16) float2 sm[];
     __shared__ RowTables tb;
-    rows_tables_init(tb, a.rowtw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t local = blockIdx.x * kRowsWarps + warp;
-    if (local >= a.n_items) return;
+    const uint32_t local0 = blockIdx.x * kRowsWarps + warp;
+    const bool valid = local0 < a.n_items;
+    const uint32_t local = valid ? local0 : 0u;   // idle warps of the last CTA shadow item 0's loads, then leave
     const uint32_t item = a.item0 + local;
     const uint32_t inst = item / a.n_out, o = item % a.n_out;
     const unsigned long long t = a.t_host_p1 ? a.t_host_p1 - 1ull : a.ctl->t_next - 1ull;
@@ -169,7 +180,8 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_inv0_rows(const InvArgs a)
         xb[j] = *reinterpret_cast<const float4 *>(x1 + 4 * j);
         accv[j] = accp ? *reinterpret_cast<const float4 *>(accp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncwarp();
+    rows_tables_init(tb, a.rowtw);  // after every global load of the prologue has been issued
+    if (!valid) return;
     rows_split<true>(row, row, true, make_float2(1.f, 0.f), tb, lane);
     __syncwarp();
     float2 v[8];
@@ -228,7 +240,6 @@ __global__ void __launch_bounds__(M1 * 32) k_tfwd_fused(const TierFwdArgs a)
     __shared__ RowTables tb;
     const TierCommon c = tier_fwd_common(a, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!c.active) return;  // uniform for the CTA
-    rows_tables_init(tb, a.rowtw);
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const uint32_t mask = a.ring_len - 1;
     const float *ring = a.ring + (size_t)c.w * a.ring_len;
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(M1 * 32) k_tfwd_fused(const TierFwdArgs a)
 #pragma unroll
         for (int k1 = 0; k1 < M1; k1++) sm[k1 * kRowSlots + e3(n2)] = col[k1];
     }
-    __syncthreads();
+    rows_tables_init(tb, a.rowtw);  // staged after the window loads were issued; its barrier also closes the column phase
     // rows: X[k1 + M1 k2] = sum_n2 A[k1][n2] W_M^(n2 k1) W_256^(n2 k2)
     float2 *row = sm + r * kRowSlots;
     float2 v[8];
@@ -270,7 +281,6 @@ __global__ void __launch_bounds__(M1 * 32) k_tinv_fused(const TierInvArgs a)
     pdl_wait();
     extern __shared__ __align__(16) float2 sm[];
     __shared__ RowTables tb;
-    rows_tables_init(tb, a.rowtw);
     const uint32_t z = blockIdx.y, o = blockIdx.x;
     const uint32_t inst = a.inst0 + z * a.inst_stride;
     const uint32_t item = inst * a.n_out + o;
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(M1 * 32) k_tinv_fused(const TierInvArgs a)
 #pragma unroll
         for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(row + e3(2 * lane + 64 * i)) = q[i];
     }
-    __syncthreads();
+    rows_tables_init(tb, a.rowtw);  // after the partial-sum loads; its barrier also publishes the rows
     const int rp = (M1 - r) % M1;
     rows_split<true>(row, sm + rp * kRowSlots, r == 0, r ? __ldg(&a.tw2M[r]) : make_float2(1.f, 0.f), tb, lane);
     __syncthreads();
@@ -390,17 +400,17 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_trows_fwd(const TierFwdArgs
     __shared__ RowTables tb;
     const TierCommon c = tier_fwd_common(a, blockIdx.x / (M1 / 8), blockIdx.y, blockIdx.z);
     if (!c.active) return;
-    rows_tables_init(tb, a.rowtw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = rows_pair_row<M1>((int)(blockIdx.x % (M1 / 8)), warp);
     float2 *row = sm + warp * kRowSlots;
     float2 *slot = a.X + ((size_t)c.w * a.Lring + c.slot) * a.S + (brev_s((uint32_t)r, a.s_log) << 8);
-    float2 v[8];
+    float2 v[8], tw[8];
 #pragma unroll
-    for (int b = 0; b < 8; b++) v[b] = slot[lane + 32 * b];
+    for (int b = 0; b < 8; b++) { v[b] = slot[lane + 32 * b]; tw[b] = __ldg(&a.twM[(lane + 32 * b) * r]); }
+    rows_tables_init(tb, a.rowtw);  // the row and its four-step twiddles are in flight meanwhile
     if (r) {
 #pragma unroll
-        for (int b = 0; b < 8; b++) v[b] = cmul(v[b], __ldg(&a.twM[(lane + 32 * b) * r]));
+        for (int b = 0; b < 8; b++) v[b] = cmul(v[b], tw[b]);
     }
     row_fft256<false>(v, row, tb, lane, NoPostTw{});
     __syncthreads();
@@ -418,7 +428,6 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_trows_inv(const TierInvArgs
     pdl_wait();
     extern __shared__ __align__(16) float2 sm[];
     __shared__ RowTables tb;
-    rows_tables_init(tb, a.rowtw);
     const uint32_t z = blockIdx.y, o = blockIdx.x / (M1 / 8);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = rows_pair_row<M1>((int)(blockIdx.x % (M1 / 8)), warp);
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(kRowsThreads, 4) k_trows_inv(const TierInvArgs
 #pragma unroll
         for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(row + e3(2 * lane + 64 * i)) = q[i];
     }
-    __syncthreads();
+    rows_tables_init(tb, a.rowtw);  // after the partial-sum loads; its barrier also publishes the rows
     const int rp = (M1 - r) % M1;
     rows_split<true>(row, rp == r ? row : sm + (warp ^ 1) * kRowSlots, r == 0, r ? __ldg(&a.tw2M[r]) : make_float2(1.f, 0.f), tb, lane);
     __syncthreads();
