@@ -8,6 +8,8 @@
 #include "kernels_rows.cuh"
 #include "kernels_persist.cuh"
 
+#include <cuda.h>  // types + prototypes only: driver entry points are resolved through the runtime (no libcuda link dependency)
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -289,6 +291,9 @@ struct ca_engine {
     float2 *d_pY = nullptr, *d_pYsum = nullptr;
     bool p_stamp = false;
     uint32_t p_ctas = 0, p_gen = 0;
+    // SM partitioning (green contexts): MAC lane on sm_mac SMs, FFT lanes on the rest
+    CUgreenCtx g_mac = nullptr, g_fft = nullptr;
+    uint32_t sm_mac = 0, sm_fft = 0;
     uint32_t *d_vpool = nullptr;  // bitmap of the shared cross-fade voice entries
     uint32_t n_voices = 0, n_extra = 0;  // voice pool: n_items homes + n_extra shared entries
     bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
@@ -954,6 +959,50 @@ int prewarm_graphs(ca_engine *e)
     return CA_OK;
 }
 
+// Split the device's SMs into two green contexts: `n_mac` SMs (rounded to the hardware's granularity) for the
+// memory-bound MAC lane, the rest for the latency-bound FFT lanes of the pipelined batch schedule.  Two kernels
+// sharing an SM starve each other (the persistent MAC holds every register); on disjoint SMs both run at their
+// own speed and the MAC still saturates HBM from a subset of the SMs.
+template <class F>
+bool drv(const char *name, F *fn)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess || !p) { (void)cudaGetLastError(); return false; }
+    *fn = reinterpret_cast<F>(p);
+    return true;
+}
+
+int setup_sm_split(ca_engine *e, uint32_t n_mac, int prio_lo, int prio_hi)
+{
+    decltype(&cuDeviceGet) pDeviceGet; decltype(&cuDeviceGetDevResource) pGetRes; decltype(&cuDevSmResourceSplitByCount) pSplit;
+    decltype(&cuDevResourceGenerateDesc) pDesc; decltype(&cuGreenCtxCreate) pCreate; decltype(&cuGreenCtxStreamCreate) pStream;
+    if (!drv("cuDeviceGet", &pDeviceGet) || !drv("cuDeviceGetDevResource", &pGetRes) || !drv("cuDevSmResourceSplitByCount", &pSplit) ||
+        !drv("cuDevResourceGenerateDesc", &pDesc) || !drv("cuGreenCtxCreate", &pCreate) || !drv("cuGreenCtxStreamCreate", &pStream)) {
+        g_last_error = "green contexts are not available in this driver";
+        return CA_ERR_UNSUPPORTED;
+    }
+    CA_CUDA(cudaFree(nullptr));  // primary context
+    CUdevice dev;
+    CUdevResource all, grp, rem;
+    unsigned int nb = 1;
+    CUdevResourceDesc d1, d2;
+    auto ok = [](CUresult r, const char *what) { if (r != CUDA_SUCCESS) { g_last_error = std::string(what) + " failed: CUresult " + std::to_string((int)r); return false; } return true; };
+    if (!ok(pDeviceGet(&dev, e->device), "cuDeviceGet") || !ok(pGetRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM), "cuDeviceGetDevResource") ||
+        !ok(pSplit(&grp, &nb, &all, &rem, 0, n_mac), "cuDevSmResourceSplitByCount") || nb != 1 || rem.sm.smCount == 0 ||
+        !ok(pDesc(&d1, &grp, 1), "cuDevResourceGenerateDesc") || !ok(pDesc(&d2, &rem, 1), "cuDevResourceGenerateDesc") ||
+        !ok(pCreate(&e->g_mac, d1, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate") || !ok(pCreate(&e->g_fft, d2, dev, CU_GREEN_CTX_DEFAULT_STREAM), "cuGreenCtxCreate"))
+        return CA_ERR_UNSUPPORTED;
+    e->sm_mac = grp.sm.smCount; e->sm_fft = rem.sm.smCount;
+    CUstream st;
+    if (!ok(pStream(&st, e->g_fft, CU_STREAM_NON_BLOCKING, prio_hi), "cuGreenCtxStreamCreate")) return CA_ERR_UNSUPPORTED;
+    e->stream = st;
+    if (!ok(pStream(&st, e->g_mac, CU_STREAM_NON_BLOCKING, prio_lo), "cuGreenCtxStreamCreate")) return CA_ERR_UNSUPPORTED;
+    e->s_mac = st;
+    for (auto &ts : e->s_tier) { if (!ok(pStream(&st, e->g_fft, CU_STREAM_NON_BLOCKING, prio_hi), "cuGreenCtxStreamCreate")) return CA_ERR_UNSUPPORTED; ts = st; }
+    return CA_OK;
+}
+
 // ---- CA_FLAG_PERSISTENT: the resident kernel and its mailbox ----
 typedef void (*persist_fn)(const PersistArgs);
 persist_fn persist_pick(uint32_t R, uint32_t n_out)
@@ -1218,6 +1267,11 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     int prio_lo = 0, prio_hi = 0;
     CA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     if (getenv("CA_PIPE_PRIO") && atoi(getenv("CA_PIPE_PRIO")) == 0) prio_hi = prio_lo;
+    const uint32_t sm_split = getenv("CA_SM_SPLIT") ? (uint32_t)atoi(getenv("CA_SM_SPLIT")) : cfg->sm_split;
+    if (sm_split) {
+        rc = setup_sm_split(e, sm_split, prio_lo, prio_hi);
+        if (rc) return rc;
+    } else
     CA_CUDA(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, prio_hi));
     for (auto &ev : e->ev) CA_CUDA(cudaEventCreate(&ev));
     for (auto &row : e->tev) for (auto &ev : row) CA_CUDA(cudaEventCreate(&ev));
@@ -1225,18 +1279,18 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaEventCreateWithFlags(&e->out_ready, cudaEventDisableTiming));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
     CA_CUDA(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-    for (auto &st : e->s_tier) CA_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
+    if (!sm_split) for (auto &st : e->s_tier) CA_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_hi));
     CA_CUDA(cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming));
     for (auto &ev : e->join_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &row : e->io_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CA_CUDA(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, prio_lo));
+    if (!sm_split) CA_CUDA(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, prio_lo));
     for (auto &ev : e->pf_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : e->pm_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : e->ptf_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &row : e->ptm_ev) for (auto &ev : row) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CA_CUDA(cudaEventCreateWithFlags(&e->pm_tail, cudaEventDisableTiming));
     for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    e->pipe_mode = (cfg->schedule & CA_SCHED_PIPELINED) ? 1 : 0;
+    e->pipe_mode = ((cfg->schedule & CA_SCHED_PIPELINED) || sm_split) ? 1 : 0;
     if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
     e->async_tiers = (cfg->flags & CA_FLAG_ASYNC_TIERS) && e->tiers.size() > 1 && !(cfg->flags & CA_FLAG_PROFILE);
     CA_CUDA(cudaStreamCreateWithPriority(&e->s_def, cudaStreamNonBlocking, prio_lo));
@@ -1286,7 +1340,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
                 int per_sm = 0;
                 CA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)t.mac.pfn, kMacThreads, t.mac.psmem));
                 if (const char *cs = getenv("CA_MAC_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(cs)));  // resident MAC CTAs per SM
-                t.p_slots = (uint32_t)std::max(1, per_sm) * (uint32_t)sms;
+                t.p_slots = (uint32_t)std::max(1, per_sm) * (e->sm_mac ? e->sm_mac : (uint32_t)sms);
                 if (const char *sl = getenv("CA_MAC_SLOTS")) t.p_slots = (uint32_t)std::max(1, atoi(sl));
             }
         }

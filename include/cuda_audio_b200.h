@@ -119,6 +119,9 @@ typedef struct ca_config {
      * environment variables of DESIGN.md section 9 override them and exist for development sweeps only. */
     uint32_t schedule;
     uint32_t io_chunks;     /* instance chunks of ca_process's H2D | kernels | D2H pipeline for batches; 0 = 2 */
+    /* Batches: give the (memory-bound) MAC lane its own `sm_split` SMs and the (latency-bound) FFT lanes the rest
+     * (CUDA green contexts), and run the two-lane pipelined schedule on them.  0 = off. */
+    uint32_t sm_split;
 } ca_config;
 
 /* Per-input parameter block == Convolution::CC::value (conv.h:40-50). */

@@ -583,3 +583,35 @@ def test_schedule_bits_in_the_config_select_the_same_kernels_as_the_env_knobs():
     assert (f0, f1, f2) == (0, 0, 1)
     assert np.array_equal(y_item, y_pers) and np.array_equal(y_pers, y_pipe)
     assert O.rel_l2(y_fused, y_item) < 2e-6
+
+
+def test_sm_split_green_contexts_bit_identical():
+    """ca_config.sm_split: MAC lane and FFT lanes of the pipelined batch schedule on disjoint SM sets (CUDA green
+    contexts).  Only the placement changes: output identical to the sequential schedule bit for bit."""
+    m = ca()
+    B, K = 64, 24
+    tiers = [(64, 8), (512, 3), (2048, 0)]
+    L = 64 * 8 + 512 * 3 + 2048 * 2 - 9
+    irs = [irs2x2(L, 9200 + 8 * s) for s in range(4)]
+    n = B * 150
+    x = np.stack([np.stack([O.synth_audio(n, 9700 + 2 * s + i) for i in range(2)]) for s in range(K)])
+
+    def go(**kw):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=8, tiers=tiers, mac_split=1,
+                      schedule=m.SCHED_MAC_PERSISTENT | m.SCHED_NO_FUSED_TIER0, **kw) as e:
+            for s in range(4):
+                for i in range(2):
+                    e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
+            for s in range(K):
+                for i in range(2):
+                    e.set_params(s, i, select=2 * (s % 4) + i, wet=0.8, dry=0.1, predelay=2 * s)
+                    e.set_glide(s, i, 0.8)
+            return e.render(x)
+
+    try:
+        y_split = go(sm_split=96)
+    except m.CaError as ex:
+        if ex.code == -5:
+            pytest.skip("green contexts not available: " + str(ex))
+        raise
+    assert np.array_equal(y_split, go())
