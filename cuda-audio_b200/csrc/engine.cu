@@ -1204,6 +1204,13 @@ int ca_destroy(ca_engine *e)
     if (e->pbox) cudaFreeHost(e->pbox);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->g_mac || e->g_fft) {
+        decltype(&cuGreenCtxDestroy) pDestroy = nullptr;
+        if (drv("cuGreenCtxDestroy", &pDestroy)) {
+            if (e->g_mac) pDestroy(e->g_mac);
+            if (e->g_fft) pDestroy(e->g_fft);
+        }
+    }
     delete e;
     return CA_OK;
 }
