@@ -85,6 +85,8 @@ enum ca_schedule {
 
 typedef struct ca_engine ca_engine;
 
+/* ca_config grows at the END between versions of this header.  ca_config_init() writes the LIBRARY's size, ca_create()
+ * refuses a struct_size it does not know: build host code against the header that ships with the library. */
 typedef struct ca_config {
     uint32_t struct_size;   /* sizeof(ca_config) */
     int32_t device;         /* CUDA device ordinal */

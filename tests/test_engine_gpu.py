@@ -574,3 +574,52 @@ def test_persistent_kernel_mode_rejects_what_it_cannot_do():
         with pytest.raises(m.CaError) as ei:
             m.Engine(**args)
         assert ei.value.code == -5, kw
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_configurations_vs_fp64(seed):
+    """Seeded random sweep over the configuration space (period, IR length, channel layout, tier plan, flags,
+    predelay, pans, instance count) against the fp64 oracle: the parity gate should not depend on the handful of
+    shapes the other tests happen to use."""
+    m = ca()
+    rng = np.random.default_rng(1234 + seed)
+    B = int(rng.choice([32, 64, 128, 256, 256, 512]))
+    n_in, n_out = int(rng.integers(1, 3)), int(rng.integers(1, 3))
+    K = int(rng.choice([1, 1, 2, 5, 19]))
+    mode = rng.choice(["uniform", "auto", "auto", "explicit"])
+    if mode == "explicit" and B <= 256:
+        S1 = int(max(256, B * int(rng.choice([4, 8]))))
+        p0 = S1 // B + int(rng.integers(0, 3))
+        tiers = [(B, p0), (S1, 0)]
+        L = B * p0 + S1 * int(rng.integers(2, 6)) - int(rng.integers(0, B))
+    else:
+        tiers = None if mode != "auto" else "auto"
+        L = int(rng.integers(3 * B, 60 * B)) if mode != "auto" else int(rng.integers(20 * B, 200 * B))
+    flags = 0
+    if K == 1 and rng.random() < 0.5:
+        flags |= m.FLAG_GRAPH
+    if tiers is not None and rng.random() < 0.3 and mode == "auto":
+        flags |= m.FLAG_ASYNC_TIERS
+    if rng.random() < 0.3:
+        flags |= m.FLAG_LEGACY_FFT
+    nper = int(max(40, (L // B) + 30))
+    pd = int(rng.choice([0, 0, 1, 63, 64, 777, 8191]))
+    irs = [[[O.synth_ir(L, 48000, 40000 + 100 * seed + 8 * s + 2 * i + o) for o in range(n_out)] for i in range(n_in)] for s in range(min(K, 3))]
+    x = np.stack([np.stack([O.synth_audio(B * nper, 41000 + 100 * seed + 2 * s + i) for i in range(n_in)]) for s in range(K)])
+    prs = [[dict(wet=float(rng.uniform(0.2, 1.0)), dry=float(rng.uniform(0, 0.5)), level=float(rng.uniform(0.5, 1.0)),
+                 panWet=float(rng.uniform(-1, 1)), panDry=float(rng.uniform(-1, 1))) for i in range(n_in)] for s in range(K)]
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_in=n_in, n_out=n_out, n_ir_slots=n_in * min(K, 3), tiers=tiers, flags=flags) as e:
+        for s in range(min(K, 3)):
+            for i in range(n_in):
+                e.load_ir(n_in * s + i, irs[s][i][0], irs[s][i][1] if n_out == 2 else None)
+        for s in range(K):
+            for i in range(n_in):
+                e.set_params(s, i, select=n_in * (s % 3 if K >= 3 else s) + i, predelay=pd, **prs[s][i])
+                e.set_glide(s, i, prs[s][i]["wet"])
+        y = e.render(x)
+        st = e.stats()
+    for s in sorted(set([0, K // 2, K - 1])):
+        truth = O.engine_truth(x[s], irs[s % 3 if K >= 3 else s], prs[s], predelay=pd)
+        for o in range(n_out):
+            err = O.rel_l2(y[s, o], truth[o])
+            assert err < 5e-6, dict(seed=seed, B=B, L=L, K=K, n_in=n_in, n_out=n_out, mode=str(mode), flags=flags, pd=pd, tiers=[int(st.tier_block[j]) for j in range(st.n_tiers)], s=s, o=o, err=err)
