@@ -6,6 +6,7 @@
 #include "../../include/cuda_audio_b200.h"
 #include "kernels.cuh"
 #include "kernels_rows.cuh"
+#include "kernels_rows16.cuh"
 #include "kernels_persist.cuh"
 
 #include <cuda.h>  // types + prototypes only: driver entry points are resolved through the runtime (no libcuda link dependency)
@@ -297,6 +298,7 @@ struct ca_engine {
     uint32_t *d_vpool = nullptr;  // bitmap of the shared cross-fade voice entries
     uint32_t n_voices = 0, n_extra = 0;  // voice pool: n_items homes + n_extra shared entries
     bool rows0 = false;         // tier 0 (period 256) on the row-FFT kernels
+    bool rows16 = true;         // row FFTs as 16 x 16, two rows per warp (kernels_rows16.cuh); false: 8 x 8 x 4 (CA_SCHED_ROWS8)
     bool fused = false;       // tier 0 runs as one fused kernel (k_fused0)
     uint32_t fused_smem = 0;
     // graphs: [0] = the period pipeline (tier 0), [mask] = the deferred tiers that fire together
@@ -410,7 +412,8 @@ void launch_fwd0(ca_engine *e, bool pdl, FwdArgs fa, cudaStream_t st)
 {
     fa.rowtw = e->d_rowtw;
     fa.vp = voice_pool(e);
-    if (e->rows0) launch_k(pdl, k_fwd0_rows, dim3((fa.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, fa);
+    if (e->rows0 && e->rows16) launch_k(pdl, k_fwd0_x2, dim3((fa.n_items + kX2Rows - 1) / kX2Rows), dim3(kX2Threads), kX2Smem, st, fa);
+    else if (e->rows0) launch_k(pdl, k_fwd0_rows, dim3((fa.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, fa);
     else launch_k(pdl, e->fft.fwd, dim3((fa.n_items + kFwdWarps - 1) / kFwdWarps), dim3(kFwdWarps * 32), 0, st, fa);
 }
 
@@ -418,7 +421,8 @@ void launch_inv0(ca_engine *e, bool pdl, InvArgs ia, cudaStream_t st)
 {
     ia.rowtw = e->d_rowtw;
     if (ia.n_split <= 4) {
-        if (e->rows0) launch_k(pdl, k_inv0_rows, dim3((ia.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, ia);
+        if (e->rows0 && e->rows16) launch_k(pdl, k_inv0_x2, dim3((ia.n_items + kX2Rows - 1) / kX2Rows), dim3(kX2Threads), kX2Smem, st, ia);
+        else if (e->rows0) launch_k(pdl, k_inv0_rows, dim3((ia.n_items + kRowsWarps - 1) / kRowsWarps), dim3(kRowsThreads), kRowsSmem, st, ia);
         else launch_k(pdl, e->fft.inv_packed, dim3((ia.n_items + kInvThreads / 32 - 1) / (kInvThreads / 32)), dim3(kInvThreads), 0, st, ia);
     } else {
         launch_k(pdl, e->fft.inv, dim3(ia.n_items), dim3(kInvThreads), 0, st, ia);  // latency schedule: one CTA sums up to 256 partials
@@ -428,23 +432,31 @@ void launch_inv0(ca_engine *e, bool pdl, InvArgs ia, cudaStream_t st)
 uint32_t tier_threads(const Tier &t) { return std::min<uint32_t>(kTierThreads, std::max<uint32_t>(tier_min(), t.S / tier_div())); }
 
 template <int M1>
-void launch_tfwd_rows(const Tier &t, bool pdl, const TierFwdArgs &fa, uint32_t nv, uint32_t n_in, uint32_t count, cudaStream_t st)
+void launch_tfwd_rows(const Tier &t, bool x2, bool pdl, const TierFwdArgs &fa, uint32_t nv, uint32_t n_in, uint32_t count, cudaStream_t st)
 {
     if constexpr (M1 <= 16) {
+        if constexpr (M1 >= 2) {
+            if (x2) { launch_k(pdl, k_tfwd_x2<M1>, dim3(nv, n_in, count), dim3(M1 * 16), M1 * kR16Slots * sizeof(float2), st, fa); return; }
+        }
         launch_k(pdl, k_tfwd_fused<M1>, dim3(nv, n_in, count), dim3(M1 * 32), M1 * kRowSlots * sizeof(float2), st, fa);
     } else {
         launch_k(pdl, k_tcols_fwd<M1>, dim3(nv * 8, n_in, count), dim3(256), 0, st, fa);
-        launch_k(pdl, k_trows_fwd<M1>, dim3(nv * (M1 / 8), n_in, count), dim3(kRowsThreads), kRowsSmem, st, fa);
+        if (x2) launch_k(pdl, k_trows_fwd_x2<M1>, dim3(nv * (M1 / 16), n_in, count), dim3(kX2Threads), kX2Smem, st, fa);
+        else launch_k(pdl, k_trows_fwd<M1>, dim3(nv * (M1 / 8), n_in, count), dim3(kRowsThreads), kRowsSmem, st, fa);
     }
 }
 
 template <int M1>
-void launch_tinv_rows(const Tier &t, bool pdl, const TierInvArgs &ia, uint32_t n_out, uint32_t count, cudaStream_t st)
+void launch_tinv_rows(const Tier &t, bool x2, bool pdl, const TierInvArgs &ia, uint32_t n_out, uint32_t count, cudaStream_t st)
 {
     if constexpr (M1 <= 16) {
+        if constexpr (M1 >= 2) {
+            if (x2) { launch_k(pdl, k_tinv_x2<M1>, dim3(n_out, count), dim3(M1 * 16), M1 * kR16Slots * sizeof(float2), st, ia); return; }
+        }
         launch_k(pdl, k_tinv_fused<M1>, dim3(n_out, count), dim3(M1 * 32), M1 * kRowSlots * sizeof(float2), st, ia);
     } else {
-        launch_k(pdl, k_trows_inv<M1>, dim3(n_out * (M1 / 8), count), dim3(kRowsThreads), kRowsSmem, st, ia);
+        if (x2) launch_k(pdl, k_trows_inv_x2<M1>, dim3(n_out * (M1 / 16), count), dim3(kX2Threads), kX2Smem, st, ia);
+        else launch_k(pdl, k_trows_inv<M1>, dim3(n_out * (M1 / 8), count), dim3(kRowsThreads), kRowsSmem, st, ia);
         launch_k(pdl, k_tcols_inv<M1>, dim3(n_out * 8, count), dim3(256), 0, st, ia);
     }
 }
@@ -454,13 +466,13 @@ uint32_t launch_tier_fwd(ca_engine *e, const Tier &t, bool pdl, TierFwdArgs fa, 
 {
     fa.rowtw = e->d_rowtw;
     switch (t.rows_mode ? t.M1 : 0u) {
-    case 1: launch_tfwd_rows<1>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
-    case 2: launch_tfwd_rows<2>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
-    case 4: launch_tfwd_rows<4>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
-    case 8: launch_tfwd_rows<8>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
-    case 16: launch_tfwd_rows<16>(t, pdl, fa, e->nv, e->n_in, count, st); return 1;
-    case 32: launch_tfwd_rows<32>(t, pdl, fa, e->nv, e->n_in, count, st); return 2;
-    case 64: launch_tfwd_rows<64>(t, pdl, fa, e->nv, e->n_in, count, st); return 2;
+    case 1: launch_tfwd_rows<1>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 2: launch_tfwd_rows<2>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 4: launch_tfwd_rows<4>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 8: launch_tfwd_rows<8>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 16: launch_tfwd_rows<16>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 1;
+    case 32: launch_tfwd_rows<32>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 2;
+    case 64: launch_tfwd_rows<64>(t, e->rows16, pdl, fa, e->nv, e->n_in, count, st); return 2;
     default: launch_k(pdl, k_tier_forward, dim3(e->nv, e->n_in, count), dim3(tier_threads(t)), t.S * sizeof(float2), st, fa); return 1;
     }
 }
@@ -469,13 +481,13 @@ uint32_t launch_tier_inv(ca_engine *e, const Tier &t, bool pdl, TierInvArgs ia, 
 {
     ia.rowtw = e->d_rowtw;
     switch (t.rows_mode ? t.M1 : 0u) {
-    case 1: launch_tinv_rows<1>(t, pdl, ia, e->n_out, count, st); return 1;
-    case 2: launch_tinv_rows<2>(t, pdl, ia, e->n_out, count, st); return 1;
-    case 4: launch_tinv_rows<4>(t, pdl, ia, e->n_out, count, st); return 1;
-    case 8: launch_tinv_rows<8>(t, pdl, ia, e->n_out, count, st); return 1;
-    case 16: launch_tinv_rows<16>(t, pdl, ia, e->n_out, count, st); return 1;
-    case 32: launch_tinv_rows<32>(t, pdl, ia, e->n_out, count, st); return 2;
-    case 64: launch_tinv_rows<64>(t, pdl, ia, e->n_out, count, st); return 2;
+    case 1: launch_tinv_rows<1>(t, e->rows16, pdl, ia, e->n_out, count, st); return 1;
+    case 2: launch_tinv_rows<2>(t, e->rows16, pdl, ia, e->n_out, count, st); return 1;
+    case 4: launch_tinv_rows<4>(t, e->rows16, pdl, ia, e->n_out, count, st); return 1;
+    case 8: launch_tinv_rows<8>(t, e->rows16, pdl, ia, e->n_out, count, st); return 1;
+    case 16: launch_tinv_rows<16>(t, e->rows16, pdl, ia, e->n_out, count, st); return 1;
+    case 32: launch_tinv_rows<32>(t, e->rows16, pdl, ia, e->n_out, count, st); return 2;
+    case 64: launch_tinv_rows<64>(t, e->rows16, pdl, ia, e->n_out, count, st); return 2;
     default: launch_k(pdl, k_tier_inverse, dim3(e->n_out, count), dim3(tier_threads(t)), t.S * sizeof(float2), st, ia); return 1;
     }
 }
@@ -1321,6 +1333,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     e->arena_bytes = 0;
     const bool legacy_fft = (cfg->flags & CA_FLAG_LEGACY_FFT) != 0;
     e->rows0 = !legacy_fft && e->B == 256;
+    e->rows16 = !(cfg->schedule & CA_SCHED_ROWS8) && !(getenv("CA_ROWS16") && getenv("CA_ROWS16")[0] == '0');
     for (size_t j = 0; j < e->tiers.size(); j++) {
         Tier &t = e->tiers[j];
         t.s_log = t.S >= 256 ? ilog2(t.S / 256) : 0;
@@ -1455,12 +1468,14 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     CA_CUDA(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
     CA_CUDA(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
     {
-        // twiddles of the 256-point row FFT, fp64 -> fp32: [W_256^n | W_512^k]
-        std::vector<float2> tw(512);
+        // twiddles of the 256-point row FFT, fp64 -> fp32: [W_256^n | W_512^k | W_256^(l q) at q * 16 + l]
+        std::vector<float2> tw(768);
         for (int n = 0; n < 256; n++) {
             const double a = -2.0 * M_PI * n / 256.0, b = -2.0 * M_PI * n / 512.0;
+            const double c = -2.0 * M_PI * (((n >> 4) * (n & 15)) % 256) / 256.0;  // between the radix-16 stages (fft_rows16.cuh)
             tw[n] = make_float2((float)cos(a), (float)sin(a));
             tw[256 + n] = make_float2((float)cos(b), (float)sin(b));
+            tw[512 + n] = make_float2((float)cos(c), (float)sin(c));
         }
         CA_CUDA(cudaMalloc(&e->d_rowtw, tw.size() * sizeof(float2)));
         CA_CUDA(cudaMemcpyAsync(e->d_rowtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));

@@ -21,7 +21,7 @@ FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 
 FLAG_ASYNC_TIERS = 32
 FLAG_LEGACY_FFT = 64
 FLAG_PERSISTENT = 128
-SCHED_MAC_PERSISTENT, SCHED_MAC_PER_ITEM, SCHED_FUSED_TIER0, SCHED_NO_FUSED_TIER0, SCHED_PIPELINED, SCHED_NO_PDL = 1, 2, 4, 8, 16, 32
+SCHED_MAC_PERSISTENT, SCHED_MAC_PER_ITEM, SCHED_FUSED_TIER0, SCHED_NO_FUSED_TIER0, SCHED_PIPELINED, SCHED_NO_PDL, SCHED_ROWS8 = 1, 2, 4, 8, 16, 32, 64
 
 EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",

@@ -80,7 +80,9 @@ enum ca_schedule {
     CA_SCHED_FUSED_TIER0 = 1u << 2,      /* tier 0 as ONE kernel per instance (forward + MAC + inverse) */
     CA_SCHED_NO_FUSED_TIER0 = 1u << 3,
     CA_SCHED_PIPELINED = 1u << 4,        /* two-lane batch schedule: FFT lanes beside the MAC lane (measured slower end to end) */
-    CA_SCHED_NO_PDL = 1u << 5            /* no programmatic dependent launch between the period's kernels */
+    CA_SCHED_NO_PDL = 1u << 5,           /* no programmatic dependent launch between the period's kernels */
+    CA_SCHED_ROWS8 = 1u << 6             /* A/B: 256-point row FFTs as 8 x 8 x 4, one row per warp (round 2's first row
+                                          * family) instead of 16 x 16, two rows per warp */
 };
 
 typedef struct ca_engine ca_engine;

@@ -147,3 +147,37 @@ def test_two_stage_column_dft_and_row_pairing(M1):
             rows.append(r)
             assert (M1 - r) % M1 in (r, row_of(rg, warp ^ 1))
     assert sorted(rows) == list(range(M1))
+
+
+# ---- 16 x 16 row-FFT family (fft_rows16.cuh / kernels_rows16.cuh) ----------------------------------
+def test_row_fft_16x16_matches_numpy_and_is_bank_conflict_free():
+    from tests import _rows16_fft_model as R
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    regs, worst = R.fft256x2(x)
+    assert np.abs(R.natural(regs) - np.fft.fft(x)).max() < 1e-12
+    assert worst == 1
+    regs, _ = R.fft256x2(x, inv=True)
+    assert np.abs(R.natural(regs) - np.fft.ifft(x) * 256).max() < 1e-12
+    assert R.SLOTS >= 256
+
+
+@pytest.mark.parametrize("M1", [1, 2, 8, 16, 64])
+def test_shuffle_split_partners_are_the_conjugate_bins(M1):
+    """every (lane, register) of every warp receives bin M - k of its own bin k = k1 + M1 k2 (k2 = l + 16 p)"""
+    from tests import _rows16_fft_model as R
+    M = 256 * M1
+    Z = np.arange(M, dtype=float) + 1j * 0.0      # the value of bin k is k itself
+    def row_regs(r):
+        return [[Z[r + M1 * (l + 16 * p)] for p in range(16)] for l in range(16)]
+    seen = set()
+    for pi in range(max(1, M1 // 2)):
+        rows = [R.x2_row(M1, pi, h) if M1 > 1 else 0 for h in range(2)]
+        parts = R.warp_partners(M1, pi, [row_regs(rows[0]), row_regs(rows[1])])
+        for h in range(2):
+            for l in range(16):
+                for p in range(16):
+                    k = rows[h] + M1 * (l + 16 * p)
+                    assert parts[h][l][p].real == (M - k) % M, (M1, pi, h, l, p)
+            seen.add(rows[h])
+    assert seen == set(range(M1))

@@ -450,8 +450,8 @@ def test_row_fft_family_matches_legacy_and_fp64(B, tiers):
     pr = [dict(wet=0.9, dry=0.2, level=0.8, panWet=0.2, panDry=-0.3), dict(wet=0.7, dry=0.1, level=1.0, panWet=-0.4, panDry=0.1)]
     t_switch = (n // B) // 2
 
-    def go(flags):
-        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, flags=flags) as e:
+    def go(flags, schedule=0):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, tiers=tiers, flags=flags, schedule=schedule) as e:
             for s in range(K):
                 for i in range(2):
                     e.load_ir(2 * s + i, irs[s][i][0], irs[s][i][1])
@@ -464,10 +464,11 @@ def test_row_fft_family_matches_legacy_and_fp64(B, tiers):
                 out[:, :, t * B:(t + 1) * B] = e.process(x[:, :, t * B:(t + 1) * B])
             return out
 
-    y_new, y_old = go(0), go(m.FLAG_LEGACY_FFT)
+    y_new, y_old, y_r8 = go(0), go(m.FLAG_LEGACY_FFT), go(0, m.SCHED_ROWS8)   # 16 x 16 rows (default), round-1 kernels, 8 x 8 x 4 rows
     for s in range(K):
         for o in range(2):
             assert O.rel_l2(y_new[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_new[s, o], y_old[s, o]))
+            assert O.rel_l2(y_r8[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_r8[s, o], y_old[s, o]))
     for s in range(2):
         truth = O.engine_truth(x[s], irs[s], pr, predelay=5 + 40 * s)
         for o in range(2):
@@ -483,8 +484,8 @@ def test_row_fft_tier0_uniform_matches_legacy():
     n = B * 60
     x = np.stack([np.stack([O.synth_audio(n, 7400 + 2 * s + i, rms=0.5) for i in range(2)]) for s in range(K)])
 
-    def go(flags):
-        with m.Engine(period=B, max_ir_frames=L, n_instances=K, flags=flags) as e:
+    def go(flags, schedule=0):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, flags=flags, schedule=schedule) as e:
             for i in range(2):
                 e.load_ir(i, 2.0 * irs[i][0], 2.0 * irs[i][1])
             for s in range(K):
@@ -493,11 +494,12 @@ def test_row_fft_tier0_uniform_matches_legacy():
                     e.set_glide(s, i, 0.9)
             return e.render(x)
 
-    y_new, y_old = go(0), go(m.FLAG_LEGACY_FFT)
+    y_new, y_old, y_r8 = go(0), go(m.FLAG_LEGACY_FFT), go(0, m.SCHED_ROWS8)
     assert (np.abs(y_new) > 0.999).sum() > 50          # clamp fires
     for s in range(K):
         for o in range(2):
             assert O.rel_l2(y_new[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_new[s, o], y_old[s, o]))
+            assert O.rel_l2(y_r8[s, o], y_old[s, o]) < 2e-6, (s, o, O.rel_l2(y_r8[s, o], y_old[s, o]))
 
 
 def test_shared_voice_pool_crossfades_and_exhaustion():
@@ -615,3 +617,31 @@ def test_sm_split_green_contexts_bit_identical():
             pytest.skip("green contexts not available: " + str(ex))
         raise
     assert np.array_equal(y_split, go())
+
+
+def test_rows16_mono_odd_batch_idle_half_warps():
+    """kernels_rows16.cuh maps one HALF-warp to an (instance, input | output) item: a mono batch of 3 leaves the last
+    warp with an idle half, and neighbouring halves carry different predelays (one zero, one not).  Tiered, against
+    fp64 and against the 8 x 8 x 4 row kernels."""
+    m = ca()
+    B, K = 256, 3
+    tiers = [(256, 4), (1024, 4), (4096, 0)]
+    L = 256 * 4 + 1024 * 4 + 4096 * 3 - 5
+    n = B * 120
+    hs = [O.synth_ir(L, 48000, 7500 + s) for s in range(K)]
+    x = np.stack([O.synth_audio(n, 7600 + s)[None, :] for s in range(K)])
+    pds = (0, 300, 8191)
+
+    def go(schedule):
+        with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_in=1, n_out=1, n_ir_slots=K, tiers=tiers, schedule=schedule) as e:
+            for s in range(K):
+                e.load_ir(s, hs[s])
+                e.set_params(s, 0, select=s, predelay=pds[s], wet=0.8, dry=0.1)
+                e.set_glide(s, 0, 0.8)
+            return e.render(x)
+
+    y, y8 = go(0), go(m.SCHED_ROWS8)
+    for s in range(K):
+        truth = O.engine_truth(x[s], [[hs[s]]], [dict(wet=0.8, dry=0.1)], predelay=pds[s])
+        assert O.rel_l2(y[s, 0], truth[0]) < 5e-6, (s, O.rel_l2(y[s, 0], truth[0]))
+        assert O.rel_l2(y[s, 0], y8[s, 0]) < 2e-6, (s, O.rel_l2(y[s, 0], y8[s, 0]))
