@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "kernels_rows.cuh"
 #include "kernels_rows16.cuh"
+#include "kernels_quirks.cuh"
 #include "kernels_persist.cuh"
 
 #include <cuda.h>  // types + prototypes only: driver entry points are resolved through the runtime (no libcuda link dependency)
@@ -283,6 +284,11 @@ struct ca_engine {
         int *gerr = nullptr;
     } link;
     float2 *d_rowtw = nullptr;  // [W_256^n | W_512^k]: twiddles of the 256-point row FFT
+    // CA_FLAG_REF_QUIRKS (kernels_quirks.cuh)
+    bool quirks = false;
+    double *d_irsum = nullptr, *d_qdelta = nullptr, *d_qrun = nullptr;
+    float *d_qring = nullptr;
+    uint32_t q_kr = 0, q_len = 0;
     // CA_FLAG_PERSISTENT (kernels_persist.cuh)
     bool persistent = false, p_running = false;
     PersistBox *pbox = nullptr;            // mapped pinned host memory
@@ -518,7 +524,7 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     ma.inst0 = i0; ma.tend_host = tp1;
     ma.gather = e->link.gather; ma.gflag = e->link.gflag; ma.gcount = e->link.gcount;
     InvArgs ia{t0.Ypart, d_in, d_out, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_ctl, t0.tw, t0.tw + e->B,
-               t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, tp1};
+               t0.n_split, e->n_in, e->n_out, e->acc_len, (i1 - i0) * e->n_out, i0 * e->n_out, last ? 1u : 0u, ((e->cfg.flags & CA_FLAG_RAW_WET) || e->quirks) ? 1u : 0u, tp1};
     if (e->link.inv_src) { ia.Ypart = e->link.inv_src; ia.n_split = e->link.inv_split; ia.wait_flags = e->link.wait_flags; ia.n_wait = e->link.n_wait; ia.gerr = e->link.gerr; }
     if (e->fused) {
         // tiered throughput schedule: forward + MAC + inverse of tier 0 in one CTA per instance
@@ -541,6 +547,11 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
     if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
     if (e->link.skip_inverse) { if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl); }  // group peer: only the period counter advances
     else if (!e->link.defer_inverse) launch_inv0(e, pdl, ia, e->stream);
+    if (e->quirks) {  // reference-compatible DC / Nyquist terms, then clamp + dry mix (the inverse above stored the raw wet block)
+        QuirkArgs qa{d_in, d_out, e->d_par, e->d_st, e->d_ctl, e->d_irsum, e->d_qdelta, e->d_qrun, e->d_qring,
+                     n_alloc, e->nv, e->B, e->cfg.ref_fft_size, e->q_kr, e->q_len, i0, i1 - i0, tp1};
+        k_ref_quirks<<<(i1 - i0 + kQuirkWarps - 1) / kQuirkWarps, kQuirkWarps * 32, 0, e->stream>>>(qa);
+    }
     if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
     CA_CUDA(cudaGetLastError());
     return CA_OK;
@@ -684,7 +695,7 @@ int run_period(ca_engine *e, const float *d_in, float *d_out)
         rc = launch_period(e, d_in, d_out, profile, 0, e->n_active, true);
         if (rc) return rc;
     }
-    e->launches += e->fused ? 2 : 3;
+    e->launches += (e->fused ? 2 : 3) + (e->quirks ? 1 : 0);
     return CA_OK;
 }
 
@@ -1212,6 +1223,7 @@ int ca_destroy(ca_engine *e)
     for (auto &t : e->tiers) { cudaFree(t.Ypart); cudaFree(t.Ypart2); cudaFree(t.tw); cudaFree(t.workctr); }
     cudaFree(e->d_arena); cudaFree(e->d_ring); cudaFree(e->d_acc);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_par); cudaFree(e->d_st); cudaFree(e->d_ctl); cudaFree(e->d_rowtw); cudaFree(e->d_vpool);
+    cudaFree(e->d_irsum); cudaFree(e->d_qdelta); cudaFree(e->d_qrun); cudaFree(e->d_qring);
     cudaFree(e->d_go); cudaFree(e->d_arrive); cudaFree(e->d_ppar); cudaFree(e->d_pY); cudaFree(e->d_pYsum);
     if (e->pbox) cudaFreeHost(e->pbox);
     cudaFreeHost(e->h_in); cudaFreeHost(e->h_out); cudaFreeHost(e->h_upload[0]); cudaFreeHost(e->h_upload[1]);
@@ -1276,6 +1288,15 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     if (const char *c = getenv("CA_IO_CHUNKS")) e->io_chunks = std::max(1, std::min<int>(kIoChunks, atoi(c)));
     int rc = plan_tiers(cfg, e);
     if (rc) return rc;
+    if (cfg->flags & CA_FLAG_REF_QUIRKS) {
+        const uint32_t N = cfg->ref_fft_size;
+        if (e->n_in != 2 || e->n_out != 2 || !N || N % e->B || N < 2 * e->B || cfg->part_begin || cfg->part_count ||
+            (cfg->flags & (CA_FLAG_RAW_WET | CA_FLAG_PERSISTENT)) || (cfg->schedule & CA_SCHED_PIPELINED) || cfg->sm_split) {
+            g_last_error = "CA_FLAG_REF_QUIRKS: true stereo (2 in, 2 out), ref_fft_size a multiple of the period, whole IR, no raw-wet / persistent / pipelined schedule";
+            return CA_ERR_UNSUPPORTED;
+        }
+        e->quirks = true;
+    }
     e->fft = fft_pick((int)e->R);
     int variant = -1;  // -1: per tier by rows per CTA (measured: short row lists want many small CTAs per SM)
     if (const char *v = getenv("CA_MAC_VARIANT")) variant = atoi(v);
@@ -1311,6 +1332,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
     for (auto &ev : e->ptinv_ev) CA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     e->pipe_mode = ((cfg->schedule & CA_SCHED_PIPELINED) || sm_split) ? 1 : 0;
     if (const char *pm = getenv("CA_PIPELINE")) e->pipe_mode = atoi(pm) ? 1 : 0;
+    if (e->quirks) e->pipe_mode = 0;
     e->async_tiers = (cfg->flags & CA_FLAG_ASYNC_TIERS) && e->tiers.size() > 1 && !(cfg->flags & CA_FLAG_PROFILE);
     CA_CUDA(cudaStreamCreateWithPriority(&e->s_def, cudaStreamNonBlocking, prio_lo));
     CA_CUDA(cudaEventCreateWithFlags(&e->ev_period, cudaEventDisableTiming));
@@ -1389,7 +1411,7 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         if (!fz && (cfg->schedule & CA_SCHED_NO_FUSED_TIER0)) fz = "0";
         fused_fn fn = e->n_out == 1 ? e->fft.fused1 : e->fft.fused2;
         e->fused = e->tiers.size() > 1 && fn && e->tiers[0].n_split == 1 && e->tiers[0].tiles == 1 && e->n_in * e->nv <= 4 &&
-                   (fz ? fz[0] == '1' : e->n_inst <= 16);  // measured: -2 us p50 for one instance, but 178 vs 132 us at 4096 instances
+                   !e->quirks && (fz ? fz[0] == '1' : e->n_inst <= 16);  // measured: -2 us p50 for one instance, but 178 vs 132 us at 4096 instances
                                                             // (2 CTAs/SM cannot hide the per-instance FFT latency chain)
         if (e->fused) {
             e->fused_smem = e->n_out == 1 ? (e->R == 8 ? FusedCfg<8, 1>::SMEM_BYTES : e->R == 4 ? FusedCfg<4, 1>::SMEM_BYTES : e->R == 2 ? FusedCfg<2, 1>::SMEM_BYTES : FusedCfg<1, 1>::SMEM_BYTES)
@@ -1480,6 +1502,20 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         CA_CUDA(cudaMalloc(&e->d_rowtw, tw.size() * sizeof(float2)));
         CA_CUDA(cudaMemcpyAsync(e->d_rowtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
         CA_CUDA(cudaStreamSynchronize(e->stream));  // pageable source: staged before `tw` goes out of scope
+    }
+    if (e->quirks) {
+        e->q_kr = cfg->ref_fft_size / e->B + kMaxPredelay / e->B + 4;
+        e->q_len = 1;
+        while (e->q_len < kMaxPredelay + 2 * e->B) e->q_len <<= 1;
+        const size_t nd = (size_t)e->n_inst * e->q_kr * 4, nq = (size_t)e->n_inst * 2 * e->q_len;
+        CA_CUDA(cudaMalloc(&e->d_irsum, (size_t)cfg->n_ir_slots * 4 * sizeof(double)));
+        CA_CUDA(cudaMalloc(&e->d_qdelta, nd * sizeof(double)));
+        CA_CUDA(cudaMalloc(&e->d_qrun, (size_t)e->n_inst * 4 * sizeof(double)));
+        CA_CUDA(cudaMalloc(&e->d_qring, nq * sizeof(float)));
+        CA_CUDA(cudaMemsetAsync(e->d_irsum, 0, (size_t)cfg->n_ir_slots * 4 * sizeof(double), e->stream));
+        CA_CUDA(cudaMemsetAsync(e->d_qdelta, 0, nd * sizeof(double), e->stream));
+        CA_CUDA(cudaMemsetAsync(e->d_qrun, 0, (size_t)e->n_inst * 4 * sizeof(double), e->stream));
+        CA_CUDA(cudaMemsetAsync(e->d_qring, 0, nq * sizeof(float), e->stream));
     }
     CA_CUDA(cudaMallocHost(&e->h_in, in_bytes));
     CA_CUDA(cudaMallocHost(&e->h_out, out_bytes));
@@ -1584,6 +1620,7 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
         if (rc) return rc;
     }
     frames = std::min(frames, e->cfg.max_ir_frames);  // truncation like conv.cu:239
+    if (e->quirks) k_ir_sums<<<1, 256, 0, e->stream>>>(d_left, d_right, frames, stride, e->d_irsum + (size_t)slot * 4);
     for (size_t j = 0; j < e->tiers.size(); j++) {
         const Tier &t = e->tiers[j];
         float2 *H = t.H + (size_t)slot * e->n_out * t.P * t.S;
@@ -1697,6 +1734,12 @@ int ca_set_active(ca_engine *e, uint32_t n)
         k_release_voices<<<(unsigned)((cnt + 127) / 128), 128, 0, e->stream>>>(e->d_st + (e->t_host & 1) * n_alloc + i0, (uint32_t)cnt, voice_pool(e));
         for (int b = 0; b < 2; b++) CA_CUDA(cudaMemsetAsync(e->d_st + b * n_alloc + i0, 0, cnt * sizeof(ItemState), e->stream));
         if (e->d_acc) CA_CUDA(cudaMemsetAsync(e->d_acc + (size_t)e->n_active * e->n_out * e->acc_len, 0, (size_t)(n - e->n_active) * e->n_out * e->acc_len * sizeof(float), e->stream));
+        if (e->quirks) {
+            const size_t a0 = e->n_active, na = n - e->n_active;
+            CA_CUDA(cudaMemsetAsync(e->d_qdelta + a0 * e->q_kr * 4, 0, na * e->q_kr * 4 * sizeof(double), e->stream));
+            CA_CUDA(cudaMemsetAsync(e->d_qrun + a0 * 4, 0, na * 4 * sizeof(double), e->stream));
+            CA_CUDA(cudaMemsetAsync(e->d_qring + a0 * 2 * e->q_len, 0, na * 2 * e->q_len * sizeof(float), e->stream));
+        }
         CA_CUDA(cudaStreamSynchronize(e->stream));
     }
     e->n_active = n;

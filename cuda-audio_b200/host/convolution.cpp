@@ -21,6 +21,7 @@ EngineOptions EngineOptions::fromEnv()
     if (const char *v = getenv("CA_ENGINE_PERIOD")) o.period = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED")) o.shared = (uint32_t)atoi(v);
     if (truthy(getenv("CA_ENGINE_ASYNC_TIERS"))) o.flags |= CA_FLAG_ASYNC_TIERS;
+    if (truthy(getenv("CA_ENGINE_REF_QUIRKS"))) o.flags |= CA_FLAG_REF_QUIRKS;
     if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;  // batches: host-driven launches + PDL
     return o;
 }
@@ -41,6 +42,8 @@ EngineOptions EngineOptions::fromSettings(Settings &st)
     flag("engine.graph", CA_FLAG_GRAPH, (o.flags & CA_FLAG_GRAPH) != 0);
     flag("engine.async_tiers", CA_FLAG_ASYNC_TIERS, (o.flags & CA_FLAG_ASYNC_TIERS) != 0);
     flag("engine.l2_persist", CA_FLAG_L2_PERSIST, (o.flags & CA_FLAG_L2_PERSIST) != 0);
+    // the reference's DC / Nyquist bins (conv.cu:47-73) reproduced for its fftSize: bit-compatible sound on any IR
+    flag("engine.ref_quirks", CA_FLAG_REF_QUIRKS, (o.flags & CA_FLAG_REF_QUIRKS) != 0);
     if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;
     return o;
 }
@@ -159,6 +162,10 @@ bool Convolution::buildEngine(size_t period)
     cfg.max_ir_frames = (uint32_t)longest;
     cfg.n_ir_slots = (uint32_t)(_irs.rbegin()->first + 1);
     cfg.flags = _opt.flags;
+    if (cfg.flags & CA_FLAG_REF_QUIRKS) {
+        if (_fftSize % period == 0 && _fftSize >= 2 * period) cfg.ref_fft_size = (uint32_t)_fftSize;  // Convolution(name, fftSize), conv.cu:142
+        else cfg.flags &= ~(uint32_t)CA_FLAG_REF_QUIRKS;  // the reference itself only works for such sizes
+    }
     cfg.max_voices = 3;  // old IR + new IR + one more switch in flight during a cross-fade
     cfg.sample_rate = samplerate ? (float)samplerate : _sampleRate;
     if (_opt.autoTiers && ca_config_auto_tiers(&cfg, _opt.tierGrowth, _opt.tierMaxBlock) != CA_OK) { fail(CA_ERR_INVALID, "ca_config_auto_tiers"); return false; }

@@ -21,6 +21,7 @@ FLAG_GRAPH, FLAG_STREAMING, FLAG_L2_PERSIST, FLAG_PROFILE, FLAG_RAW_WET = 1, 2, 
 FLAG_ASYNC_TIERS = 32
 FLAG_LEGACY_FFT = 64
 FLAG_PERSISTENT = 128
+FLAG_REF_QUIRKS = 256
 SCHED_MAC_PERSISTENT, SCHED_MAC_PER_ITEM, SCHED_FUSED_TIER0, SCHED_NO_FUSED_TIER0, SCHED_PIPELINED, SCHED_NO_PDL, SCHED_ROWS8 = 1, 2, 4, 8, 16, 32, 64
 
 EXPORTS = [
@@ -46,7 +47,7 @@ class Config(C.Structure):
                 ("max_ir_frames", C.c_uint32), ("n_ir_slots", C.c_uint32), ("flags", C.c_uint32),
                 ("mac_split", C.c_uint32), ("max_voices", C.c_uint32), ("part_begin", C.c_uint32), ("part_count", C.c_uint32),
                 ("n_tiers", C.c_uint32), ("tier_block", C.c_uint32 * CA_MAX_TIERS),
-                ("tier_parts", C.c_uint32 * CA_MAX_TIERS), ("sample_rate", C.c_float), ("voice_pool", C.c_uint32), ("schedule", C.c_uint32), ("io_chunks", C.c_uint32), ("sm_split", C.c_uint32)]
+                ("tier_parts", C.c_uint32 * CA_MAX_TIERS), ("sample_rate", C.c_float), ("voice_pool", C.c_uint32), ("schedule", C.c_uint32), ("io_chunks", C.c_uint32), ("sm_split", C.c_uint32), ("ref_fft_size", C.c_uint32)]
 
 
 class Params(C.Structure):
@@ -190,11 +191,11 @@ class Engine:
 
     def __init__(self, period=256, max_ir_frames=130048, n_instances=1, n_in=2, n_out=2, n_ir_slots=2, device=0,
                  flags=0, mac_split=0, part_begin=0, part_count=0, sample_rate=48000.0, tiers=None, max_voices=0, tier_growth=0,
-                 tier_max_block=0, voice_pool=0, schedule=0, io_chunks=0, sm_split=0):
+                 tier_max_block=0, voice_pool=0, schedule=0, io_chunks=0, sm_split=0, ref_fft_size=0):
         kw = dict(period=period, max_ir_frames=max_ir_frames, n_instances=n_instances, n_in=n_in, n_out=n_out,
                   n_ir_slots=n_ir_slots, device=device, flags=flags, mac_split=mac_split, part_begin=part_begin,
                   part_count=part_count, sample_rate=sample_rate, max_voices=max_voices, voice_pool=voice_pool, schedule=schedule,
-                  io_chunks=io_chunks, sm_split=sm_split)
+                  io_chunks=io_chunks, sm_split=sm_split, ref_fft_size=ref_fft_size)
         if tiers and tiers != "auto":
             kw.update(n_tiers=len(tiers), tier_block=[t[0] for t in tiers], tier_parts=[t[1] for t in tiers])
         self.cfg = default_config(**kw)

@@ -69,6 +69,12 @@ enum ca_flags {
                                    * uniformly partitioned instance (period <= 256); ca_process only writes the
                                    * block + parameters and spins on the answer.  The kernel leaves by itself after
                                    * ~1 s of silence and is relaunched by the next call.  ca_process only. */
+    CA_FLAG_REF_QUIRKS = 1u << 8, /* reference-compatible DC / Nyquist bins: the reference's two-for-one FFT
+                                   * split mis-unpacks bin 0 and never writes bin N/2 (conv.cu:47-73); the exact engine
+                                   * matches it only for DC/Nyquist-free IRs.  With this flag the engine adds the
+                                   * per-block rank-1 terms those two bins produce in an N-point reference
+                                   * (N = ca_config.ref_fft_size), so its output equals conv.cu's on ANY impulse
+                                   * response.  True stereo only. */
     CA_FLAG_LEGACY_FFT = 1u << 6  /* A/B: transforms on the warp-shuffle / whole-transform-per-CTA FFT kernels
                                    * of round 1 instead of the row-FFT family (same layouts, same results
                                    * to fp32 rounding) */
@@ -126,6 +132,7 @@ typedef struct ca_config {
     /* Batches: give the (memory-bound) MAC lane its own `sm_split` SMs and the (latency-bound) FFT lanes the rest
      * (CUDA green contexts), and run the two-lane pipelined schedule on them.  0 = off. */
     uint32_t sm_split;
+    uint32_t ref_fft_size;  /* CA_FLAG_REF_QUIRKS: the reference's fftSize (Convolution::Convolution, conv.cu:142) */
 } ca_config;
 
 /* Per-input parameter block == Convolution::CC::value (conv.h:40-50). */

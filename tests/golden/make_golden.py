@@ -58,6 +58,13 @@ def case_inputs(name):
         # (period, input, cc-field 1..8 (select, predelay, dry, wet, speed, panDry, panWet, level), 7-bit value)
         events = [(100, 0, 1, 127 * 2 // 3 + 1), (160, 1, 4, 64), (200, 1, 1, 0)]
         return N, B, irs, x, cc, events
+    if name == "E":   # not a golden: unconstrained IRs below the clamp, for the live drop-in comparison with engine.ref_quirks
+        N, B = 8192, 128
+        L = N - B - 500
+        irs = [[O.synth_ir(L, FS, 1400 + 2 * i + o, parity_safe=False) for o in range(2)] for i in range(2)]
+        x = np.stack([O.synth_audio(B * 150, 2400 + i) for i in range(2)])
+        cc = [dict(select=0, wet=0.9, dry=0.3, panWet=0.2, predelay=333), dict(select=1, wet=0.9, dry=0.3, panWet=-0.3)]
+        return N, B, irs, x, cc, []
     raise KeyError(name)
 
 

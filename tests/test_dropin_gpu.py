@@ -8,6 +8,7 @@ import json
 import os
 import struct
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -65,6 +66,32 @@ def test_same_driver_same_output(name):
     assert O.rel_l2(rl, z["L"]) < 1e-6          # the live reference reproduces its committed golden
     eL, eR = O.rel_l2(ml, rl), O.rel_l2(mr, rr)
     assert eL < TOL_REF and eR < TOL_REF, (name, eL, eR)
+
+
+@needs_libs
+def test_class_api_with_ref_quirks_matches_reference_on_unconstrained_irs():
+    """`engine.ref_quirks` (CA_ENGINE_REF_QUIRKS): through the reference's own class API the mirror reproduces conv.cu's
+    DC / Nyquist bins for the object's fftSize, so raw noise IRs match too.  Own process: the default engine options are
+    read from the environment once."""
+    code = (
+        "import sys, json, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import importlib.util\n"
+        "spec = importlib.util.spec_from_file_location('t', %r); t = importlib.util.module_from_spec(spec); spec.loader.exec_module(t)\n"
+        "from oracle import oracle as O\n"
+        "rl, rr, _, _ = t.drive(None, 'E')\n"
+        "ml, mr, _, _ = t.drive(t.DROPIN, 'E')\n"
+        "print(json.dumps([O.rel_l2(ml, rl), O.rel_l2(mr, rr), float(max(abs(rl).max(), abs(rr).max()))]))\n"
+    ) % (ROOT, os.path.abspath(__file__))
+    res = {}
+    for quirks in ("0", "1"):
+        env = dict(os.environ, CA_ENGINE_REF_QUIRKS=quirks)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[quirks] = json.loads(out.stdout.strip().split("\n")[-1])
+    assert res["1"][2] < 0.99                                   # below the clamp
+    assert max(res["0"][:2]) > 1e-4, res                        # exact engine: differs by the reference's DC / Nyquist terms
+    assert max(res["1"][:2]) < TOL_REF, res
 
 
 @needs_libs

@@ -409,6 +409,87 @@ def test_restatement_pinned_by_live_reference():
     assert O.rel_l2(cr, rr) < TOL_REF, O.rel_l2(cr, rr)
 
 
+@needs_ref
+@pytest.mark.parametrize("N,B,pd,tiers,graph", [
+    (8192, 128, 0, None, False),          # uniform, no predelay
+    (16384, 256, 301, None, True),        # odd predelay (the Nyquist term changes sign), CUDA graph per period
+    (65536, 256, 8191, "auto", False),    # non-uniform partitioning, maximum predelay
+])
+def test_ref_quirks_match_reference_on_unconstrained_irs(N, B, pd, tiers, graph):
+    """CA_FLAG_REF_QUIRKS: raw white-noise IRs WITHOUT the DC/Nyquist correction, reference defaults
+    plus pan / level / predelay, compared from the first period (fade-in glide included).  The exact engine differs
+    from conv.cu by the DC / Nyquist terms (> 1e-4); with the flag it matches to the reference tolerance."""
+    m = ca()
+    fs = 48000
+    L = N - 2 * B - pd if pd < 4096 else 20000
+    irs = [[O.synth_ir(L, fs, 60 + 2 * i + o, parity_safe=False) for o in range(2)] for i in range(2)]
+    x = np.stack([O.synth_audio(B * 300, 2000 + i) for i in range(2)])
+    cc = [dict(select=0, predelay=pd, wet=0.8, dry=0.4, panWet=0.3, panDry=-0.2, level=0.8), dict(select=1, wet=0.6, dry=0.2, panWet=-0.5, panDry=0.4)]
+    ref = refgpu.RefGpu(N)
+    for i in range(2):
+        ref.prepare(i, irs[i][0], irs[i][1], B)
+        ref.set_cc(i, **cc[i])
+    rl, rr = ref.render(x[0], x[1], B)
+    assert max(np.abs(rl).max(), np.abs(rr).max()) < 0.99      # the clamp (which the reference applies to partial sums) stays out of it
+
+    def go(flags):
+        with m.Engine(period=B, max_ir_frames=L, tiers=tiers, flags=flags, ref_fft_size=N) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, **cc[i])
+            return e.render(x[None])[0]
+
+    y = go(m.FLAG_REF_QUIRKS | (m.FLAG_GRAPH if graph else 0))
+    y_exact = go(0)
+    eq = [O.rel_l2(y[0], rl), O.rel_l2(y[1], rr)]
+    ee = [O.rel_l2(y_exact[0], rl), O.rel_l2(y_exact[1], rr)]
+    assert max(ee) > 1e-4, ee          # the quirks are audible in the difference ...
+    assert max(eq) < TOL_REF, (eq, ee)  # ... and reproduced with the flag
+
+
+@needs_ref
+def test_ref_quirks_follow_an_ir_switch_and_a_batch():
+    """The DC / Nyquist terms glide with the live IR (conv.cu:15-32): mid-run `select` change on unconstrained IRs;
+    second instance of the same engine with other parameters (chunk arguments of the quirk kernel)."""
+    m = ca()
+    fs, N, B = 48000, 8192, 128
+    L = 3000
+    irs = [[O.synth_ir(L, fs, 80 + 2 * i + o, parity_safe=False) for o in range(2)] for i in range(3)]
+    x = np.stack([O.synth_audio(B * 260, 2300 + i) for i in range(2)])
+    ccs = [[dict(select=0, wet=1.0, dry=0.0, speed=40), dict(select=1, wet=1.0, dry=0.0, speed=40)],
+           [dict(select=2, wet=0.5, dry=0.5, predelay=77, panWet=0.4), dict(select=0, wet=0.7, dry=0.1, level=0.6)]]
+    refs = []
+    for cc in ccs:
+        ref = refgpu.RefGpu(N)
+        for s in range(3):
+            ref.prepare(s, irs[s][0], irs[s][1], B)
+        for i in range(2):
+            ref.set_cc(i, **cc[i])
+        refs.append(ref)
+    periods = x.shape[1] // B
+    out_ref = np.zeros((2, 2, periods * B), np.float32)
+    out = np.zeros((2, 2, periods * B), np.float32)
+    with m.Engine(period=B, max_ir_frames=L, n_instances=2, n_ir_slots=3, max_voices=3, flags=m.FLAG_REF_QUIRKS, ref_fft_size=N) as e:
+        for s in range(3):
+            e.load_ir(s, irs[s][0], irs[s][1])
+        for k in range(2):
+            for i in range(2):
+                e.set_params(k, i, **ccs[k][i])
+        for t in range(periods):
+            if t == 100:   # instance 0 cross-fades input 0 to IR 2 over 40 periods (handleCC: vsteps = speed, conv.cu:261)
+                refs[0].set_cc(0, select=2, vsteps=40)
+                e.set_params(0, 0, **dict(ccs[0][0], select=2, vsteps=40))
+            blk = x[:, t * B:(t + 1) * B]
+            for k in range(2):
+                l, r = refs[k].process(blk[0], blk[1])
+                out_ref[k, 0, t * B:(t + 1) * B] = l
+                out_ref[k, 1, t * B:(t + 1) * B] = r
+            out[:, :, t * B:(t + 1) * B] = e.process(np.stack([blk, blk]))
+    for k in range(2):
+        for o in range(2):
+            assert O.rel_l2(out[k, o], out_ref[k, o]) < TOL_REF, (k, o, O.rel_l2(out[k, o], out_ref[k, o]))
+
+
 def test_chunked_host_pipeline_matches_single_stream():
     """>= 512 instances: ca_process pipelines H2D | kernels | D2H in instance chunks on three streams;
     results must equal the device-resident single-stream path bit for bit."""

@@ -121,3 +121,40 @@ def test_handle_cc_mapping_table():
     O.handle_cc(cc, 7, 4, 10)
     assert cc.speed == 32 and cc.vsteps == 32            # vsteps clipped to the new speed
     assert O.pan_gains(0.25) == (0.75, 1.0) and O.pan_gains(-0.25) == (1.0, 0.75)
+
+
+def test_ref_quirk_model_rank1_terms_explain_the_reference():
+    """The model behind CA_FLAG_REF_QUIRKS (cuda-audio_b200/csrc/kernels_quirks.cuh): the pinned restatement of
+    conv.cu on UNCONSTRAINED IRs equals the exact convolution plus, per input block t, a constant D and an
+    alternating E (-1)^(s - pd) over accumulator samples [tB + pd, tB + N)."""
+    fs, N, B, pd = 48000, 4096, 64, 301
+    L = N - B - 700
+    irs = [[O.synth_ir(L, fs, 50 + 2 * i + o, parity_safe=False) for o in range(2)] for i in range(2)]
+    warm = 100
+    x = np.stack([np.concatenate([np.zeros(warm * B, np.float32), O.synth_audio(B * 200, 2000 + i)]) for i in range(2)])
+    pr = [dict(wet=0.9, level=0.8, panWet=0.3), dict(wet=0.7, panWet=-0.5)]
+    cpu = O.RefConv(N)
+    for i in range(2):
+        cpu.prepare(i, irs[i][0], irs[i][1], B)
+        cpu.set_cc(i, select=i, dry=0.0, predelay=pd if i == 0 else 0, **pr[i])
+    cl, cr = cpu.render(x[0], x[1], B)
+    truth = O.engine_truth(x, irs, pr, predelay=pd)
+    n = x.shape[1]
+    sg = (-1.0) ** np.arange(N)
+    hs = [[(irs[i][o].astype(np.float64).sum(), (irs[i][o].astype(np.float64) * sg[:L]).sum()) for o in range(2)] for i in range(2)]
+    s = [[O.pan_gains(pr[i].get("panWet", 0.0))[o] * pr[i].get("level", 1.0) / N for o in range(2)] for i in range(2)]
+    A = [[pr[i]["wet"] * hs[i][o][0] for o in range(2)] for i in range(2)]     # converged glide: c = wet
+    Ap = [[pr[i]["wet"] * hs[i][o][1] for o in range(2)] for i in range(2)]
+    corr = np.zeros((2, n + N + B))
+    for t in range(n // B):
+        blk = x[:, t * B:(t + 1) * B].astype(np.float64)
+        a, ap = blk.sum(axis=1), (blk * sg[:B]).sum(axis=1)
+        D = [-(s[0][0] * a[1] * A[0][1] + s[1][0] * a[1] * A[1][0]), -(s[0][1] * a[0] * A[0][1] + s[1][1] * a[1] * A[1][1])]
+        E = [-(s[0][o] * ap[0] * Ap[0][o] + s[1][o] * ap[1] * Ap[1][o]) for o in range(2)]
+        lo, hi = t * B + pd, t * B + N
+        for o in range(2):
+            corr[o, lo:hi] += D[o] + E[o] * sg[:hi - lo]
+    sl = slice(warm * B, n)
+    for o, r in enumerate((cl, cr)):
+        assert O.rel_l2(r[sl], truth[o][sl]) > 1e-3                       # the quirks matter on such IRs
+        assert O.rel_l2(r[sl], truth[o][sl] + corr[o][sl]) < 1e-6         # and the rank-1 terms are all of it
