@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     import cuda_audio_b200 as m
     # ca_config: 14 u32/i32 + 2*4 u32 + float + voice_pool + schedule + io_chunks + sm_split = 27 words ; ca_params: 9 words
-    assert ctypes.sizeof(m.Config) == 27 * 4
+    assert ctypes.sizeof(m.Config) == 28 * 4
     assert ctypes.sizeof(m.Params) == 9 * 4
     cfg = m.default_config()
     assert cfg.struct_size == ctypes.sizeof(m.Config)
