@@ -19,7 +19,7 @@
 // below keeps their running sums per (instance, output): a block's terms join at the first period boundary after
 // tB + pd and leave at tB + N (a period boundary); the part of the starting period goes through a small ring.
 // It also finishes the block: clamp(wet + correction) + dry mix -- tier 0's inverse kernel runs in raw-wet mode.
-// Checked in fp64 against the pinned restatement (tests/test_oracle_cpu.py::test_ref_quirk_model_*) and on the GPU
+// Checked in fp64 against the pinned CPU restatement of conv.cu (tests: test_ref_quirk_model_*) and on the GPU
 // against the live reference (tests/test_engine_gpu.py::test_ref_quirks_*).
 #pragma once
 #include "kernels.cuh"
