@@ -1716,34 +1716,50 @@ int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g)
     return CA_OK;
 }
 
+// instances [a0, a1) start like new ones: voices restart at the current period (so every older delay-line block is
+// skipped, and a voice's first forward clears its time ring), pending tier output and the reference-compatibility
+// terms are dropped; shared cross-fade voices go back to the pool.  The engine must be drained.
+static int reset_instances(ca_engine *e, size_t a0, size_t a1)
+{
+    if (a1 <= a0) return CA_OK;
+    const size_t i0 = a0 * e->n_in, cnt = (a1 - a0) * e->n_in, n_alloc = (size_t)e->n_inst * e->n_in, na = a1 - a0;
+    k_release_voices<<<(unsigned)((cnt + 127) / 128), 128, 0, e->stream>>>(e->d_st + (e->t_host & 1) * n_alloc + i0, (uint32_t)cnt, voice_pool(e));
+    for (int b = 0; b < 2; b++) CA_CUDA(cudaMemsetAsync(e->d_st + b * n_alloc + i0, 0, cnt * sizeof(ItemState), e->stream));
+    if (e->d_acc) CA_CUDA(cudaMemsetAsync(e->d_acc + a0 * e->n_out * e->acc_len, 0, na * e->n_out * e->acc_len * sizeof(float), e->stream));
+    if (e->quirks) {
+        CA_CUDA(cudaMemsetAsync(e->d_qdelta + a0 * e->q_kr * 4, 0, na * e->q_kr * 4 * sizeof(double), e->stream));
+        CA_CUDA(cudaMemsetAsync(e->d_qrun + a0 * 4, 0, na * 4 * sizeof(double), e->stream));
+        CA_CUDA(cudaMemsetAsync(e->d_qring + a0 * 2 * e->q_len, 0, na * 2 * e->q_len * sizeof(float), e->stream));
+    }
+    CA_CUDA(cudaStreamSynchronize(e->stream));
+    return CA_OK;
+}
+
 int ca_set_active(ca_engine *e, uint32_t n)
 {
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
     if (n == e->n_active) return CA_OK;
     if (e->persistent) return CA_ERR_UNSUPPORTED;
+    int rc = drain_all(e);
+    if (rc) return rc;
+    CA_CUDA(cudaStreamSynchronize(e->stream));
+    // instances that were parked keep frozen voice state, delay lines and tier output: a reactivated instance must
+    // not replay pre-deactivation audio as a tail
+    rc = reset_instances(e, e->n_active, n);
+    if (rc) return rc;
+    e->n_active = n;
+    return prewarm_graphs(e);  // not a real-time call: rebuild the graphs for the new batch size now
+}
+
+int ca_reset(ca_engine *e)
+{
+    if (!e) return CA_ERR_INVALID;
+    if (e->persistent) return CA_ERR_UNSUPPORTED;
+    CA_CUDA(cudaSetDevice(e->device));
     const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
-    if (n > e->n_active) {
-        // instances that were parked keep frozen voice state, delay lines and tier output: a reactivated
-        // instance must start like a new one (voices restart at the current period, so every older
-        // delay-line block is skipped, and the voice's first forward clears its time ring) instead of
-        // replaying pre-deactivation audio as a tail
-        const size_t i0 = (size_t)e->n_active * e->n_in, cnt = (size_t)(n - e->n_active) * e->n_in, n_alloc = (size_t)e->n_inst * e->n_in;
-        // shared cross-fade voices the parked items still hold go back to the pool first
-        k_release_voices<<<(unsigned)((cnt + 127) / 128), 128, 0, e->stream>>>(e->d_st + (e->t_host & 1) * n_alloc + i0, (uint32_t)cnt, voice_pool(e));
-        for (int b = 0; b < 2; b++) CA_CUDA(cudaMemsetAsync(e->d_st + b * n_alloc + i0, 0, cnt * sizeof(ItemState), e->stream));
-        if (e->d_acc) CA_CUDA(cudaMemsetAsync(e->d_acc + (size_t)e->n_active * e->n_out * e->acc_len, 0, (size_t)(n - e->n_active) * e->n_out * e->acc_len * sizeof(float), e->stream));
-        if (e->quirks) {
-            const size_t a0 = e->n_active, na = n - e->n_active;
-            CA_CUDA(cudaMemsetAsync(e->d_qdelta + a0 * e->q_kr * 4, 0, na * e->q_kr * 4 * sizeof(double), e->stream));
-            CA_CUDA(cudaMemsetAsync(e->d_qrun + a0 * 4, 0, na * 4 * sizeof(double), e->stream));
-            CA_CUDA(cudaMemsetAsync(e->d_qring + a0 * 2 * e->q_len, 0, na * 2 * e->q_len * sizeof(float), e->stream));
-        }
-        CA_CUDA(cudaStreamSynchronize(e->stream));
-    }
-    e->n_active = n;
-    return prewarm_graphs(e);  // not a real-time call: rebuild the graphs for the new batch size now
+    return reset_instances(e, 0, e->n_active);
 }
 
 int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nframes)

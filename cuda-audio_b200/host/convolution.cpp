@@ -108,6 +108,7 @@ bool Convolution::buildNow(size_t period)
     memset(_in, 0, 2 * period * sizeof(float));
     const int rc = ca_process(_engine, _in, _out, (uint32_t)period);
     if (rc) { fail(rc, "ca_process (warm-up)"); return false; }
+    ca_reset(_engine);  // the warm-up period must not count as the first step of the fade-in glide (conv.cu:15-32)
     return true;
 }
 

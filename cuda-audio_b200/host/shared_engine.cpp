@@ -89,6 +89,7 @@ bool SharedEngine::build(size_t period, float sampleRate)
     memset(_in, 0, bytes);
     memset(_out, 0, bytes);
     if (ca_process(_engine, _in, _out, (uint32_t)period) != CA_OK) { ca_destroy(_engine); _engine = nullptr; return false; }  // warm-up
+    ca_reset(_engine);  // ... which must not count as the first step of the fade-in glide
     _dirty.store(false, std::memory_order_release);
     _ok.store(true, std::memory_order_release);
     return true;

@@ -26,7 +26,7 @@ SCHED_MAC_PERSISTENT, SCHED_MAC_PER_ITEM, SCHED_FUSED_TIER0, SCHED_NO_FUSED_TIER
 
 EXPORTS = [
     "ca_api_version", "ca_strerror", "ca_last_error_string", "ca_config_init", "ca_config_auto_tiers", "ca_create", "ca_destroy",
-    "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active",
+    "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active", "ca_reset",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
     "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs", "ca_persist_stamps",
     "ca_group_config_init", "ca_group_create", "ca_group_destroy", "ca_group_load_ir", "ca_group_set_params", "ca_group_set_glide",
@@ -120,6 +120,7 @@ def lib():
         L.ca_get_params.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(Params)]
         L.ca_set_glide.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_float]
         L.ca_set_active.argtypes = [vp, C.c_uint32]
+        L.ca_reset.argtypes = [vp]
         L.ca_process.argtypes = [vp, vp, vp, C.c_uint32]
         L.ca_process_device.argtypes = [vp, vp, vp, C.c_uint32]
         L.ca_sync.argtypes = [vp]
@@ -253,6 +254,10 @@ class Engine:
 
     def set_glide(self, instance, inp, g):
         _check(lib().ca_set_glide(self._h, instance, inp, g), "ca_set_glide")
+
+    def reset(self):
+        """every active instance restarts like a new one (history dropped, wet glide from silence)"""
+        _check(lib().ca_reset(self._h), "ca_reset")
 
     def set_active(self, n):
         _check(lib().ca_set_active(self._h, n), "ca_set_active")

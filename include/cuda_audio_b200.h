@@ -195,6 +195,11 @@ int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g);
  * output are reset (no replay of pre-deactivation audio); re-apply ca_set_glide to skip their fade-in. */
 int ca_set_active(ca_engine *e, uint32_t n);
 
+/* Every active instance restarts like a new one: the history in the delay lines is dropped, the wet glide starts from
+ * silence again (the state of a fresh reference object, conv.cu:142-195); IR bank and parameters stay.  Not a
+ * real-time call.  The host mirror calls it after its silent warm-up period. */
+int ca_reset(ca_engine *e);
+
 /* One period for every active instance.
  *   in : host, planar [instance][input ][nframes] fp32, contiguous
  *   out: host, planar [instance][output][nframes] fp32, contiguous

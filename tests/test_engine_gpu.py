@@ -704,3 +704,21 @@ def test_random_configurations_vs_fp64(seed):
         for o in range(n_out):
             err = O.rel_l2(y[s, o], truth[o])
             assert err < 5e-6, dict(seed=seed, B=B, L=L, K=K, n_in=n_in, n_out=n_out, mode=str(mode), flags=flags, pd=pd, tiers=[int(st.tier_block[j]) for j in range(st.n_tiers)], s=s, o=o, err=err)
+
+
+def test_reset_restarts_like_a_new_engine():
+    """ca_reset: history dropped, fade-in glide from silence again -- the second render equals the first bit for bit
+    (uniform and tiered; the host mirror relies on it after its silent warm-up period)."""
+    m = ca()
+    fs, B, L = 48000, 256, 256 * 4 + 1024 * 3 + 4096 * 2 - 7
+    irs = make_irs(L, fs, seed0=3100)
+    x = np.stack([O.synth_audio(B * 70, 3200 + i) for i in range(2)])
+    for tiers in (None, [(256, 4), (1024, 3), (4096, 0)]):
+        with m.Engine(period=B, max_ir_frames=L, tiers=tiers) as e:
+            load_true_stereo(e, irs)
+            for i in range(2):
+                e.set_params(0, i, select=i, wet=0.7, dry=0.2, predelay=50 * i)
+            y1 = e.render(x[None])[0]
+            e.reset()
+            y2 = e.render(x[None])[0]
+        assert np.abs(y1).max() > 0.01 and np.array_equal(y1, y2)
