@@ -197,7 +197,7 @@ private:
     uint64_t deq_ = 0;
 };
 
-constexpr uint32_t kIoChunks = 16;  // upper bound; the count used is io_chunks (default 2, env CA_IO_CHUNKS)
+constexpr uint32_t kIoChunks = 16;  // upper bound; the count used is io_chunks (default 3, env CA_IO_CHUNKS)
 
 struct Tier {
     uint32_t S = 0, m = 1, P = 0, off = 0, s_log = 0, bt = 0, tiles = 1, n_split = 1, Lring = 0;
@@ -259,7 +259,7 @@ struct ca_engine {
     std::vector<TraceEv> trace;
     uint64_t trace_at = 0;
     bool tracing = false;
-    uint32_t io_chunks = 2;  // measured at 12 288 instances: 2 chunks 1.178 ms, 3: 1.206, 4: 1.237, 8: 1.316 (device-resident 1.124)
+    uint32_t io_chunks = 3;  // measured at 16 128 instances (16 x 16 row kernels): 2 chunks 1.189 ms, 3: 1.159, 4: 1.172 (device-resident 1.095)
     int upload_idx = 0;
     // parameters: `par` (host shadow of the device blocks) belongs to the processing thread; setters reach it
     // through the lock-free command ring; `user` (what ca_get_params returns) is seqlock-guarded per item
@@ -1163,8 +1163,11 @@ void ca_config_init(ca_config *cfg)
 int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block)
 {
     if (!cfg || !is_pow2(cfg->period) || !cfg->max_ir_frames) return CA_ERR_INVALID;
-    if (!growth) growth = 8;
     if (!max_block) max_block = 16384;
+    // growth 8 keeps the FFT work low (fewest tiers; single instances and short periods); batches gain from growth 4
+    // when four tiers still reach max_block: 256 x 4 | 1024 x 3 | 4096 x 3 | 16384 streams 258 KB per instance-period
+    // instead of 319 KB (measured at 16 128 instances: 1 095 -> 1 046 us per period)
+    if (!growth) growth = (cfg->n_instances >= 512 && (uint64_t)cfg->period * 64 >= max_block && !(cfg->flags & CA_FLAG_ASYNC_TIERS)) ? 4 : 8;
     if (!is_pow2(growth) || growth < 2 || !is_pow2(max_block)) return CA_ERR_INVALID;
     uint32_t n = 0, S = cfg->period, off = 0;
     memset(cfg->tier_block, 0, sizeof(cfg->tier_block));
@@ -1368,7 +1371,10 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /
         // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 4 CTAs per SM (the register limit) of 3 x 12 KB
         // stages (measured r01, K = 4096: tier-0 MAC 83 us with 96 KB, 78 with 4 x 12 KB, 74.5 with 3 x 12 KB)
-        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 6 : 1);
+        // short row lists: 3 x 12 KB ring; tier 0's items are the shortest (8-16 rows of 2 KB arrays) and stream best with a
+        // TWO-stage ring (measured at 16 128 instances: 275 -> 264 us with 8 partitions, 168 -> 154 us with 4; the long
+        // tiers lose 0.3-1 % with it)
+        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? (j == 0 ? 7 : 6) : 1);
         t.mac = mac_pick((int)t.bt, (int)e->n_out, tier_variant);
         CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
         {

@@ -18,6 +18,8 @@ constexpr int kRowsWarps = 8;
 constexpr int kRowsThreads = kRowsWarps * 32;
 constexpr uint32_t kRowsSmem = kRowsWarps * kRowSlots * sizeof(float2);  // 18 432 B
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint32_t brev_s(uint32_t r, uint32_t s_log) { return s_log ? (__brev(r) >> (32 - s_log)) : 0u; }
 
 // ------------------------------------------------------------------------------------------
@@ -363,6 +365,14 @@ __global__ void __launch_bounds__(256, 4) k_tcols_fwd(const TierFwdArgs a)
     pdl_wait();
     constexpr int Mb = M1 / 8;
     __shared__ float2 S[Mb * 8 * 32];
+    if ((blockIdx.x >> 3) == 0 && a.tend_host && threadIdx.x < 2 * M1) {
+        // the window sits behind two dependent round trips (voice state -> storage entry -> ring): pull this CTA's 32
+        // columns of the item's HOME entry (where its voice lives outside cross-fades) into L2 meanwhile
+        const uint32_t item = (a.inst0 + blockIdx.z * a.inst_stride) * a.n_in + blockIdx.y, mask0 = a.ring_len - 1;
+        const uint32_t start0 = (uint32_t)((a.tend_host * (unsigned long long)a.B - 2ull * a.S) & mask0);
+        const uint32_t n1 = threadIdx.x >> 1, half = threadIdx.x & 1;   // 64 floats (two lines) per row of the column block
+        prefetch_l2(a.ring + (size_t)item * a.ring_len + ((start0 + 2u * (256u * n1 + 32u * (blockIdx.x & 7)) + 32u * half) & mask0));
+    }
     const TierCommon c = tier_fwd_common(a, blockIdx.x >> 3, blockIdx.y, blockIdx.z);
     if (!c.active) return;
     const int cc = threadIdx.x & 31, j = threadIdx.x >> 5;

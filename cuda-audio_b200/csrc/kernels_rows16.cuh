@@ -24,8 +24,6 @@ constexpr int kX2Threads = kX2Warps * 32;
 constexpr int kX2Rows = 2 * kX2Warps;
 constexpr uint32_t kX2Smem = kX2Rows * kR16Slots * sizeof(float2);  // 36 864 B
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // item_step_warp_from for a half-warp per item: lane l == 0 of the half owns the side effects
 __device__ __forceinline__ ItemState item_step_half_from(const ItemState &old, ItemState *st, uint32_t n_items_alloc, uint32_t item, const InParamDev &p,
                                                          unsigned long long t, int nv, uint32_t ring_out, const VoicePool &vp, int lane, bool valid)
@@ -249,6 +247,19 @@ template <int M1>
 __device__ __forceinline__ int x2_row(int pi, int h) { return pi == 0 ? (h ? M1 / 2 : 0) : (h ? M1 - pi : pi); }
 __device__ __forceinline__ int x2_partner_half(int pi, int h) { return pi == 0 ? h : (h ^ 1); }
 
+// The window of a forward tier transform sits behind two dependent round trips (period count -> voice state -> storage
+// entry -> ring).  Voice 0's CTA pulls the window of the item's HOME entry (where its voice lives outside cross-fades)
+// into L2 while the state is on its way; `tend` must not need a load (host-driven launches).
+__device__ __forceinline__ void tier_prefetch_home(const TierFwdArgs &a, uint32_t v, uint32_t i, uint32_t z, uint32_t tid, uint32_t nthreads)
+{
+    if (v != 0 || !a.tend_host) return;
+    const uint32_t item = (a.inst0 + z * a.inst_stride) * a.n_in + i;
+    const uint32_t mask = a.ring_len - 1;
+    const uint32_t start = (uint32_t)((a.tend_host * (unsigned long long)a.B - 2ull * a.S) & mask);
+    const float *home = a.ring + (size_t)item * a.ring_len;
+    for (uint32_t line = tid; line < a.S / 16; line += nthreads) prefetch_l2(home + ((start + 32u * line) & mask));  // 2 S floats = S / 16 lines of 128 B
+}
+
 // One CTA of M1 / 2 warps per (voice, input, firing instance): window -> column DFTs -> rows -> split -> FDL slot
 template <int M1>
 __global__ void __launch_bounds__(M1 * 16) k_tfwd_x2(const TierFwdArgs a)
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(M1 * 16) k_tfwd_x2(const TierFwdArgs a)
     pdl_wait();
     extern __shared__ __align__(16) float2 sm[];  // [M1][kR16Slots]
     __shared__ R16Tables tb;
+    tier_prefetch_home(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, M1 * 16);
     const TierCommon c = tier_fwd_common(a, blockIdx.x, blockIdx.y, blockIdx.z);
     if (!c.active) return;  // uniform for the CTA
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, h = lane >> 4, l = lane & 15;

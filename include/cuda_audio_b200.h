@@ -128,7 +128,7 @@ typedef struct ca_config {
     /* Schedule choices that change which kernels run (ca_schedule bits; 0 = the engine picks).  The CA_*
      * environment variables of DESIGN.md section 9 override them and exist for development sweeps only. */
     uint32_t schedule;
-    uint32_t io_chunks;     /* instance chunks of ca_process's H2D | kernels | D2H pipeline for batches; 0 = 2 */
+    uint32_t io_chunks;     /* instance chunks of ca_process's H2D | kernels | D2H pipeline for batches; 0 = 3 */
     /* Batches: give the (memory-bound) MAC lane its own `sm_split` SMs and the (latency-bound) FFT lanes the rest
      * (CUDA green contexts), and run the two-lane pipelined schedule on them.  0 = off. */
     uint32_t sm_split;
@@ -171,7 +171,9 @@ const char *ca_last_error_string(void); /* thread-local detail of the last CUDA 
 
 void ca_config_init(ca_config *cfg); /* zero + struct_size + reference defaults (2x2, period 256) */
 /* Fill n_tiers / tier_block / tier_parts for cfg->period and cfg->max_ir_frames: every tier's block
- * is `growth` (power of two, 0 = 8) times the previous one, up to max_block (0 = 16384). */
+ * is `growth` (power of two) times the previous one, up to max_block (0 = 16384).  growth 0 = the engine picks:
+ * 8, or 4 for batches (n_instances >= 512) whose period reaches max_block in four tiers.  Set n_instances, period,
+ * max_ir_frames and flags before calling. */
 int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block);
 
 int ca_create(const ca_config *cfg, ca_engine **out);

@@ -71,7 +71,8 @@ def test_cfg2_reference_size_uniform_and_tiered(monkeypatch):
 
 def test_batch_2048_tiered_chunked_host_pipeline_vs_fp64():
     """K = 2048 distinct-IR instances, cfg2 geometry, tiers auto + streaming hints, host buffers through
-    ca_process (2-chunk H2D | kernels | D2H pipeline, persistent MAC, side-stream tiers, PDL): 900
+    ca_process (3-chunk H2D | kernels | D2H pipeline, persistent MAC, side-stream tiers, PDL; the tier shape the
+    engine picks for batches: 256 x 4 | 1024 x 3 | 4096 x 3 | 16384): 900
     periods, instances 0 / 1023 / 2047 against the fp64 oracle."""
     import torch
     m = ca()
@@ -105,7 +106,7 @@ def test_batch_2048_tiered_chunked_host_pipeline_vs_fp64():
             xs[:, :, t * B:(t + 1) * B] = xb[picks]
             ys[:, :, t * B:(t + 1) * B] = pout.array[picks]
         st = e.stats()
-        assert st.n_tiers == 3 and st.tier0_fused == 0
+        assert [int(st.tier_block[j]) for j in range(st.n_tiers)] == [256, 1024, 4096, 16384] and st.tier0_fused == 0   # batches: growth 4
         pin.free()
         pout.free()
     pr = [dict(wet=0.8, dry=0.3, panWet=0.25, level=0.9), dict(wet=0.8, dry=0.3, panWet=-0.5, level=0.9)]
