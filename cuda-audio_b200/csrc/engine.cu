@@ -394,12 +394,12 @@ MacArgs mac_args(ca_engine *e, const Tier &t, uint32_t t_bias)
                    e->k_off, t.m, t_bias, t.n_split, (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, 0u, 1u, t.m > 1 ? 1u : 0u};
 }
 
-MacArgs with_workctr(MacArgs ma, const Tier &t) { ma.work_ctr = t.workctr; return ma; }
+MacArgs with_workctr(MacArgs ma, const Tier &t, uint32_t set) { ma.work_ctr = t.workctr + 2u * set; return ma; }  // two sets: launches of alternating chunks may overlap
 constexpr uint32_t kMacDynamicItems = 10;  // work items per CTA from which the persistent MAC hands them out dynamically
 
 // One MAC launch over `count` instances of tier t.  Batches (n_split == 1 and more work items than
 // resident CTA slots) take the persistent schedule: every CTA gets the same number of work items.
-void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st, bool pdl = false)
+void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t st, bool pdl = false, uint32_t ctr_set = 0)
 {
     const uint32_t n_work = count * t.tiles;
     if (t.p_slots && t.n_split == 1 && (t.p_force || n_work > t.p_slots)) {
@@ -407,7 +407,7 @@ void launch_mac(const Tier &t, const MacArgs &ma, uint32_t count, cudaStream_t s
         // many items per CTA: hand them out with a counter (no tail of late CTAs: -4 % per period at 16 128 instances);
         // few: static stride (the counter costs ~3 % when every CTA has the same 7 items anyway)
         const bool dynamic = per >= kMacDynamicItems;
-        launch_k(pdl, t.mac.pfn, dim3((n_work + per - 1) / per), dim3(kMacThreads), t.mac.psmem, st, dynamic ? with_workctr(ma, t) : ma, n_work, t.tiles);
+        launch_k(pdl, t.mac.pfn, dim3((n_work + per - 1) / per), dim3(kMacThreads), t.mac.psmem, st, dynamic ? with_workctr(ma, t, ctr_set) : ma, n_work, t.tiles);
     } else {
         launch_k(pdl, t.mac.fn, dim3(t.n_split, t.tiles, count), dim3(kMacThreads), t.mac.smem, st, ma);
     }
@@ -511,8 +511,9 @@ uint32_t tier_count(const ca_engine *e, const Tier &t, uint64_t tend)
 
 // tier 0: the period pipeline for instances [i0, i1).  After the launch that covers the last
 // instance (last == true) the output block is complete and the device period counter advances.
-int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, uint32_t i0, uint32_t i1, bool last)
+int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, uint32_t i0, uint32_t i1, bool last, cudaStream_t st = nullptr, uint32_t ctr_set = 0)
 {
+    if (!st) st = e->stream;
     const Tier &t0 = e->tiers[0];
     const uint32_t n_items = (i1 - i0) * e->n_in;
     const uint32_t n_alloc = e->n_inst * e->n_in;
@@ -532,27 +533,27 @@ int launch_period(ca_engine *e, const float *d_in, float *d_out, bool profile, u
         FusedArgs ga{d_in, d_out, e->d_ring, t0.X, t0.H, e->tiers.size() > 1 ? e->d_acc : nullptr, e->d_par, e->d_st, e->d_ctl, t0.tw, t0.tw + e->B,
                      n_alloc, e->n_in, e->nv, t0.Lring, t0.P, e->ring_len, e->ring_out, e->acc_len, i0,
                      (e->cfg.flags & CA_FLAG_STREAMING) ? 1u : 0u, (e->cfg.flags & CA_FLAG_RAW_WET) ? 1u : 0u, voice_pool(e)};
-        if (profile) { CA_CUDA(cudaEventRecord(e->ev[0], e->stream)); CA_CUDA(cudaEventRecord(e->ev[1], e->stream)); }
-        fn<<<i1 - i0, kFusedThreads, e->fused_smem, e->stream>>>(ga);
-        if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl);
-        if (profile) { CA_CUDA(cudaEventRecord(e->ev[2], e->stream)); CA_CUDA(cudaEventRecord(e->ev[3], e->stream)); }
+        if (profile) { CA_CUDA(cudaEventRecord(e->ev[0], st)); CA_CUDA(cudaEventRecord(e->ev[1], st)); }
+        fn<<<i1 - i0, kFusedThreads, e->fused_smem, st>>>(ga);
+        if (last) k_tick<<<1, 1, 0, st>>>(e->d_ctl);
+        if (profile) { CA_CUDA(cudaEventRecord(e->ev[2], st)); CA_CUDA(cudaEventRecord(e->ev[3], st)); }
         CA_CUDA(cudaGetLastError());
         return CA_OK;
     }
-    if (profile) CA_CUDA(cudaEventRecord(e->ev[0], e->stream));
+    if (profile) CA_CUDA(cudaEventRecord(e->ev[0], st));
     const bool pdl = e->pdl && !profile;
-    launch_fwd0(e, pdl, fa, e->stream);
-    if (profile) CA_CUDA(cudaEventRecord(e->ev[1], e->stream));
-    launch_mac(t0, ma, i1 - i0, e->stream, pdl);
-    if (profile) CA_CUDA(cudaEventRecord(e->ev[2], e->stream));
-    if (e->link.skip_inverse) { if (last) k_tick<<<1, 1, 0, e->stream>>>(e->d_ctl); }  // group peer: only the period counter advances
-    else if (!e->link.defer_inverse) launch_inv0(e, pdl, ia, e->stream);
+    launch_fwd0(e, pdl, fa, st);
+    if (profile) CA_CUDA(cudaEventRecord(e->ev[1], st));
+    launch_mac(t0, ma, i1 - i0, st, pdl, ctr_set);
+    if (profile) CA_CUDA(cudaEventRecord(e->ev[2], st));
+    if (e->link.skip_inverse) { if (last) k_tick<<<1, 1, 0, st>>>(e->d_ctl); }  // group peer: only the period counter advances
+    else if (!e->link.defer_inverse) launch_inv0(e, pdl, ia, st);
     if (e->quirks) {  // reference-compatible DC / Nyquist terms, then clamp + dry mix (the inverse above stored the raw wet block)
         QuirkArgs qa{d_in, d_out, e->d_par, e->d_st, e->d_ctl, e->d_irsum, e->d_qdelta, e->d_qrun, e->d_qring,
                      n_alloc, e->nv, e->B, e->cfg.ref_fft_size, e->q_kr, e->q_len, i0, i1 - i0, tp1};
-        k_ref_quirks<<<(i1 - i0 + kQuirkWarps - 1) / kQuirkWarps, kQuirkWarps * 32, 0, e->stream>>>(qa);
+        k_ref_quirks<<<(i1 - i0 + kQuirkWarps - 1) / kQuirkWarps, kQuirkWarps * 32, 0, st>>>(qa);
     }
-    if (profile) CA_CUDA(cudaEventRecord(e->ev[3], e->stream));
+    if (profile) CA_CUDA(cudaEventRecord(e->ev[3], st));
     CA_CUDA(cudaGetLastError());
     return CA_OK;
 }
@@ -1461,8 +1462,8 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
             CA_CUDA(cudaMemsetAsync(t.Ypart2, 0, yp_bytes, e->stream));
             e->device_bytes += yp_bytes;
         }
-        CA_CUDA(cudaMalloc(&t.workctr, 2 * sizeof(uint32_t)));
-        CA_CUDA(cudaMemsetAsync(t.workctr, 0, 2 * sizeof(uint32_t), e->stream));
+        CA_CUDA(cudaMalloc(&t.workctr, 4 * sizeof(uint32_t)));
+        CA_CUDA(cudaMemsetAsync(t.workctr, 0, 4 * sizeof(uint32_t), e->stream));
         // twiddles, fp64 -> fp32: [W_S^n, n < S | W_2S^k, k < S]
         std::vector<float2> tw(2 * (size_t)t.S);
         for (uint32_t n = 0; n < t.S; n++) {
@@ -1826,24 +1827,58 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     } else {
         rc = flush_params(e);
         if (rc) return rc;
+        // CA_IO_TRACE=n: device timeline of call n (development): when each chunk's upload, kernels and download end
+        static const long trace_at = getenv("CA_IO_TRACE") ? atol(getenv("CA_IO_TRACE")) : -1;
+        const bool trace = trace_at >= 0 && (long)e->t_host == trace_at;
+        static cudaEvent_t tr_base, tr_ev[3][kIoChunks], tr_tiers, tr_prev;
+        static bool tr_init = false;
+        if (trace_at >= 0 && !tr_init) {
+            cudaEventCreate(&tr_base); cudaEventCreate(&tr_tiers); cudaEventCreate(&tr_prev);
+            for (auto &row : tr_ev) for (auto &ev : row) cudaEventCreate(&ev);
+            tr_init = true;
+        }
+        if (trace) { cudaEventRecord(tr_base, e->s_in); cudaEventRecord(tr_prev, e->stream); }
         // d_in / d_out are free: the previous call returned only after its D2H (hence every kernel of its
         // period pipeline) had completed; the deferred tiers still running on e->stream touch neither.
         for (uint32_t c = 0; c < chunks; c++) {
             const uint32_t i0 = (uint32_t)((uint64_t)e->n_active * c / chunks), i1 = (uint32_t)((uint64_t)e->n_active * (c + 1) / chunks);
             CA_CUDA(cudaMemcpyAsync(e->d_in + i0 * in_stride, src + i0 * in_stride, (i1 - i0) * in_stride * sizeof(float), cudaMemcpyHostToDevice, e->s_in));
             CA_CUDA(cudaEventRecord(e->io_ev[0][c], e->s_in));
+            if (trace) cudaEventRecord(tr_ev[0][c], e->s_in);
         }
+        // (Alternating chunks on two streams, so that one chunk's kernels fill the ramp and tail of the other's, was
+        // measured and dropped: 1 149 -> 1 204 us with 3 chunks, 1 135 -> 1 159 us with 4 -- the uploads and the deferred
+        // tiers slow down by more than the tier-0 kernels gain.)
         for (uint32_t c = 0; c < chunks; c++) {
             const uint32_t i0 = (uint32_t)((uint64_t)e->n_active * c / chunks), i1 = (uint32_t)((uint64_t)e->n_active * (c + 1) / chunks);
             CA_CUDA(cudaStreamWaitEvent(e->stream, e->io_ev[0][c], 0));
             rc = launch_period(e, e->d_in, e->d_out, false, i0, i1, c + 1 == chunks);
             if (rc) return rc;
             CA_CUDA(cudaEventRecord(e->io_ev[1][c], e->stream));
+            if (trace) cudaEventRecord(tr_ev[1][c], e->stream);
             CA_CUDA(cudaStreamWaitEvent(e->s_out, e->io_ev[1][c], 0));
             CA_CUDA(cudaMemcpyAsync(dst + i0 * out_stride, e->d_out + i0 * out_stride, (i1 - i0) * out_stride * sizeof(float), cudaMemcpyDeviceToHost, e->s_out));
+            if (trace) cudaEventRecord(tr_ev[2][c], e->s_out);
         }
         e->launches += e->fused ? chunks + 1 : 3 * chunks;
         CA_CUDA(cudaEventRecord(e->out_ready, e->s_out));
+        if (trace) {
+            const double t_enq = now_us() - t0;
+            rc = run_deferred(e);
+            if (rc) return rc;
+            const double t_enq2 = now_us() - t0;
+            cudaEventRecord(tr_tiers, e->stream);
+            CA_CUDA(cudaEventSynchronize(e->out_ready));
+            const double t_ret = now_us() - t0;
+            cudaEventSynchronize(tr_tiers);
+            auto el = [&](cudaEvent_t ev) { float ms = 0; cudaEventElapsedTime(&ms, tr_base, ev); return 1e3 * ms; };
+            fprintf(stderr, "[io trace] call %ld: host enqueue tier0 %.0f us, + tiers %.0f us, returns at %.0f us | previous tiers end %.0f\n", trace_at, t_enq, t_enq2, t_ret, el(tr_prev));
+            for (uint32_t c = 0; c < chunks; c++) fprintf(stderr, "[io trace]   chunk %u: upload done %.0f, kernels done %.0f, download done %.0f\n", c, el(tr_ev[0][c]), el(tr_ev[1][c]), el(tr_ev[2][c]));
+            fprintf(stderr, "[io trace]   this call's tiers end %.0f\n", el(tr_tiers));
+            if (dst != out) memcpy(out, e->h_out, out_bytes);
+            record_wall(e, now_us() - t0);
+            return CA_OK;
+        }
     }
     rc = run_deferred(e);  // long tiers keep the GPU busy while the host already has its output
     if (rc) return rc;

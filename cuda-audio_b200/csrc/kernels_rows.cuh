@@ -487,6 +487,12 @@ __global__ void __launch_bounds__(256, 4) k_tcols_inv(const TierInvArgs a)
     const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     const int cc = threadIdx.x & 31, j = threadIdx.x >> 5;
     const int n2 = (blockIdx.x & 7) * 32 + cc;
+    if (threadIdx.x < M1) {  // the output-ring samples these 32 columns add into (M1 / 2 kept rows of 64 floats): into L2 now
+        const uint32_t amask0 = a.acc_len - 1;
+        const uint32_t p0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask0);
+        const uint32_t hrow = threadIdx.x >> 1, half = threadIdx.x & 1;
+        prefetch_l2(a.accring + (size_t)item * a.acc_len + ((p0 + 2u * (256u * hrow + 32u * (blockIdx.x & 7)) + 32u * half) & amask0));
+    }
     const float2 *src = a.Ypart + (((size_t)z * a.n_split) * a.n_out + o) * a.S;
     // k1 = j + 8 b: radix Mb over b, twiddle conj W_M1^(j q)
     float2 y[Mb];

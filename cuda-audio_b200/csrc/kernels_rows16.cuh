@@ -316,6 +316,12 @@ __global__ void __launch_bounds__(M1 * 16) k_tinv_x2(const TierInvArgs a)
     const uint32_t item = inst * a.n_out + o;
     const unsigned long long tend = ctl_tend(a.ctl, a.tend_host, a.t_sel, 0u);
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, h = lane >> 4, l = lane & 15;
+    {   // the output-ring block this transform adds into is read at the very end: pull it into L2 now
+        const uint32_t amask0 = a.acc_len - 1;
+        const uint32_t p0 = (uint32_t)((tend * (unsigned long long)a.B - a.S + a.off) & amask0);
+        const float *acc0 = a.accring + (size_t)item * a.acc_len;
+        for (uint32_t line = threadIdx.x; line < a.S / 32; line += M1 * 16) prefetch_l2(acc0 + ((p0 + 32u * line) & amask0));
+    }
     const int r = x2_row<M1>(wi, h);
     float2 *reg = sm + r * kR16Slots;
     float2 y[16];
