@@ -58,6 +58,13 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.lines, self.proc, self.gpu = [], None, gpu_index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -70,7 +77,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -80,8 +87,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # nvidia-smi needs a few hundred ms before its first sample, the timed regions last ~0.15 s: the sampler starts with
+        # the warm-up (same load); samples inside [mark_begin, mark_end] are used when there are any, else every sample
+        # taken under that load, and `window` says which
+        inside = [ln for (ts, ln) in self.lines if self.t_begin is not None and self.t_begin <= ts <= (self.t_end or ts)]
+        window = "timed region" if inside else "warm-up + timed region (same load)"
         sm, smax, power, reasons = [], [], [], set()
-        for ln in self.lines:
+        for ln in (inside or [ln for (_ts, ln) in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -94,7 +106,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def pin_to_gpu_numa_node(torch, local_rank, world):
@@ -417,6 +429,9 @@ def run_ours(args):
     # Steady state only: the engine skips delay-line slots that are older than a voice's start, so
     # the first IR-length worth of periods after start-up does LESS work than a running system.
     warm = max(args.warmup, 3) + STEADY + cycle
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warm):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
     e.sync()
@@ -424,9 +439,7 @@ def run_ours(args):
     # the same mix of long-tier launches whatever --steps is
     steps = args.steps if args.no_round_to_cycle else ((args.steps + cycle - 1) // cycle) * cycle
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     launches0 = e.stats().gpu_launches
     ev0.record(stream)
     for _ in range(steps):
@@ -449,6 +462,7 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
     launches = e.stats().gpu_launches - launches0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     y_rms = float(np.sqrt((pout.array.astype(np.float64) ** 2).mean()))
     st_main = e.stats()
@@ -823,6 +837,7 @@ def run_reference(args):
     best = None
     sweep = {}
     sampler.start()
+    sampler.mark_begin()   # the whole sweep is the measurement
     for k in cand:
         while len(insts) < k:
             r = refgpu.RefGpu(N, 0)
@@ -840,6 +855,7 @@ def run_reference(args):
         sweep[str(k)] = res
         if best is None or res["rt_channels"] > best[1]["rt_channels"]:
             best = (k, res)
+    sampler.mark_end()
     clocks = sampler.stop()
     os.dup2(saved_stdout, 1)
     os.close(devnull)

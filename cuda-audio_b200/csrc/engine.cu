@@ -100,6 +100,12 @@ MacVariant mac_pick_v(int variant)
     case 5: return mac_variant<BT, NOUT, 2, 6>();   // 144 KB: 1 CTA / SM, deep
     case 6: return mac_variant<BT, NOUT, 1, 3>();   //  36 KB: 6 CTAs / SM
     case 7: return mac_variant<BT, NOUT, 1, 2>();   //  24 KB: 9 CTAs / SM
+    case 12: return mac_variant<BT, NOUT, 2, 2>();  //  48 KB: two stages of twice the rows
+    case 13: return mac_variant<BT, NOUT, 4, 1>();  //  48 KB: ONE stage
+    case 14: return mac_variant<BT, NOUT, 2, 1>();  //  24 KB: ONE stage
+    case 15: return mac_variant<BT, NOUT, 8, 1>();  //  96 KB: ONE stage, 2 CTAs / SM
+    case 16: return mac_variant<BT, NOUT, 6, 1>();  //  72 KB: ONE stage, 3 CTAs / SM
+    case 17: return mac_variant<BT, NOUT, 3, 1>();  //  36 KB: ONE stage
     default: return mac_variant<BT, NOUT, 2, 4>();  //  96 KB: 2 CTAs / SM (measured best)
     }
 }
@@ -1165,10 +1171,11 @@ int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block)
 {
     if (!cfg || !is_pow2(cfg->period) || !cfg->max_ir_frames) return CA_ERR_INVALID;
     if (!max_block) max_block = 16384;
-    // growth 8 keeps the FFT work low (fewest tiers; single instances and short periods); batches gain from growth 4
-    // when four tiers still reach max_block: 256 x 4 | 1024 x 3 | 4096 x 3 | 16384 streams 258 KB per instance-period
-    // instead of 319 KB (measured at 16 128 instances: 1 095 -> 1 046 us per period)
-    if (!growth) growth = (cfg->n_instances >= 512 && (uint64_t)cfg->period * 64 >= max_block && !(cfg->flags & CA_FLAG_ASYNC_TIERS)) ? 4 : 8;
+    // growth 8: fewest tiers, least FFT work.  For batches at period 256 growth 4 (256 x 4 | 1024 x 3 | 4096 x 3 | 16384)
+    // streams 258 KB per instance-period instead of 319 KB and is 4 % faster device-resident (1 077 -> 1 034 us at
+    // 16 128 instances) but no faster through ca_process (1 158 vs 1 157 us) and its short work items stream at 0.93 of
+    // the HBM peak instead of 0.99: not the default.
+    if (!growth) growth = 8;
     if (!is_pow2(growth) || growth < 2 || !is_pow2(max_block)) return CA_ERR_INVALID;
     uint32_t n = 0, S = cfg->period, off = 0;
     memset(cfg->tier_block, 0, sizeof(cfg->tier_block));
@@ -1372,10 +1379,12 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
         // rows per CTA before splitting: long lists (uniform, P in the hundreds) stream best with 96 KB /
         // 2 CTAs per SM, short ones (tiers: 14..22 rows) with 4 CTAs per SM (the register limit) of 3 x 12 KB
         // stages (measured r01, K = 4096: tier-0 MAC 83 us with 96 KB, 78 with 4 x 12 KB, 74.5 with 3 x 12 KB)
-        // short row lists: 3 x 12 KB ring; tier 0's items are the shortest (8-16 rows of 2 KB arrays) and stream best with a
-        // TWO-stage ring (measured at 16 128 instances: 275 -> 264 us with 8 partitions, 168 -> 154 us with 4; the long
-        // tiers lose 0.3-1 % with it)
-        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? (j == 0 ? 7 : 6) : 1);
+        // Short row lists (the tiers of a batch: 6..22 rows per work item) stream best with ONE 48 KB stage per CTA and
+        // 4 CTAs per SM: the overlap comes from the other CTAs of the SM, and nothing is paid per stage hand-off.
+        // Measured at 16 128 instances, us per period (tier 0 / long tiers; 8-7-11 partitions): 3 x 12 KB ring 275 / 556,
+        // 2 x 12 KB 264 / 561, 2 x 24 KB 255 / 550, 1 x 48 KB 249 / 553 (= 6.3 / 6.4 TB/s), 1 x 36 KB 256 / 555, 1 x 72 KB
+        // 366 / 555, 1 x 96 KB 312 / 560; one-row stages (6 KB x 2..6) 295-342 / 586.
+        const int tier_variant = variant >= 0 ? variant : (t.P * e->n_in <= 128 ? 13 : 1);
         t.mac = mac_pick((int)t.bt, (int)e->n_out, tier_variant);
         CA_CUDA(cudaFuncSetAttribute((const void *)t.mac.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.mac.smem));
         {

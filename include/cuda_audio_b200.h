@@ -171,9 +171,9 @@ const char *ca_last_error_string(void); /* thread-local detail of the last CUDA 
 
 void ca_config_init(ca_config *cfg); /* zero + struct_size + reference defaults (2x2, period 256) */
 /* Fill n_tiers / tier_block / tier_parts for cfg->period and cfg->max_ir_frames: every tier's block
- * is `growth` (power of two) times the previous one, up to max_block (0 = 16384).  growth 0 = the engine picks:
- * 8, or 4 for batches (n_instances >= 512) whose period reaches max_block in four tiers.  Set n_instances, period,
- * max_ir_frames and flags before calling. */
+ * is `growth` (power of two, 0 = 8) times the previous one, up to max_block (0 = 16384).  Set period, max_ir_frames
+ * and flags before calling.  (Growth 4 streams fewer bytes for batches at period 256 but runs more transforms:
+ * measured 4 % faster device-resident, equal through ca_process) */
 int ca_config_auto_tiers(ca_config *cfg, uint32_t growth, uint32_t max_block);
 
 int ca_create(const ca_config *cfg, ca_engine **out);

@@ -71,8 +71,7 @@ def test_cfg2_reference_size_uniform_and_tiered(monkeypatch):
 
 def test_batch_2048_tiered_chunked_host_pipeline_vs_fp64():
     """K = 2048 distinct-IR instances, cfg2 geometry, tiers auto + streaming hints, host buffers through
-    ca_process (3-chunk H2D | kernels | D2H pipeline, persistent MAC, side-stream tiers, PDL; the tier shape the
-    engine picks for batches: 256 x 4 | 1024 x 3 | 4096 x 3 | 16384): 900
+    ca_process (3-chunk H2D | kernels | D2H pipeline, persistent MAC, side-stream tiers, PDL): 900
     periods, instances 0 / 1023 / 2047 against the fp64 oracle."""
     import torch
     m = ca()
@@ -106,13 +105,60 @@ def test_batch_2048_tiered_chunked_host_pipeline_vs_fp64():
             xs[:, :, t * B:(t + 1) * B] = xb[picks]
             ys[:, :, t * B:(t + 1) * B] = pout.array[picks]
         st = e.stats()
-        assert [int(st.tier_block[j]) for j in range(st.n_tiers)] == [256, 1024, 4096, 16384] and st.tier0_fused == 0   # batches: growth 4
+        assert [int(st.tier_block[j]) for j in range(st.n_tiers)] == [256, 2048, 16384] and st.tier0_fused == 0
         pin.free()
         pout.free()
     pr = [dict(wet=0.8, dry=0.3, panWet=0.25, level=0.9), dict(wet=0.8, dry=0.3, panWet=-0.5, level=0.9)]
     for j, s in enumerate(picks):
         irs = [[kept[2 * s + i][o] for o in range(2)] for i in range(2)]
         truth = O.engine_truth(xs[j], irs, pr)
+        for o in range(2):
+            err = O.rel_l2(ys[j, o], truth[o])
+            assert err < 5e-6, (s, o, err)
+
+
+def test_batch_growth4_four_tiers_chunked_host_pipeline_vs_fp64():
+    """The four-tier shape (tier_growth = 4: 256 x 4 | 1024 x 3 | 4096 x 3 | 16384 x ..) as a batch of 768 through
+    ca_process (chunked pipeline, persistent single-stage MAC on every tier): instances 0 / 383 / 767 vs fp64."""
+    import torch
+    m = ca()
+    B, L, K, nper = 256, 40000, 768, 260
+    dev = torch.device("cuda", 0)
+    picks = [0, 383, 767]
+    n = torch.arange(L, device=dev, dtype=torch.float32)
+    env = torch.exp(-6.91 * n / (0.8 * L))
+    g = torch.Generator(device=dev)
+    kept = {}
+    with m.Engine(period=B, max_ir_frames=L, n_instances=K, n_ir_slots=2 * K, flags=m.FLAG_STREAMING, tiers="auto", tier_growth=4) as e:
+        for s in range(2 * K):
+            g.manual_seed(5000 + s)
+            h = torch.randn(2, L, device=dev, generator=g) * env
+            h = h / h.pow(2).sum(dim=1, keepdim=True).sqrt()
+            e.load_ir_device(s, h[0].data_ptr(), h[1].data_ptr(), L)
+            if s // 2 in picks:
+                kept[s] = h.cpu().numpy().astype(np.float64)
+        for s in range(K):
+            for i in range(2):
+                e.set_params(s, i, select=2 * s + i, wet=0.8, dry=0.3, panWet=0.25 if i == 0 else -0.5, level=0.9, predelay=(7 * s) % 300)
+                e.set_glide(s, i, 0.8)
+        pin, pout = m.PinnedArray((K, 2, B)), m.PinnedArray((K, 2, B))
+        g.manual_seed(78)
+        xs = np.zeros((len(picks), 2, nper * B), np.float32)
+        ys = np.zeros((len(picks), 2, nper * B), np.float32)
+        for t in range(nper):
+            xb = (torch.randn(K, 2, B, device=dev, generator=g) * 0.1).clamp_(-0.9, 0.9).cpu().numpy()
+            pin.array[...] = xb
+            e.process_raw(pin.ptr, pout.ptr)
+            xs[:, :, t * B:(t + 1) * B] = xb[picks]
+            ys[:, :, t * B:(t + 1) * B] = pout.array[picks]
+        st = e.stats()
+        assert [int(st.tier_block[j]) for j in range(st.n_tiers)] == [256, 1024, 4096, 16384] and st.tier0_fused == 0
+        pin.free()
+        pout.free()
+    pr = [dict(wet=0.8, dry=0.3, panWet=0.25, level=0.9), dict(wet=0.8, dry=0.3, panWet=-0.5, level=0.9)]
+    for j, s in enumerate(picks):
+        irs = [[kept[2 * s + i][o] for o in range(2)] for i in range(2)]
+        truth = O.engine_truth(xs[j], irs, pr, predelay=(7 * s) % 300)
         for o in range(2):
             err = O.rel_l2(ys[j, o], truth[o])
             assert err < 5e-6, (s, o, err)
