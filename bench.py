@@ -430,7 +430,7 @@ def run_ours(args):
     # the first IR-length worth of periods after start-up does LESS work than a running system.
     warm = max(args.warmup, 3) + STEADY + cycle
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     for _ in range(warm):
         e.process_device(x_dev.data_ptr(), y_dev.data_ptr())
@@ -955,6 +955,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-max-instances", type=int, default=32)
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi clock sampler (profiler runs)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
