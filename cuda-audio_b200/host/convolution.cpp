@@ -93,7 +93,9 @@ void Convolution::onStart()
 {
     _stopping.store(false, std::memory_order_seq_cst);
     const size_t period = _opt.period ? _opt.period : (handle ? (size_t)jack_get_buffer_size(handle) : 0);
-    if (period && numIRs() && !_shared) buildNow(period);
+    // a shared batch is built by the member that completes it (earlier ones would build an engine that is rebuilt when the
+    // next member joins); a group that never fills up is built at its first rendezvous
+    if (period && numIRs() && (!_shared || _shared->full())) buildNow(period);
     activate();
     playback[0] = addOutput("playback_1");
     playback[1] = addOutput("playback_2");

@@ -65,6 +65,12 @@ void SharedEngine::leave(Convolution *c)
     }
 }
 
+bool SharedEngine::full()
+{
+    std::lock_guard<std::mutex> lk(_buildMutex);
+    return _members.size() >= std::max<size_t>(_opt.shared, 1);
+}
+
 void SharedEngine::standDown(int idx)
 {
     if (idx < 0 || (size_t)idx >= std::max<size_t>(_opt.shared, 1)) return;
@@ -81,9 +87,11 @@ bool SharedEngine::buildNow(size_t period, float sampleRate)
     // Nobody may be inside process() while the engine and its buffers are replaced: new arrivals see _exclusive
     // and answer with silence, waiting members leave the rendezvous, a running batch finishes.
     _exclusive.fetch_add(1, std::memory_order_seq_cst);
+    _evict.store(true, std::memory_order_seq_cst);
     while (_inside.load(std::memory_order_seq_cst) != 0) std::this_thread::yield();
     const bool ok = build(period, sampleRate);
     _state.store((genOf(_state.load(std::memory_order_relaxed)) + 1) << 16, std::memory_order_release);  // abandoned cycle, if any
+    _evict.store(false, std::memory_order_seq_cst);
     _exclusive.fetch_sub(1, std::memory_order_seq_cst);
     return ok;
 }
@@ -229,7 +237,10 @@ bool SharedEngine::process(Convolution *c, int idx, const float *in1, const floa
                 continue;
             }
         }
-        if (_exclusive.load(std::memory_order_seq_cst) != 0) return false;  // a build started: this cycle is silence, leave now
+        // buildNow() on another thread waits for everybody to leave: this cycle is silence.  (A rebuild by this
+        // cycle's runner is waited for instead: a driver that is not paced by a clock -- an offline render, one
+        // loop per member -- would otherwise run through its input while the build lasts.)
+        if (_evict.load(std::memory_order_seq_cst)) return false;
         if (spins > 2000) {
             std::this_thread::yield();
             if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(_opt.sharedTimeoutMs ? _opt.sharedTimeoutMs : 200)) {

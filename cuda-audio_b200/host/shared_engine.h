@@ -30,6 +30,7 @@ public:
     bool process(Convolution *c, int idx, const float *in1, const float *in2, float *L, float *R, size_t nframes);
     ca_engine *engine() const { return _engine; }
     size_t size() const { return _members.size(); }
+    bool full();  // every one of the opt.shared seats is taken
     // diagnostics
     uint64_t batches() const { return _batches.load(std::memory_order_relaxed); }   // ca_process calls for the whole batch
     uint64_t rebuilds() const { return _rebuilds.load(std::memory_order_relaxed); } // engine (re)builds so far
@@ -64,5 +65,6 @@ private:
     // build exclusion: a builder raises _exclusive, then needs _inside == 0 (buildNow: waits) or _staging == 0
     // (rebuild at the rendezvous: gives up for this cycle); members raise their counter first, then read _exclusive
     std::atomic<int> _exclusive{0}, _inside{0}, _staging{0};
+    std::atomic<bool> _evict{false};  // buildNow() is waiting for _inside == 0: members waiting at the rendezvous leave
     std::atomic<uint64_t> _batches{0}, _rebuilds{0}, _dropped{0};
 };

@@ -85,11 +85,11 @@ struct Member {
 
 using Members = std::vector<std::unique_ptr<Member>>;
 
-Members makeGroup(int K, uint32_t timeoutMs, bool prebuild)
+Members makeGroup(int K, uint32_t timeoutMs, bool prebuild, bool periodKnown = true)
 {
     EngineOptions o;
     o.shared = (uint32_t)K;
-    o.period = (uint32_t)B;
+    o.period = periodKnown ? (uint32_t)B : 0;  // 0: nobody knows the period before the first callback (plain harness)
     o.sharedTimeoutMs = timeoutMs;
     o.flags = CA_FLAG_STREAMING;
     Convolution::setDefaultOptions(o);
@@ -168,6 +168,21 @@ void lockstepHost(int K, uint64_t P)
     CHECK(sec < 3.0, "%.2f s: somebody waited for a timeout", sec);
     CHECK(m[0]->c->sharedGroup()->dropped() == 0, "a member was set aside");
     for (auto &x : m) CHECK(x->silent == 0 && x->good == P && x->wrong == 0, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+}
+
+// A driver without a clock (an offline render: one loop per member, as fast as it goes) whose engine is only built at
+// the first rendezvous: the members wait for that build instead of running through their input
+void unpacedDriverFirstBuild(int K, uint64_t P)
+{
+    fprintf(stderr, "== unpaced driver, engine built at the first rendezvous: %d members\n", K);
+    const uint64_t v0 = fake_violations();
+    hj_set_buffer_size(0);
+    fake_set_create_delay_us(30000);
+    Members m = makeGroup(K, 5000, false, false);
+    runThreads(m, P);
+    fake_set_create_delay_us(0);
+    CHECK(fake_violations() == v0, "contract violations");
+    for (auto &x : m) CHECK(x->wrong == 0 && x->silent <= 2 && x->good + x->silent == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
 }
 
 void prepareOnLiveGroup(int K, uint64_t P)
@@ -304,6 +319,7 @@ int main(int argc, char **argv)
     hj_set_sample_rate(48000);
     steady(K, P);
     lockstepHost(K, P);
+    unpacedDriverFirstBuild(3, P);
     prepareOnLiveGroup(K, P);
     memberStopsAndResumes(4, P);
     memberDestroyedMidRun(4, P);
