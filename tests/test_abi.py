@@ -132,3 +132,90 @@ int main(void)
     assert "api=1 rc=0 tiers=4 64x9 512x7 4096x3 16384x0" in out, out   # one more tier-0 partition than the synchronous plan
     from tests import conftest
     assert ("create=0" in out) if conftest._has_gpu() else ("create=-2" in out), out
+
+
+def test_invalid_configs_are_refused_before_any_cuda_call():
+    """The C ABI reports errors, it never aborts (SURVEY 8b "error convention"; the reference asserts, conv.cu:152-194).
+    Argument validation comes before the device check, so it is testable without a GPU: every malformed config is
+    CA_ERR_INVALID (-1) with a reason in ca_last_error_string(), not CA_ERR_CUDA (-2) and not a crash."""
+    import ctypes as C
+
+    import cuda_audio_b200 as m
+    L = m.lib()
+
+    def create(**kw):
+        cfg = m.default_config()
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        h = C.c_void_p(0xdead)
+        rc = L.ca_create(C.byref(cfg), C.byref(h))
+        assert rc != 0 and not h.value, kw      # the out pointer is cleared on failure
+        return rc, L.ca_last_error_string().decode()
+
+    for bad in (dict(period=0), dict(period=48), dict(period=16), dict(period=2048), dict(n_in=0), dict(n_in=3), dict(n_out=0), dict(n_out=3),
+                dict(n_instances=0), dict(max_ir_frames=0), dict(n_ir_slots=0), dict(max_voices=5), dict(struct_size=8)):
+        rc, why = create(**bad)
+        assert rc == -1 and why, (bad, rc, why)
+    assert L.ca_create(None, None) == -1
+    cfg = m.default_config()
+    assert L.ca_create(C.byref(cfg), None) == -1
+
+
+def test_null_handles_are_errors_not_crashes():
+    import ctypes as C
+
+    import cuda_audio_b200 as m
+    L = m.lib()
+    p = m.Params()
+    st = m.Stats()
+    buf = (C.c_float * 8)()
+    f32p = C.POINTER(C.c_float)
+    none = C.c_void_p(None)
+    assert L.ca_load_ir(none, 0, C.cast(buf, f32p), C.cast(buf, f32p), 8) == -1
+    assert L.ca_set_params(none, 0, 0, C.byref(p)) == -1
+    assert L.ca_get_params(none, 0, 0, C.byref(p)) == -1
+    assert L.ca_set_glide(none, 0, 0, C.c_float(1.0)) == -1
+    assert L.ca_set_active(none, 1) == -1
+    assert L.ca_reset(none) == -1
+    assert L.ca_process(none, C.cast(buf, f32p), C.cast(buf, f32p), 4) == -1
+    assert L.ca_sync(none) == -1
+    assert L.ca_get_stats(none, C.byref(st)) == -1
+    assert L.ca_reset_stats(none) == -1
+    assert L.ca_destroy(none) in (0, -1)     # destroying nothing is harmless
+    assert L.ca_strerror(-1) and L.ca_strerror(-6) and L.ca_strerror(12345)
+
+
+def test_group_entry_points_validate_without_a_gpu():
+    """ca_group_* (one long IR over the GPUs of a node): malformed configs and null handles are CA_ERR_INVALID."""
+    import ctypes as C
+
+    import cuda_audio_b200 as m
+    L = m.lib()
+
+    def create(**kw):
+        cfg = m.GroupConfig()
+        L.ca_group_config_init(C.byref(cfg))
+        assert cfg.struct_size == C.sizeof(m.GroupConfig)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        h = C.c_void_p(0xdead)
+        rc = L.ca_group_create(C.byref(cfg), C.byref(h))
+        assert not h.value
+        return rc
+
+    assert create(n_devices=0) == -1 and create(n_devices=9) == -1 and create(exchange=7) == -1 and create(struct_size=4) == -1
+    from tests import conftest
+    if not conftest._has_gpu():
+        assert create() == -2 and "no CPU fallback" in L.ca_last_error_string().decode()
+    none = C.c_void_p(None)
+    p = m.Params()
+    st = m.GroupStats()
+    buf = (C.c_float * 8)()
+    f32p = C.POINTER(C.c_float)
+    assert L.ca_group_load_ir(none, 0, C.cast(buf, f32p), C.cast(buf, f32p), 8) == -1
+    assert L.ca_group_set_params(none, 0, C.byref(p)) == -1
+    assert L.ca_group_set_glide(none, 0, C.c_float(1.0)) == -1
+    assert L.ca_group_process(none, C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 4) == -1
+    assert L.ca_group_get_stats(none, C.byref(st)) == -1
+    assert L.ca_group_reset_stats(none) == -1
+    assert L.ca_group_destroy(none) in (0, -1)
