@@ -1,0 +1,61 @@
+// param_queue.h -- parameter hand-off of the C ABI (plain C++, no CUDA: also compiled by tests/hostsim under ThreadSanitizer).
+#pragma once
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/cuda_audio_b200.h"
+
+// Parameter hand-off: ca_set_params / ca_set_glide may be called from ANY thread (MIDI thread, UI, the
+// real-time thread itself) and never take a lock: commands go through a bounded multi-producer /
+// single-consumer ring (Vyukov's sequence-numbered slots) that the processing thread drains at the top of
+// the next period ("set_params lock-free from any thread").
+struct ParamCmd {
+    uint32_t item = 0, kind = 0;  // kind 0: parameter block, 1: glide jump
+    ca_params p{};
+    float glide = 0.f;
+};
+
+class ParamQueue {
+public:
+    ParamQueue() { resize(1u << 13); }
+    ~ParamQueue() { delete[] slots_; }
+    // before the engine is shared: room for a full set-up pass (parameters + glide of every item, twice)
+    void resize(uint64_t min_slots)
+    {
+        delete[] slots_;
+        kSlots = 1u << 13;
+        while (kSlots < min_slots) kSlots <<= 1;
+        slots_ = new Slot[kSlots];
+        for (uint64_t i = 0; i < kSlots; i++) slots_[i].seq.store(i, std::memory_order_relaxed);
+        enq_.store(0, std::memory_order_relaxed);
+        deq_ = 0;
+    }
+    bool push(const ParamCmd &c)
+    {
+        uint64_t pos = enq_.load(std::memory_order_relaxed);
+        for (;;) {
+            Slot &s = slots_[pos & (kSlots - 1)];
+            const int64_t dif = (int64_t)s.seq.load(std::memory_order_acquire) - (int64_t)pos;
+            if (dif == 0) {
+                if (enq_.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) { s.cmd = c; s.seq.store(pos + 1, std::memory_order_release); return true; }
+            } else if (dif < 0) return false;  // full
+            else pos = enq_.load(std::memory_order_relaxed);
+        }
+    }
+    bool pop(ParamCmd *c)  // single consumer
+    {
+        Slot &s = slots_[deq_ & (kSlots - 1)];
+        if (s.seq.load(std::memory_order_acquire) != deq_ + 1) return false;
+        *c = s.cmd;
+        s.seq.store(deq_ + kSlots, std::memory_order_release);
+        deq_++;
+        return true;
+    }
+
+private:
+    struct Slot { std::atomic<uint64_t> seq; ParamCmd cmd; };
+    uint64_t kSlots = 0;
+    Slot *slots_ = nullptr;
+    std::atomic<uint64_t> enq_{0};
+    uint64_t deq_ = 0;
+};

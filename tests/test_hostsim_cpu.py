@@ -53,3 +53,13 @@ def test_host_mirror_threading_under_address_sanitizer():
     if not ok:
         pytest.skip("no AddressSanitizer runtime for this g++: " + log[-300:])
     _run("hostsim_asan", 1500, 6)
+
+
+def test_parameter_ring_of_the_c_abi_under_thread_sanitizer():
+    """csrc/param_queue.h (behind ca_set_params / ca_set_glide, "lock-free from any thread"): six producers
+    against the draining thread: nothing lost, duplicated, reordered per producer or torn; a full ring refuses."""
+    ok, log = _build("paramq_tsan")
+    assert ok, log
+    r = subprocess.run([os.path.join(SIM, "paramq_tsan"), "6", "100000"], capture_output=True, text=True, timeout=600)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert r.returncode == 0 and "PARAMQ OK" in r.stdout, r.stdout + r.stderr[-2000:]
