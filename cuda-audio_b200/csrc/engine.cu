@@ -218,10 +218,9 @@ struct ca_engine {
     // through the lock-free command ring; `user` (what ca_get_params returns) is seqlock-guarded per item
     ParamQueue par_queue;
     std::vector<InParamDev> par;
-    std::vector<ca_params> user;
-    std::unique_ptr<std::atomic<uint32_t>[]> user_seq;
+    ParamMirror user;
     bool par_dirty = true;  // processing thread only
-    std::vector<uint8_t> ir_loaded;
+    std::unique_ptr<std::atomic<uint8_t>[]> ir_loaded;  // set by ca_load_ir*, read by ca_set_params on any thread
     FftFns fft{};
     // member of a ca_group (one IR split by partition range across GPUs, csrc/group.cuh)
     struct Link {
@@ -1487,17 +1486,17 @@ static int create_impl(const ca_config *cfg, ca_engine *e)
 
     // parameter defaults == Convolution::CC::value defaults (conv.h:42-50)
     e->par.assign(n_items, InParamDev{});
-    e->user.assign(n_items, ca_params{});
+    e->user.resize(n_items);
     e->par_queue.resize(4 * n_items);
-    e->user_seq.reset(new std::atomic<uint32_t>[n_items]);
-    for (size_t i = 0; i < n_items; i++) e->user_seq[i].store(0, std::memory_order_relaxed);
     for (size_t i = 0; i < n_items; i++) {
-        ca_params &u = e->user[i];
+        ca_params u{};
         u.select = 0; u.predelay = 0; u.speed = 100; u.vsteps = -1;
         u.dry = 0.5f; u.wet = 0.5f; u.panDry = 0.f; u.panWet = 0.f; u.level = 1.0f;
+        e->user.set(i, u);
         fill_dev_param(e->par[i], u);
     }
-    e->ir_loaded.assign(cfg->n_ir_slots, 0);
+    e->ir_loaded.reset(new std::atomic<uint8_t>[cfg->n_ir_slots]);
+    for (uint32_t i = 0; i < cfg->n_ir_slots; i++) e->ir_loaded[i].store(0, std::memory_order_relaxed);
     e->wall.assign(1u << 16, 0.f);
     e->deadline_us = cfg->sample_rate > 0 ? 1e6 * (double)e->B / (double)cfg->sample_rate : 0.0;
 
@@ -1608,7 +1607,7 @@ static int load_ir_dev(ca_engine *e, uint32_t slot, const float *d_left, const f
     }
     CA_CUDA(cudaGetLastError());
     CA_CUDA(cudaStreamSynchronize(e->stream));
-    e->ir_loaded[slot] = 1;
+    e->ir_loaded[slot].store(1, std::memory_order_release);
     return CA_OK;
 }
 
@@ -1646,28 +1645,21 @@ int ca_set_params(ca_engine *e, uint32_t instance, uint32_t input, const ca_para
 {
     if (!e || !p || instance >= e->n_inst || input >= e->n_in) return CA_ERR_INVALID;
     if (p->select >= e->cfg.n_ir_slots || p->predelay >= CA_MAX_PREDELAY) return CA_ERR_INVALID;
-    if (!e->ir_loaded[p->select]) return CA_ERR_STATE;  // the reference would dereference nullptr (conv.cu:340)
+    if (!e->ir_loaded[p->select].load(std::memory_order_acquire)) return CA_ERR_STATE;  // the reference would dereference nullptr (conv.cu:340)
     ParamCmd c;
     c.item = instance * e->n_in + input; c.kind = 0; c.p = *p;
     if (!e->par_queue.push(c)) { g_last_error = "parameter queue full (no ca_process call is draining it)"; return CA_ERR_STATE; }
-    std::atomic<uint32_t> &sq = e->user_seq[c.item];  // seqlock: odd while the block is being written
-    sq.fetch_add(1, std::memory_order_acq_rel);
-    e->user[c.item] = *p;
-    e->user[c.item].vsteps = -1;
-    sq.fetch_add(1, std::memory_order_release);
+    ca_params shown = *p;
+    shown.vsteps = -1;
+    e->user.set(c.item, shown);
     return CA_OK;
 }
 
 int ca_get_params(ca_engine *e, uint32_t instance, uint32_t input, ca_params *p)
 {
     if (!e || !p || instance >= e->n_inst || input >= e->n_in) return CA_ERR_INVALID;
-    const size_t i = (size_t)instance * e->n_in + input;
-    for (;;) {
-        const uint32_t a = e->user_seq[i].load(std::memory_order_acquire);
-        *p = e->user[i];
-        std::atomic_thread_fence(std::memory_order_acquire);
-        if (!(a & 1u) && e->user_seq[i].load(std::memory_order_relaxed) == a) return CA_OK;
-    }
+    e->user.get((size_t)instance * e->n_in + input, p);
+    return CA_OK;
 }
 
 int ca_set_glide(ca_engine *e, uint32_t instance, uint32_t input, float g)

@@ -2,6 +2,8 @@
 #pragma once
 #include <atomic>
 #include <cstdint>
+#include <cstring>
+#include <memory>
 
 #include "../../include/cuda_audio_b200.h"
 
@@ -58,4 +60,52 @@ private:
     Slot *slots_ = nullptr;
     std::atomic<uint64_t> enq_{0};
     uint64_t deq_ = 0;
+};
+
+// What ca_get_params answers: the last block handed to ca_set_params per (instance, input), readable from any thread
+// while any number of threads set it.  A seqlock per item whose payload is words of relaxed atomics (no data race in
+// the language's sense either): writers take the item by moving its sequence from even to odd (two writers of the same
+// item at the same instant: the second spins for the few stores of the first), readers retry while it is odd or moved.
+class ParamMirror {
+public:
+    static constexpr size_t kWords = sizeof(ca_params) / sizeof(uint32_t);
+    static_assert(sizeof(ca_params) % sizeof(uint32_t) == 0, "ca_params is made of 32-bit fields");
+    void resize(size_t n_items)
+    {
+        n_ = n_items;
+        seq_.reset(new std::atomic<uint32_t>[n_items]);
+        words_.reset(new std::atomic<uint32_t>[n_items * kWords]);
+        for (size_t i = 0; i < n_items; i++) seq_[i].store(0, std::memory_order_relaxed);
+        for (size_t i = 0; i < n_items * kWords; i++) words_[i].store(0, std::memory_order_relaxed);
+    }
+    size_t size() const { return n_; }
+    void set(size_t item, const ca_params &p)
+    {
+        uint32_t w[kWords];
+        memcpy(w, &p, sizeof(p));
+        std::atomic<uint32_t> &sq = seq_[item];
+        uint32_t s = sq.load(std::memory_order_relaxed);
+        for (;;) {
+            if (s & 1u) { s = sq.load(std::memory_order_relaxed); continue; }
+            if (sq.compare_exchange_weak(s, s + 1, std::memory_order_acquire, std::memory_order_relaxed)) break;
+        }
+        // release stores: none of them may become visible before the odd sequence (no fence: ThreadSanitizer models none)
+        for (size_t k = 0; k < kWords; k++) words_[item * kWords + k].store(w[k], std::memory_order_release);
+        sq.store(s + 2, std::memory_order_release);
+    }
+    void get(size_t item, ca_params *p) const
+    {
+        uint32_t w[kWords];
+        const std::atomic<uint32_t> &sq = seq_[item];
+        for (;;) {
+            const uint32_t a = sq.load(std::memory_order_acquire);
+            for (size_t k = 0; k < kWords; k++) w[k] = words_[item * kWords + k].load(std::memory_order_acquire);  // the re-check below stays below
+            if (!(a & 1u) && sq.load(std::memory_order_relaxed) == a) break;
+        }
+        memcpy(p, w, sizeof(*p));
+    }
+
+private:
+    size_t n_ = 0;
+    std::unique_ptr<std::atomic<uint32_t>[]> seq_, words_;
 };

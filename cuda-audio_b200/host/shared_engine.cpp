@@ -216,13 +216,15 @@ bool SharedEngine::process(Convolution *c, int idx, const float *in1, const floa
     }
     // arrive -- unless this generation's batch already ran without us (we had been set aside, or we joined while the
     // runner was deciding): then this period is silence and the next one is in step again
+    // (the buffers are not touched again before the generation ends: leave the staging section BEFORE arriving, or a
+    // runner that sees the last arrival could still find _staging != 0 and put a rebuild off for no reason)
+    _staging.fetch_sub(1, std::memory_order_seq_cst);
     bool counted = false;
     while (genOf(s) == gen) {
         if (_state.compare_exchange_weak(s, s + 1, std::memory_order_acq_rel, std::memory_order_acquire)) { counted = true; break; }
     }
-    if (counted) _arrivedGen[idx].store(gen + 1, std::memory_order_release);
-    _staging.fetch_sub(1, std::memory_order_seq_cst);
     if (!counted) return false;
+    _arrivedGen[idx].store(gen + 1, std::memory_order_release);
 
     auto t0 = std::chrono::steady_clock::now();
     for (int spins = 0;; spins++) {

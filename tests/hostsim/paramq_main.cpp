@@ -66,6 +66,34 @@ int main(int argc, char **argv)
     ParamCmd c;
     if (q.pop(&c)) { fprintf(stderr, "FAIL: extra command\n"); failures++; }
     fprintf(stderr, "%d producers x %u commands, ring refused %llu pushes\n", W, N, (unsigned long long)refused.load());
+
+    {  // ParamMirror (what ca_get_params answers): several writers of the SAME item, readers never see a torn block
+        ParamMirror m;
+        m.resize(4);
+        auto block = [](uint32_t n) { ca_params p; p.select = n; p.predelay = n + 1; p.speed = n + 2; p.vsteps = -1; p.dry = (float)(n & 0xffff); p.wet = p.dry + 1.f; p.panDry = p.dry + 2.f; p.panWet = p.dry + 3.f; p.level = p.dry + 4.f; return p; };
+        m.set(2, block(0));
+        std::atomic<bool> stop{false};
+        std::atomic<uint64_t> torn{0}, reads{0};
+        std::vector<std::thread> writers, readers;
+        for (int w = 0; w < 3; w++) writers.emplace_back([&, w] { for (uint32_t n = 0; n < N; n++) m.set(2, block(n * 3 + (uint32_t)w)); });
+        for (int r = 0; r < 2; r++)
+            readers.emplace_back([&] {
+                while (!stop.load()) {
+                    ca_params p;
+                    m.get(2, &p);
+                    const float d = (float)(p.select & 0xffff);
+                    if (p.predelay != p.select + 1 || p.speed != p.select + 2 || p.dry != d || p.wet != d + 1.f || p.panDry != d + 2.f || p.panWet != d + 3.f || p.level != d + 4.f) torn.fetch_add(1);
+                    reads.fetch_add(1);
+                }
+            });
+        for (auto &t : writers) t.join();
+        stop.store(true);
+        for (auto &t : readers) t.join();
+        ca_params other;
+        m.get(1, &other);
+        if (torn.load() || other.select != 0 || other.level != 0.f) { fprintf(stderr, "FAIL: %llu torn reads of %llu\n", (unsigned long long)torn.load(), (unsigned long long)reads.load()); failures++; }
+        fprintf(stderr, "mirror: 3 writers x %u sets of one item, %llu reads, %llu torn\n", N, (unsigned long long)reads.load(), (unsigned long long)torn.load());
+    }
     printf("PARAMQ %s failures=%d\n", failures ? "FAIL" : "OK", failures);
     return failures ? 1 : 0;
 }

@@ -183,6 +183,8 @@ void unpacedDriverFirstBuild(int K, uint64_t P)
     fake_set_create_delay_us(0);
     CHECK(fake_violations() == v0, "contract violations");
     for (auto &x : m) CHECK(x->wrong == 0 && x->silent <= 2 && x->good + x->silent == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
+    auto g = m[0]->c->sharedGroup();
+    fprintf(stderr, "   rebuilds %llu batches %llu dropped %llu\n", (unsigned long long)g->rebuilds(), (unsigned long long)g->batches(), (unsigned long long)g->dropped());
 }
 
 void prepareOnLiveGroup(int K, uint64_t P)
@@ -317,14 +319,16 @@ int main(int argc, char **argv)
     const uint64_t P = argc > 1 ? (uint64_t)atoll(argv[1]) : 3000;
     const int K = argc > 2 ? atoi(argv[2]) : 6;
     hj_set_sample_rate(48000);
-    steady(K, P);
-    lockstepHost(K, P);
-    unpacedDriverFirstBuild(3, P);
-    prepareOnLiveGroup(K, P);
-    memberStopsAndResumes(4, P);
-    memberDestroyedMidRun(4, P);
-    buildFailureThenRecovery(3, P / 2);
-    singleObjectPrepareWhileRunning(P);
+    const std::string only = argc > 3 ? argv[3] : "";  // run one scenario only (debugging)
+    auto want = [&](const char *name) { return only.empty() || only == name; };
+    if (want("steady")) steady(K, P);
+    if (want("lockstep")) lockstepHost(K, P);
+    if (want("unpaced")) unpacedDriverFirstBuild(3, P);
+    if (want("prepare")) prepareOnLiveGroup(K, P);
+    if (want("stops")) memberStopsAndResumes(4, P);
+    if (want("destroyed")) memberDestroyedMidRun(4, P);
+    if (want("failure")) buildFailureThenRecovery(3, P / 2);
+    if (want("single")) singleObjectPrepareWhileRunning(P);
     fprintf(stderr, "engines created %llu destroyed %llu, batches %llu, IR loads %llu, violations %llu\n", (unsigned long long)fake_engines_created(),
             (unsigned long long)fake_engines_destroyed(), (unsigned long long)fake_periods_processed(), (unsigned long long)fake_ir_loads(), (unsigned long long)fake_violations());
     printf("HOSTSIM %s failures=%d violations=%llu\n", g_failures || fake_violations() ? "FAIL" : "OK", g_failures, (unsigned long long)fake_violations());

@@ -27,11 +27,16 @@ def _build(target):
 
 
 def _run(exe, periods, members, env=None):
-    r = subprocess.run([os.path.join(SIM, exe), str(periods), str(members)], capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
-    lines = [ln for ln in (r.stdout + r.stderr).splitlines() if not ln.startswith("[")]   # the mirror's log lines
-    tail = "\n".join(lines[-60:])
-    assert "ThreadSanitizer" not in r.stderr and "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, tail
-    assert r.returncode == 0 and "HOSTSIM OK" in r.stdout, tail
+    for attempt in range(2):
+        r = subprocess.run([os.path.join(SIM, exe), str(periods), str(members)], capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
+        lines = [ln for ln in (r.stdout + r.stderr).splitlines() if not ln.startswith("[")]   # the mirror's log lines
+        tail = "\n".join(lines[-60:])
+        # sanitizer reports and contract violations are never retried; the scenarios' own bounds (elapsed time, periods
+        # lost around a rebuild) get one second chance on a machine that is busy with something else
+        assert "ThreadSanitizer" not in r.stderr and "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr and "VIOLATION" not in r.stderr, tail
+        if r.returncode == 0 and "HOSTSIM OK" in r.stdout:
+            return
+    raise AssertionError(tail)
 
 
 def test_host_mirror_threading_plain():
