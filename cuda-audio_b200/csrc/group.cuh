@@ -242,6 +242,16 @@ int ca_group_set_glide(ca_group *g, uint32_t input, float glide)
     return CA_OK;
 }
 
+int ca_group_reset(ca_group *g)
+{
+    if (!g) return CA_ERR_INVALID;
+    for (uint32_t i = 0; i < g->G; i++) {  // every member restarts at the same period: their counters stay in step
+        const int rc = ca_reset(g->eng[i]);  // sets the device, drains, synchronises
+        if (rc) return rc;
+    }
+    return CA_OK;
+}
+
 int ca_group_process(ca_group *g, const float *in, float *out, uint32_t nframes)
 {
     if (!g || !in || !out) return CA_ERR_INVALID;

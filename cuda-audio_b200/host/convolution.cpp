@@ -21,6 +21,10 @@ EngineOptions EngineOptions::fromEnv()
     if (const char *v = getenv("CA_ENGINE_PERIOD")) o.period = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED")) o.shared = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED_TIMEOUT_MS")) o.sharedTimeoutMs = (uint32_t)atoi(v);
+    if (const char *v = getenv("CA_ENGINE_GPUS")) o.gpus = (uint32_t)std::max(1, atoi(v));
+    if (const char *v = getenv("CA_ENGINE_IR_SPLIT")) o.irSplit = (uint32_t)atoi(v);
+    if (const char *v = getenv("CA_ENGINE_EXCHANGE")) o.exchange = std::string(v) == "nccl" ? CA_EXCHANGE_NCCL : CA_EXCHANGE_P2P;
+    if (o.irSplit) o.shared = 0;  // one object IS the whole group of GPUs
     if (truthy(getenv("CA_ENGINE_ASYNC_TIERS"))) o.flags |= CA_FLAG_ASYNC_TIERS;
     if (truthy(getenv("CA_ENGINE_REF_QUIRKS"))) o.flags |= CA_FLAG_REF_QUIRKS;
     if (o.shared > 1) o.flags = (o.flags & ~(uint32_t)CA_FLAG_GRAPH) | CA_FLAG_STREAMING;  // batches: host-driven launches + PDL
@@ -37,6 +41,10 @@ EngineOptions EngineOptions::fromSettings(Settings &st)
     if (st.has("engine.period")) o.period = st.u32("engine.period");
     if (st.has("engine.shared")) o.shared = st.u32("engine.shared");
     if (st.has("engine.shared_timeout_ms")) o.sharedTimeoutMs = st.u32("engine.shared_timeout_ms");
+    if (st.has("engine.gpus")) o.gpus = std::max<uint32_t>(1, st.u32("engine.gpus"));
+    if (st.has("engine.ir_split")) o.irSplit = st.u32("engine.ir_split");
+    if (st.has("engine.exchange")) o.exchange = st.str("engine.exchange") == "nccl" ? CA_EXCHANGE_NCCL : CA_EXCHANGE_P2P;
+    if (o.irSplit) o.shared = 0;
     auto flag = [&](const char *key, uint32_t bit, bool dflt) {
         const bool on = st.has(key) ? truthy(st.str(key).c_str()) : dflt;
         o.flags = on ? (o.flags | bit) : (o.flags & ~bit);
@@ -56,16 +64,29 @@ static EngineOptions &defaultOptions()
     return o;
 }
 
-void Convolution::setDefaultOptions(const EngineOptions &o) { defaultOptions() = o; }
+// engine.gpus: objects are dealt onto the GPUs in construction order (main.cu:31-39 constructs conv.count/2 of them)
+static std::atomic<uint32_t> g_constructed{0};
+static EngineOptions nextOptions()
+{
+    EngineOptions o = defaultOptions();
+    if (o.gpus > 1) o.device += (int)((g_constructed.fetch_add(1) % o.gpus) * std::max<uint32_t>(1, o.irSplit));
+    return o;
+}
+
+void Convolution::setDefaultOptions(const EngineOptions &o)
+{
+    defaultOptions() = o;
+    g_constructed.store(0);
+}
 
 void Convolution::setOptions(const EngineOptions &o)
 {
-    if (_engine || _shared) { fail(CA_ERR_STATE, "setOptions: the engine is already built"); return; }
+    if (built() || _shared) { fail(CA_ERR_STATE, "setOptions: the engine is already built"); return; }
     _opt = o;
     if (_opt.shared > 1) _shared = SharedEngine::join(this, _opt, &_sharedIdx);
 }
 
-Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize), _opt(defaultOptions())
+Convolution::Convolution(const std::string &name, size_t fftSize) : JackClient(name), capture{nullptr, nullptr}, playback{nullptr, nullptr}, _fftSize(fftSize), _opt(nextOptions())
 {
     for (auto &h : _hasIR) h.store(false, std::memory_order_relaxed);
     if (_opt.shared > 1) _shared = SharedEngine::join(this, _opt, &_sharedIdx);
@@ -75,7 +96,7 @@ Convolution::~Convolution()
 {
     stop();  // no callback may be running or arrive from here on
     if (_shared) _shared->leave(this);
-    if (_engine) ca_destroy(_engine);
+    destroyEngine();
     if (_in) ca_host_free(_in);
     if (_out) ca_host_free(_out);
 }
@@ -114,17 +135,39 @@ bool Convolution::buildNow(size_t period)
 {
     if (_shared) return _shared->buildNow(period, samplerate ? (float)samplerate : _sampleRate);
     std::lock_guard<std::mutex> lk(_engineMutex);
-    if (_engine && _period == period) return true;
-    if (_engine) { ca_destroy(_engine); _engine = nullptr; }
+    if (built() && _period == period) return true;
+    destroyEngine();
     if (!buildEngine(period)) return false;
     pushParams(true);
     // one silent period: first-launch costs (module load, graph upload) are paid here, not in the callback
     memset(_in, 0, 2 * period * sizeof(float));
-    const int rc = ca_process(_engine, _in, _out, (uint32_t)period);
+    const int rc = processBlock((uint32_t)period);
     if (rc) { fail(rc, "ca_process (warm-up)"); return false; }
-    ca_reset(_engine);  // the warm-up period must not count as the first step of the fade-in glide (conv.cu:15-32)
+    resetEngine();  // the warm-up period must not count as the first step of the fade-in glide (conv.cu:15-32)
     return true;
 }
+
+// ---- the engine behind this object: a ca_engine of its own, or (engine.ir_split) a ca_group over several GPUs ----
+void Convolution::destroyEngine()
+{
+    if (_engine) ca_destroy(_engine);
+    if (_group) ca_group_destroy(_group);
+    _engine = nullptr;
+    _group = nullptr;
+}
+
+int Convolution::loadIR(size_t idx, const HostIR &ir)
+{
+    return _group ? ca_group_load_ir(_group, (uint32_t)idx, ir.left.data(), ir.right.data(), (uint32_t)ir.left.size())
+                  : ca_load_ir(_engine, (uint32_t)idx, ir.left.data(), ir.right.data(), (uint32_t)ir.left.size());
+}
+
+int Convolution::processBlock(uint32_t nframes)
+{
+    return _group ? ca_group_process(_group, _in, _out, nframes) : ca_process(_engine, _in, _out, nframes);  // pinned staging: used in place
+}
+
+int Convolution::resetEngine() { return _group ? ca_group_reset(_group) : ca_reset(_engine); }
 
 // conv.cu:207-253: the stereo IR `wav` (device float2 frames, half scale) becomes bank entry idx,
 // truncated to fftSize - nframes frames.  Synchronous: wav may be destroyed on return.
@@ -165,11 +208,10 @@ void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
     std::lock_guard<std::mutex> lk(_engineMutex);
     store();
     const HostIR &cur = _irs[idx];
-    if (_engine) {
-        if (idx < _engineSlots && n <= _engineCapFrames && ca_load_ir(_engine, (uint32_t)idx, cur.left.data(), cur.right.data(), (uint32_t)n) == CA_OK) return;
+    if (built()) {
+        if (idx < _engineSlots && n <= _engineCapFrames && loadIR(idx, cur) == CA_OK) return;
         const size_t period = _period;
-        ca_destroy(_engine);
-        _engine = nullptr;
+        destroyEngine();
         if (buildEngine(period)) pushParams(true);
     } else if (_opt.period) {
         // period known up front (engine.period): build as soon as there is an IR, rebuild above when the bank grows
@@ -180,37 +222,59 @@ void Convolution::prepare(size_t idx, const WavFile &wav, size_t nframes)
 bool Convolution::buildEngine(size_t period)
 {
     if (_irs.empty()) { fail(CA_ERR_STATE, "onProcess: no IR prepared"); return false; }
-    ca_config cfg;
-    ca_config_init(&cfg);
-    cfg.device = _opt.device;
-    cfg.period = (uint32_t)period;
-    cfg.n_instances = 1;
-    cfg.n_in = cfg.n_out = 2;
     size_t longest = 1;
     for (auto &kv : _irs) longest = std::max(longest, kv.second.left.size());
-    cfg.max_ir_frames = (uint32_t)longest;
-    cfg.n_ir_slots = (uint32_t)(_irs.rbegin()->first + 1);
-    cfg.flags = _opt.flags;
-    if (cfg.flags & CA_FLAG_REF_QUIRKS) {
-        if (_fftSize % period == 0 && _fftSize >= 2 * period) cfg.ref_fft_size = (uint32_t)_fftSize;  // Convolution(name, fftSize), conv.cu:142
-        else cfg.flags &= ~(uint32_t)CA_FLAG_REF_QUIRKS;  // the reference itself only works for such sizes
+    const uint32_t slots = (uint32_t)(_irs.rbegin()->first + 1);
+    const float rate = samplerate ? (float)samplerate : _sampleRate;
+    int rc;
+    if (_opt.irSplit) {
+        // one IR over several GPUs (BASELINE configs[4]): the reference's only answer to a long IR is a bigger fftSize
+        // on one GPU (conv.cu:239, conv.h:63)
+        ca_group_config gc;
+        ca_group_config_init(&gc);
+        gc.n_devices = std::min<uint32_t>(_opt.irSplit, 8);
+        for (uint32_t g = 0; g < gc.n_devices; g++) gc.devices[g] = _opt.device + (int)g;
+        gc.period = (uint32_t)period;
+        gc.n_in = gc.n_out = 2;
+        gc.max_ir_frames = (uint32_t)longest;
+        gc.n_ir_slots = slots;
+        gc.flags = _opt.flags & (uint32_t)(CA_FLAG_STREAMING | CA_FLAG_L2_PERSIST);
+        gc.exchange = _opt.exchange;
+        gc.max_voices = 3;
+        gc.sample_rate = rate;
+        rc = ca_group_create(&gc, &_group);
+        if (rc) { _group = nullptr; fail(rc, "ca_group_create"); return false; }
+    } else {
+        ca_config cfg;
+        ca_config_init(&cfg);
+        cfg.device = _opt.device;
+        cfg.period = (uint32_t)period;
+        cfg.n_instances = 1;
+        cfg.n_in = cfg.n_out = 2;
+        cfg.max_ir_frames = (uint32_t)longest;
+        cfg.n_ir_slots = slots;
+        cfg.flags = _opt.flags;
+        if (cfg.flags & CA_FLAG_REF_QUIRKS) {
+            if (_fftSize % period == 0 && _fftSize >= 2 * period) cfg.ref_fft_size = (uint32_t)_fftSize;  // Convolution(name, fftSize), conv.cu:142
+            else cfg.flags &= ~(uint32_t)CA_FLAG_REF_QUIRKS;  // the reference itself only works for such sizes
+        }
+        cfg.max_voices = 3;  // old IR + new IR + one more switch in flight during a cross-fade
+        cfg.sample_rate = rate;
+        if (_opt.autoTiers && ca_config_auto_tiers(&cfg, _opt.tierGrowth, _opt.tierMaxBlock) != CA_OK) { fail(CA_ERR_INVALID, "ca_config_auto_tiers"); return false; }
+        rc = ca_create(&cfg, &_engine);
+        if (rc) { _engine = nullptr; fail(rc, "ca_create"); return false; }
     }
-    cfg.max_voices = 3;  // old IR + new IR + one more switch in flight during a cross-fade
-    cfg.sample_rate = samplerate ? (float)samplerate : _sampleRate;
-    if (_opt.autoTiers && ca_config_auto_tiers(&cfg, _opt.tierGrowth, _opt.tierMaxBlock) != CA_OK) { fail(CA_ERR_INVALID, "ca_config_auto_tiers"); return false; }
-    int rc = ca_create(&cfg, &_engine);
-    if (rc) { _engine = nullptr; fail(rc, "ca_create"); return false; }
     for (auto &kv : _irs) {
-        rc = ca_load_ir(_engine, (uint32_t)kv.first, kv.second.left.data(), kv.second.right.data(), (uint32_t)kv.second.left.size());
-        if (rc) { fail(rc, "ca_load_ir"); ca_destroy(_engine); _engine = nullptr; return false; }
+        rc = loadIR(kv.first, kv.second);
+        if (rc) { fail(rc, "ca_load_ir"); destroyEngine(); return false; }
     }
     _period = period;
-    _engineSlots = cfg.n_ir_slots;
-    _engineCapFrames = cfg.max_ir_frames;
+    _engineSlots = slots;
+    _engineCapFrames = longest;
     if (_in) ca_host_free(_in);
     if (_out) ca_host_free(_out);
     _in = _out = nullptr;
-    if (ca_host_alloc((void **)&_in, 2 * period * sizeof(float)) || ca_host_alloc((void **)&_out, 2 * period * sizeof(float))) { fail(CA_ERR_NOMEM, "ca_host_alloc"); ca_destroy(_engine); _engine = nullptr; return false; }
+    if (ca_host_alloc((void **)&_in, 2 * period * sizeof(float)) || ca_host_alloc((void **)&_out, 2 * period * sizeof(float))) { fail(CA_ERR_NOMEM, "ca_host_alloc"); destroyEngine(); return false; }
     memset(_in, 0, 2 * period * sizeof(float));
     memset(_out, 0, 2 * period * sizeof(float));
     _havePushed = false;
@@ -260,7 +324,7 @@ void Convolution::pushParamsTo(ca_engine *e, uint32_t instance, size_t slotBase,
             q.speed = (uint32_t)v.speed;
             q.vsteps = (vstepsChanged || !_havePushed) ? (int32_t)v.vsteps : -1;
             q.dry = v.dry; q.wet = v.wet; q.panDry = v.panDry; q.panWet = v.panWet; q.level = v.level;
-            const int rc = ca_set_params(e, instance, (uint32_t)i, &q);
+            const int rc = (_group && e == nullptr) ? ca_group_set_params(_group, (uint32_t)i, &q) : ca_set_params(e, instance, (uint32_t)i, &q);
             if (rc) fail(rc, "ca_set_params");
             p = v;
         }
@@ -287,15 +351,15 @@ void Convolution::onProcess(size_t nframes)
     } else {
         std::unique_lock<std::mutex> lk(_engineMutex, std::try_to_lock);
         if (!lk.owns_lock()) { silence(); _skipped++; return; }  // prepare() is loading an IR: never block the RT thread
-        if (!_engine || _period != nframes) {
+        if (!built() || _period != nframes) {
             // no buildNow() / onStart() with a known buffer size came first (plain harness): build here
-            if (_engine) { ca_destroy(_engine); _engine = nullptr; }
+            destroyEngine();
             if (!buildEngine(nframes)) { silence(); return; }
         }
         pushParams(false);
         memcpy(_in, IN1, nframes * sizeof(float));
         memcpy(_in + nframes, IN2, nframes * sizeof(float));
-        const int rc = ca_process(_engine, _in, _out, (uint32_t)nframes);  // pinned staging: used in place
+        const int rc = processBlock((uint32_t)nframes);
         if (rc) { fail(rc, "ca_process"); silence(); return; }
         memcpy(L, _out, nframes * sizeof(float));
         memcpy(R, _out + nframes, nframes * sizeof(float));

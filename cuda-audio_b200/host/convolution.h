@@ -54,6 +54,13 @@ class SharedEngine;
 //   engine.shared <N>            every N consecutive Convolution objects of the process are the N instances of
 //                                ONE batched engine (one set of kernel launches per JACK cycle for all of them)
 //   engine.shared_timeout_ms <n> how long the others wait for a member that stopped calling (default 200)
+//   engine.gpus <G>              the process's Convolution objects are dealt round-robin onto G GPUs starting at
+//                                engine.device (independent streams, no collective); shared batches
+//                                form per GPU
+//   engine.ir_split <G>          ONE object's IR is split by partition range over G GPUs (engine.device ..
+//                                engine.device + G - 1) behind the same prepare / onProcess surface: the ca_group of
+//                                the C ABI (BASELINE configs[4]); engine.exchange p2p|nccl picks the
+//                                exchange (default p2p: fused into the MAC kernel over NVLink)
 // The same options can come from the environment (CA_ENGINE_TIERS, CA_ENGINE_SHARED, CA_ENGINE_PERIOD,
 // CA_ENGINE_DEVICE, CA_ENGINE_ASYNC_TIERS) for drivers that construct Convolution objects themselves.
 struct EngineOptions {
@@ -63,6 +70,9 @@ struct EngineOptions {
     uint32_t tierGrowth = 0, tierMaxBlock = 0;
     uint32_t period = 0;
     uint32_t shared = 0;
+    uint32_t gpus = 1;        // engine.gpus
+    uint32_t irSplit = 0;     // engine.ir_split: > 0 = this many GPUs behind one object (ca_group)
+    uint32_t exchange = 0;    // engine.exchange: ca_exchange (CA_EXCHANGE_P2P / CA_EXCHANGE_NCCL)
     uint32_t sharedTimeoutMs = 200;  // engine.shared: a member that has not arrived for this long is set aside until it calls again
     static EngineOptions fromEnv();
     static EngineOptions fromSettings(Settings &settings);
@@ -104,6 +114,7 @@ public:
     int lastError() const { return _lastError; }          // ca_error of the last failing call, 0 = none
     const std::string &lastErrorText() const { return _lastErrorText; }
     ca_engine *engine() const { return _engine; }          // null until the engine is built (buildNow / onStart / first onProcess)
+    ca_group *group() const { return _group; }             // engine.ir_split: the multi-GPU group that stands in for the engine
     void setDevice(int device) { _opt.device = device; }   // before the engine is built
     void setFlags(uint32_t flags) { _opt.flags = flags; }  // ca_flags, before the engine is built
     void setSampleRate(float fs) { _sampleRate = fs; }
@@ -135,6 +146,12 @@ private:
     std::atomic<size_t> _numIRs{0}, _firstIR{0};
     size_t _minPrepareFrames = 1024;
     ca_engine *_engine = nullptr;
+    ca_group *_group = nullptr;  // engine.ir_split: used instead of _engine (same lock, same life cycle)
+    bool built() const { return _engine || _group; }
+    void destroyEngine();
+    int loadIR(size_t idx, const HostIR &ir);
+    int processBlock(uint32_t nframes);
+    int resetEngine();
     std::mutex _engineMutex;  // prepare() on a live engine vs onProcess(): the RT thread only try_locks (silence on contention)
     size_t _period = 0, _engineSlots = 0, _engineCapFrames = 0;
     EngineOptions _opt;

@@ -39,7 +39,7 @@ struct Options {
     unsigned rate = 0;
     double synthIr = 0, synthIn = 0;
     bool mono = false;
-    int bits = 32, device = 0, warmup = 0;
+    int bits = 32, device = -1, warmup = 0;  // device -1: engine.device / engine.gpus of the settings file (default 0)
     float wet = -1, dry = -1, level = -1, panWet = -2, panDry = -2;
     long predelay = -1;
     bool resample = false;
@@ -199,7 +199,7 @@ int main(int argc, char **argv)
             if (!o.fftSize) fftSize = fs1;
         }
         auto c = std::make_unique<Convolution>(std::string("cudaconv_") + char('1' + (int)n), fftSize);
-        c->setDevice(o.device);
+        if (o.device >= 0) c->setDevice(o.device);  // --device overrides engine.device / engine.gpus
         c->setSampleRate((float)rate);
         for (int i = 0; i < 2; i++) {
             const int idx = (int)(n * 2 + i);

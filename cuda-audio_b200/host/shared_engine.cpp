@@ -3,11 +3,12 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <thread>
 
 namespace {
 std::mutex g_registryMutex;
-std::shared_ptr<SharedEngine> g_open;  // the group that still has room
+std::map<int, std::shared_ptr<SharedEngine>> g_openByDevice;  // per GPU (engine.gpus): the group that still has room
 
 constexpr uint64_t kCountMask = 0xffff;
 inline uint64_t genOf(uint64_t s) { return s >> 16; }
@@ -32,6 +33,7 @@ SharedEngine::SharedEngine(const EngineOptions &opt) : _opt(opt)
 std::shared_ptr<SharedEngine> SharedEngine::join(Convolution *c, const EngineOptions &opt, int *index)
 {
     std::lock_guard<std::mutex> lk(g_registryMutex);
+    std::shared_ptr<SharedEngine> &g_open = g_openByDevice[opt.device];
     if (!g_open || g_open->_members.size() >= g_open->_opt.shared || g_open->_opt.shared != opt.shared)
         g_open = std::shared_ptr<SharedEngine>(new SharedEngine(opt));
     std::lock_guard<std::mutex> bl(g_open->_buildMutex);  // a rebuild at the rendezvous walks _members

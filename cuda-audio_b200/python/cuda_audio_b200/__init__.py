@@ -29,7 +29,7 @@ EXPORTS = [
     "ca_load_ir", "ca_load_ir_device", "ca_load_ir_interleaved_device", "ca_set_params", "ca_get_params", "ca_set_glide", "ca_set_active", "ca_reset",
     "ca_process", "ca_process_device", "ca_sync", "ca_stream", "ca_get_stats", "ca_reset_stats",
     "ca_host_alloc", "ca_host_free", "ca_measure_read_gbs", "ca_persist_stamps",
-    "ca_group_config_init", "ca_group_create", "ca_group_destroy", "ca_group_load_ir", "ca_group_set_params", "ca_group_set_glide",
+    "ca_group_config_init", "ca_group_create", "ca_group_destroy", "ca_group_load_ir", "ca_group_set_params", "ca_group_set_glide", "ca_group_reset",
     "ca_group_process", "ca_group_get_stats", "ca_group_reset_stats",
 ]
 EXCHANGE_P2P, EXCHANGE_NCCL = 0, 1
@@ -138,6 +138,7 @@ def lib():
         L.ca_group_load_ir.argtypes = [vp, C.c_uint32, f32p, f32p, C.c_uint32]
         L.ca_group_set_params.argtypes = [vp, C.c_uint32, C.POINTER(Params)]
         L.ca_group_set_glide.argtypes = [vp, C.c_uint32, C.c_float]
+        L.ca_group_reset.argtypes = [vp]
         L.ca_group_process.argtypes = [vp, vp, vp, C.c_uint32]
         L.ca_group_get_stats.argtypes = [vp, C.POINTER(GroupStats)]
         L.ca_group_reset_stats.argtypes = [vp]
@@ -380,6 +381,9 @@ class Group:
         s = GroupStats()
         _check(lib().ca_group_get_stats(self._h, C.byref(s)), "ca_group_get_stats")
         return s
+
+    def reset(self):
+        _check(lib().ca_group_reset(self._h), "ca_group_reset")
 
     def reset_stats(self):
         _check(lib().ca_group_reset_stats(self._h), "ca_group_reset_stats")

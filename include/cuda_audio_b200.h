@@ -269,6 +269,8 @@ int ca_group_destroy(ca_group *g);
 int ca_group_load_ir(ca_group *g, uint32_t slot, const float *left, const float *right, uint32_t frames);
 int ca_group_set_params(ca_group *g, uint32_t input, const ca_params *p);
 int ca_group_set_glide(ca_group *g, uint32_t input, float glide);
+/* ca_reset on every member: history dropped, wet glide from silence again (after a silent warm-up period). */
+int ca_group_reset(ca_group *g);
 /* One period: in = planar [n_in][nframes], out = planar [n_out][nframes], host memory; synchronous. */
 int ca_group_process(ca_group *g, const float *in, float *out, uint32_t nframes);
 int ca_group_get_stats(ca_group *g, ca_group_stats *s);

@@ -24,6 +24,7 @@ namespace {
 std::atomic<uint64_t> g_violations{0}, g_created{0}, g_destroyed{0}, g_processed{0}, g_loads{0};
 std::atomic<int> g_processDelayUs{0}, g_createDelayUs{0};
 std::atomic<int> g_failCreate{0};
+std::atomic<uint64_t> g_onDevice[16], g_groups{0};
 
 void violation(const char *what)
 {
@@ -73,6 +74,8 @@ uint64_t fake_engines_created(void) { return g_created.load(); }
 uint64_t fake_engines_destroyed(void) { return g_destroyed.load(); }
 uint64_t fake_periods_processed(void) { return g_processed.load(); }
 uint64_t fake_ir_loads(void) { return g_loads.load(); }
+uint64_t fake_engines_on_device(int d) { return d >= 0 && d < 16 ? g_onDevice[d].load() : 0; }
+uint64_t fake_groups_created(void) { return g_groups.load(); }
 void fake_set_process_delay_us(int us) { g_processDelayUs.store(us); }
 void fake_set_create_delay_us(int us) { g_createDelayUs.store(us); }
 void fake_fail_next_creates(int n) { g_failCreate.store(n); }
@@ -103,8 +106,10 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     if (!cfg || !out || cfg->struct_size != sizeof(ca_config) || !cfg->n_instances || !cfg->n_ir_slots || !cfg->period) { violation("ca_create: bad config"); return CA_ERR_INVALID; }
     if (int us = g_createDelayUs.load()) std::this_thread::sleep_for(std::chrono::microseconds(us));
     if (g_failCreate.load() > 0 && g_failCreate.fetch_sub(1) > 0) return CA_ERR_NOMEM;
+    if (cfg->device < 0 || cfg->device >= 16) { violation("ca_create: device out of range"); return CA_ERR_INVALID; }
     *out = new ca_engine(*cfg);
     g_created.fetch_add(1);
+    g_onDevice[cfg->device].fetch_add(1);
     return CA_OK;
 }
 
@@ -171,6 +176,42 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
     g_processed.fetch_add(1);
     return CA_OK;
 }
+
+// ---- ca_group (one IR over several GPUs): the double is one 1-instance engine that remembers the devices it was given ----
+void ca_group_config_init(ca_group_config *cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(*cfg);
+    cfg->n_devices = 1;
+    cfg->period = 256;
+    cfg->n_in = cfg->n_out = 2;
+    cfg->n_ir_slots = 2;
+}
+
+int ca_group_create(const ca_group_config *gc, ca_group **out)
+{
+    if (!gc || !out || gc->struct_size != sizeof(*gc) || gc->n_devices < 1 || gc->n_devices > 8) { violation("ca_group_create: bad config"); return CA_ERR_INVALID; }
+    for (uint32_t i = 0; i < gc->n_devices; i++)
+        for (uint32_t j = 0; j < i; j++)
+            if (gc->devices[i] == gc->devices[j]) { violation("ca_group_create: a device appears twice"); return CA_ERR_INVALID; }
+    ca_config cfg;
+    ca_config_init(&cfg);
+    cfg.device = gc->devices[0];
+    cfg.period = gc->period; cfg.n_in = gc->n_in; cfg.n_out = gc->n_out;
+    cfg.max_ir_frames = gc->max_ir_frames; cfg.n_ir_slots = gc->n_ir_slots;
+    ca_engine *e = nullptr;
+    const int rc = ca_create(&cfg, &e);
+    if (rc) return rc;
+    for (uint32_t i = 1; i < gc->n_devices; i++) g_onDevice[gc->devices[i] & 15].fetch_add(1);
+    g_groups.fetch_add(1);
+    *out = reinterpret_cast<ca_group *>(e);
+    return CA_OK;
+}
+int ca_group_destroy(ca_group *g) { return ca_destroy(reinterpret_cast<ca_engine *>(g)); }
+int ca_group_load_ir(ca_group *g, uint32_t slot, const float *l, const float *r, uint32_t frames) { return ca_load_ir(reinterpret_cast<ca_engine *>(g), slot, l, r, frames); }
+int ca_group_set_params(ca_group *g, uint32_t input, const ca_params *p) { return ca_set_params(reinterpret_cast<ca_engine *>(g), 0, input, p); }
+int ca_group_reset(ca_group *g) { return ca_reset(reinterpret_cast<ca_engine *>(g)); }
+int ca_group_process(ca_group *g, const float *in, float *out, uint32_t nframes) { return ca_process(reinterpret_cast<ca_engine *>(g), in, out, nframes); }
 
 // "pinned" memory: plain heap, so AddressSanitizer sees every access after ca_host_free
 int ca_host_alloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? CA_OK : CA_ERR_NOMEM; }

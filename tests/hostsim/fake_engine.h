@@ -9,6 +9,8 @@ uint64_t fake_engines_created(void);
 uint64_t fake_engines_destroyed(void);
 uint64_t fake_periods_processed(void); /* ca_process calls that ran */
 uint64_t fake_ir_loads(void);
+uint64_t fake_engines_on_device(int device); /* engines (and group members) created on that device ordinal */
+uint64_t fake_groups_created(void);
 void fake_set_process_delay_us(int us); /* every ca_process sleeps this long (widens the windows) */
 void fake_set_create_delay_us(int us);  /* every ca_create sleeps this long (a build takes a while) */
 void fake_fail_next_creates(int n);     /* the next n ca_create calls fail with CA_ERR_NOMEM */

@@ -286,6 +286,53 @@ void buildFailureThenRecovery(int K, uint64_t P)
     for (auto &x : m) CHECK(x->good >= P - 20 && x->good + x->silent == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
 }
 
+// engine.gpus 2 + engine.shared 3: six objects become two batches of three, one per GPU; engine.ir_split 2: one object
+// whose engine is a group over two GPUs, with prepare() against its running callback
+void multiGpuOptions(uint64_t P)
+{
+    fprintf(stderr, "== engine.gpus / engine.ir_split\n");
+    const uint64_t v0 = fake_violations(), d0 = fake_engines_on_device(0), d1 = fake_engines_on_device(1);
+    {
+        EngineOptions o;
+        o.shared = 3; o.gpus = 2; o.period = (uint32_t)B; o.sharedTimeoutMs = 5000; o.flags = CA_FLAG_STREAMING;
+        Convolution::setDefaultOptions(o);
+        Members m;
+        for (int k = 0; k < 6; k++) { m.emplace_back(new Member()); m.back()->open(k); prepareIR(*m.back()->c, k, 0); prepareIR(*m.back()->c, k, 1); }
+        for (auto &x : m) x->start();
+        CHECK(m[0]->c->options().device == 0 && m[1]->c->options().device == 1 && m[4]->c->options().device == 0, "objects are not dealt round-robin onto the GPUs");
+        CHECK(m[0]->c->sharedGroup() == m[2]->c->sharedGroup() && m[0]->c->sharedGroup() == m[4]->c->sharedGroup() && m[1]->c->sharedGroup() == m[5]->c->sharedGroup() &&
+              m[0]->c->sharedGroup() != m[1]->c->sharedGroup(), "batches do not form per GPU");
+        runThreads(m, P);
+        for (auto &x : m) CHECK(x->wrong == 0 && x->silent == 0 && x->good == P, "member %d: good %llu silent %llu wrong %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent, (unsigned long long)x->wrong);
+        CHECK(fake_engines_on_device(0) - d0 == 1 && fake_engines_on_device(1) - d1 == 1, "expected one batched engine per GPU");
+    }
+    {
+        const uint64_t g0 = fake_groups_created(), e0 = fake_engines_on_device(2), e1 = fake_engines_on_device(3);
+        EngineOptions o;
+        o.irSplit = 2; o.device = 2; o.period = (uint32_t)B;
+        Convolution::setDefaultOptions(o);
+        Members m;
+        m.emplace_back(new Member());
+        m[0]->open(0);
+        prepareIR(*m[0]->c, 0, 0);
+        prepareIR(*m[0]->c, 0, 1);
+        m[0]->start();
+        CHECK(m[0]->c->group() != nullptr && m[0]->c->engine() == nullptr, "engine.ir_split did not build a group");
+        fake_set_process_delay_us(20);
+        runThreads(m, P, [&] {
+            for (int round = 0; round < 6; round++) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(5));
+                prepareIR(*m[0]->c, 0, round % 2 ? 2 : 1, 300 + 40 * round);
+                if (round % 2) m[0]->ir2Ready.store(true, std::memory_order_release);
+            }
+        });
+        fake_set_process_delay_us(0);
+        CHECK(m[0]->wrong == 0 && m[0]->good > P / 2 && m[0]->good + m[0]->silent == P, "ir_split: good %llu silent %llu wrong %llu", (unsigned long long)m[0]->good, (unsigned long long)m[0]->silent, (unsigned long long)m[0]->wrong);
+        CHECK(fake_groups_created() > g0 && fake_engines_on_device(2) > e0 && fake_engines_on_device(3) > e1, "the group does not span devices 2 and 3");
+    }
+    CHECK(fake_violations() == v0, "contract violations");
+}
+
 void singleObjectPrepareWhileRunning(uint64_t P)
 {
     fprintf(stderr, "== one Convolution of its own: prepare() from a control thread against the running callback\n");
@@ -329,6 +376,7 @@ int main(int argc, char **argv)
     if (want("destroyed")) memberDestroyedMidRun(4, P);
     if (want("failure")) buildFailureThenRecovery(3, P / 2);
     if (want("single")) singleObjectPrepareWhileRunning(P);
+    if (want("multigpu")) multiGpuOptions(P);
     fprintf(stderr, "engines created %llu destroyed %llu, batches %llu, IR loads %llu, violations %llu\n", (unsigned long long)fake_engines_created(),
             (unsigned long long)fake_engines_destroyed(), (unsigned long long)fake_periods_processed(), (unsigned long long)fake_ir_loads(), (unsigned long long)fake_violations());
     printf("HOSTSIM %s failures=%d violations=%llu\n", g_failures || fake_violations() ? "FAIL" : "OK", g_failures, (unsigned long long)fake_violations());

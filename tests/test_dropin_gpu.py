@@ -213,6 +213,23 @@ def test_shared_batched_engine_through_the_class_api():
     assert res["K"] == 3 and max(res["rel_l2"]) < 5e-6, res
 
 
+@needs_libs
+@pytest.mark.parametrize("G", [1, 2])
+def test_ir_split_group_through_the_class_api(G):
+    """`engine.ir_split` / CA_ENGINE_IR_SPLIT: the engine behind ONE mirror Convolution object is a ca_group over G GPUs
+    (BASELINE configs[4]; G = 1 runs the same code path on one GPU), same prepare / onProcess surface, results
+    against fp64, including a prepare() that rebuilds the live group."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < G:
+        pytest.skip("needs %d GPUs" % G)
+    env = dict(os.environ, CA_ENGINE_IR_SPLIT=str(G))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_irsplit_worker.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("IRSPLIT_RESULT ")][-1].split(" ", 1)[1])
+    assert res["G"] == G and res["rel_l2"] < 5e-6 and res["rel_l2_after_prepare"] < 5e-6, res
+
+
 def test_render_with_engine_keys_shared_and_tiers(tmp_path):
     """settings.txt `engine.*` keys reach the engine: two instances as ONE shared, tiered, batched engine give
     the same audio as two private uniform engines."""

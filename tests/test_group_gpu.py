@@ -111,3 +111,27 @@ def test_group_cfg5_60s_ir_sampled_fp64_and_fftconvolve():
     idx = np.sort(np.random.default_rng(3).integers(L, B * nper, 2000))
     d = O.direct_conv_at(x[0], irs[0][0], idx) + O.direct_conv_at(x[1], irs[1][0], idx)
     assert O.rel_l2(y[0][idx], d) < 1e-4
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_group_reset_restarts_every_member_in_step(world):
+    """ca_group_reset (the host mirror calls it after its silent warm-up period): history and glide state are dropped on
+    every member at the same period, so a second render of the same input repeats the first one bit for bit and
+    matches fp64 with the wet fade-in starting from silence again."""
+    if n_gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    m = ca()
+    B, L = 256, 256 * 37 + 9
+    irs = irs2x2(L, 8700)
+    x = np.stack([O.synth_audio(B * 120, 8800 + i, rms=0.3) for i in range(2)])
+    pr = [dict(wet=0.9, dry=0.3, panWet=0.2), dict(wet=0.7, dry=0.1, panDry=0.3)]
+    with m.Group(list(range(world)), period=B, max_ir_frames=L) as g:
+        for i in range(2):
+            g.load_ir(i, irs[i][0], irs[i][1])
+            g.set_params(i, select=i, **pr[i])
+        y1 = g.render(x)
+        g.reset()
+        y2 = g.render(x)
+        assert np.array_equal(y1, y2)
+        assert g.stats().peer_timeout == 0
+    assert np.abs(y1[:, :B]).max() < np.abs(y1[:, 60 * B:61 * B]).max()      # the fade-in of a fresh object (conv.cu:27)
