@@ -21,6 +21,7 @@ EngineOptions EngineOptions::fromEnv()
     if (const char *v = getenv("CA_ENGINE_PERIOD")) o.period = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED")) o.shared = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_SHARED_TIMEOUT_MS")) o.sharedTimeoutMs = (uint32_t)atoi(v);
+    if (const char *v = getenv("CA_ENGINE_SHARED_LATENCY")) o.sharedLatency = (uint32_t)atoi(v) ? 1u : 0u;
     if (const char *v = getenv("CA_ENGINE_GPUS")) o.gpus = (uint32_t)std::max(1, atoi(v));
     if (const char *v = getenv("CA_ENGINE_IR_SPLIT")) o.irSplit = (uint32_t)atoi(v);
     if (const char *v = getenv("CA_ENGINE_EXCHANGE")) o.exchange = std::string(v) == "nccl" ? CA_EXCHANGE_NCCL : CA_EXCHANGE_P2P;
@@ -41,6 +42,7 @@ EngineOptions EngineOptions::fromSettings(Settings &st)
     if (st.has("engine.period")) o.period = st.u32("engine.period");
     if (st.has("engine.shared")) o.shared = st.u32("engine.shared");
     if (st.has("engine.shared_timeout_ms")) o.sharedTimeoutMs = st.u32("engine.shared_timeout_ms");
+    if (st.has("engine.shared_latency")) o.sharedLatency = st.u32("engine.shared_latency") ? 1u : 0u;
     if (st.has("engine.gpus")) o.gpus = std::max<uint32_t>(1, st.u32("engine.gpus"));
     if (st.has("engine.ir_split")) o.irSplit = st.u32("engine.ir_split");
     if (st.has("engine.exchange")) o.exchange = st.str("engine.exchange") == "nccl" ? CA_EXCHANGE_NCCL : CA_EXCHANGE_P2P;

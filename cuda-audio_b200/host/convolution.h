@@ -54,6 +54,8 @@ class SharedEngine;
 //   engine.shared <N>            every N consecutive Convolution objects of the process are the N instances of
 //                                ONE batched engine (one set of kernel launches per JACK cycle for all of them)
 //   engine.shared_timeout_ms <n> how long the others wait for a member that stopped calling (default 200)
+//   engine.shared_latency 1      shared batch without a rendezvous: every member's output is one period late, nobody waits
+//                                inside a cycle -- for hosts that call their clients one after the other (jack1)
 //   engine.gpus <G>              the process's Convolution objects are dealt round-robin onto G GPUs starting at
 //                                engine.device (independent streams, no collective); shared batches
 //                                form per GPU
@@ -73,6 +75,7 @@ struct EngineOptions {
     uint32_t gpus = 1;        // engine.gpus
     uint32_t irSplit = 0;     // engine.ir_split: > 0 = this many GPUs behind one object (ca_group)
     uint32_t exchange = 0;    // engine.exchange: ca_exchange (CA_EXCHANGE_P2P / CA_EXCHANGE_NCCL)
+    uint32_t sharedLatency = 0;  // engine.shared_latency: 0 = rendezvous inside the cycle, 1 = hand in / take out, one period later
     uint32_t sharedTimeoutMs = 200;  // engine.shared: a member that has not arrived for this long is set aside until it calls again
     static EngineOptions fromEnv();
     static EngineOptions fromSettings(Settings &settings);

@@ -27,7 +27,8 @@ SharedEngine::SharedEngine(const EngineOptions &opt) : _opt(opt)
     _members.reserve(cap);
     _active.reset(new std::atomic<bool>[cap]);
     _arrivedGen.reset(new std::atomic<uint64_t>[cap]);
-    for (size_t i = 0; i < cap; i++) { _active[i].store(false); _arrivedGen[i].store(0); }
+    _stagedGen.reset(new std::atomic<uint64_t>[cap]);
+    for (size_t i = 0; i < cap; i++) { _active[i].store(false); _arrivedGen[i].store(0); _stagedGen[i].store(0); }
 }
 
 std::shared_ptr<SharedEngine> SharedEngine::join(Convolution *c, const EngineOptions &opt, int *index)
@@ -141,7 +142,7 @@ bool SharedEngine::build(size_t period, float sampleRate)
     if (_in) ca_host_free(_in);
     if (_out) ca_host_free(_out);
     _in = _out = nullptr;
-    const size_t bytes = (size_t)n * 2 * period * sizeof(float);
+    const size_t bytes = (size_t)n * 2 * period * sizeof(float) * (_opt.sharedLatency ? 2 : 1);  // pipelined: one buffer per generation parity
     if (ca_host_alloc((void **)&_in, bytes) || ca_host_alloc((void **)&_out, bytes)) return fail();
     memset(_in, 0, bytes);
     memset(_out, 0, bytes);
@@ -171,7 +172,8 @@ void SharedEngine::runBatch(Convolution *c, size_t nframes, uint64_t gen)
 {
     bool ok = false;
     if (_ok.load(std::memory_order_acquire) && _period == nframes && !_dirty.load(std::memory_order_acquire)) {
-        ok = ca_process(_engine, _in, _out, (uint32_t)nframes) == CA_OK;
+        const size_t half = _opt.sharedLatency ? _builtMembers * 2 * nframes * (gen & 1) : 0;  // pipelined: buffers by generation parity
+        ok = ca_process(_engine, _in + half, _out + half, (uint32_t)nframes) == CA_OK;
         _batches.fetch_add(1, std::memory_order_relaxed);
         if (!ok) { _ok.store(false, std::memory_order_release); _dirty.store(true, std::memory_order_release); }
     } else {
@@ -181,32 +183,89 @@ void SharedEngine::runBatch(Convolution *c, size_t nframes, uint64_t gen)
         // (between entry and arrival, or a member set aside as stalled that wakes up now) may still touch the
         // buffers: then the rebuild waits for the next cycle.
         _exclusive.fetch_add(1, std::memory_order_seq_cst);
-        if (_staging.load(std::memory_order_seq_cst) == 0 && _inside.load(std::memory_order_seq_cst) == countOf(_state.load(std::memory_order_seq_cst))) {
+        // (pipelined members touch the buffers inside the staging section only, and are not inside between their calls)
+        if (_staging.load(std::memory_order_seq_cst) == 0 && (_opt.sharedLatency || _inside.load(std::memory_order_seq_cst) == countOf(_state.load(std::memory_order_seq_cst)))) {
             std::unique_lock<std::mutex> lk(_buildMutex, std::try_to_lock);
             if (lk.owns_lock()) build(nframes, c->samplerate ? (float)c->samplerate : c->_sampleRate);
         }
         _exclusive.fetch_sub(1, std::memory_order_seq_cst);
     }
-    _batchOk.store(ok, std::memory_order_release);
+    if (ok) _okGen.store(gen + 1, std::memory_order_release);
     _state.store((gen + 1) << 16, std::memory_order_release);
+}
+
+// Has every member that takes part handed in its block for generation `gen`?  The rendezvous counts arrivals (its
+// members stay inside process() until the generation ends, so the count cannot go stale).  A pipelined member is gone
+// as soon as it has arrived and may stand down, leave or be set aside before the generation ends: there the answer is
+// taken from the members' own marks.
+bool SharedEngine::everybodyArrived(uint64_t s, uint64_t gen) const
+{
+    if (genOf(s) != gen) return false;
+    if (!_opt.sharedLatency) return countOf(s) >= _live.load(std::memory_order_seq_cst);
+    const size_t cap = std::max<size_t>(_opt.shared, 1);
+    bool any = false;
+    for (size_t i = 0; i < cap; i++) {
+        if (!_active[i].load(std::memory_order_seq_cst)) continue;
+        if (_arrivedGen[i].load(std::memory_order_acquire) != gen + 1) return false;
+        any = true;
+    }
+    return any;
+}
+
+// Wait until generation `gen` has ended; whoever finds everybody arrived runs its batch.  false: buildNow() on another
+// thread wants everybody out (this cycle is silence).
+bool SharedEngine::waitGeneration(Convolution *c, size_t nframes, uint64_t gen)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    for (int spins = 0;; spins++) {
+        uint64_t s = _state.load(std::memory_order_acquire);
+        if (genOf(s) != gen) return true;  // the batch ran
+        if (everybodyArrived(s, gen)) {
+            bool expected = false;
+            if (_runner.compare_exchange_strong(expected, true, std::memory_order_seq_cst)) {
+                if (everybodyArrived(_state.load(std::memory_order_seq_cst), gen)) runBatch(c, nframes, gen);
+                _runner.store(false, std::memory_order_seq_cst);
+                continue;
+            }
+        }
+        // buildNow() on another thread waits for everybody to leave: this cycle is silence.  (A rebuild by this
+        // cycle's runner is waited for instead: a driver that is not paced by a clock -- an offline render, one
+        // loop per member -- would otherwise run through its input while the build lasts.)
+        if (_evict.load(std::memory_order_seq_cst)) return false;
+        if (spins > 2000) {
+            std::this_thread::yield();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(_opt.sharedTimeoutMs ? _opt.sharedTimeoutMs : 200)) {
+                dropStalled(gen);
+                t0 = std::chrono::steady_clock::now();
+            }
+        }
+    }
+}
+
+// Entry of a member into the section in which it may touch the batch's buffers.  false: a build is in progress.
+bool SharedEngine::enterStaging(int idx)
+{
+    _staging.fetch_add(1, std::memory_order_seq_cst);
+    if (_exclusive.load(std::memory_order_seq_cst) != 0) {  // never block, never touch the buffers
+        _staging.fetch_sub(1, std::memory_order_seq_cst);
+        return false;
+    }
+    if (!_active[idx].load(std::memory_order_acquire)) {  // back after having been set aside (stopped client, stall)
+        _live.fetch_add(1, std::memory_order_seq_cst);
+        _active[idx].store(true, std::memory_order_seq_cst);
+        // A runner that decided before it could see us is reading the input buffer: stage only after its batch.
+        // (It cannot be rebuilding: _staging != 0.  Steady-state members never wait here.)
+        while (_runner.load(std::memory_order_seq_cst)) std::this_thread::yield();
+    }
+    return true;
 }
 
 bool SharedEngine::process(Convolution *c, int idx, const float *in1, const float *in2, float *L, float *R, size_t nframes)
 {
     if (idx < 0 || (size_t)idx >= std::max<size_t>(_opt.shared, 1)) return false;
     Inside inside(_inside);
-    _staging.fetch_add(1, std::memory_order_seq_cst);
-    if (_exclusive.load(std::memory_order_seq_cst) != 0) {  // a build is in progress: never block, never touch the buffers
-        _staging.fetch_sub(1, std::memory_order_seq_cst);
-        return false;
-    }
-    if (!_active[idx].load(std::memory_order_acquire)) {  // back after having been set aside (stopped client, stall)
-        _live.fetch_add(1, std::memory_order_seq_cst);
-        _active[idx].store(true, std::memory_order_release);
-        // A runner that decided before it could see us is reading the input buffer: stage only after its batch.
-        // (It cannot be rebuilding: _staging != 0.  Steady-state members never wait here.)
-        while (_runner.load(std::memory_order_seq_cst)) std::this_thread::yield();
-    }
+    if (_opt.sharedLatency) return processPipelined(c, idx, in1, in2, L, R, nframes);
+    if (!enterStaging(idx)) return false;
     uint64_t s = _state.load(std::memory_order_acquire);
     const uint64_t gen = genOf(s);
     const bool usable = _ok.load(std::memory_order_acquire) && !_dirty.load(std::memory_order_acquire) && _period == nframes && (size_t)idx < _builtMembers;
@@ -227,35 +286,60 @@ bool SharedEngine::process(Convolution *c, int idx, const float *in1, const floa
     }
     if (!counted) return false;
     _arrivedGen[idx].store(gen + 1, std::memory_order_release);
-
-    auto t0 = std::chrono::steady_clock::now();
-    for (int spins = 0;; spins++) {
-        s = _state.load(std::memory_order_acquire);
-        if (genOf(s) != gen) break;  // the batch ran
-        if (countOf(s) >= _live.load(std::memory_order_seq_cst)) {
-            bool expected = false;
-            if (_runner.compare_exchange_strong(expected, true, std::memory_order_seq_cst)) {
-                s = _state.load(std::memory_order_seq_cst);
-                if (genOf(s) == gen && countOf(s) >= _live.load(std::memory_order_seq_cst)) runBatch(c, nframes, gen);
-                _runner.store(false, std::memory_order_seq_cst);
-                continue;
-            }
-        }
-        // buildNow() on another thread waits for everybody to leave: this cycle is silence.  (A rebuild by this
-        // cycle's runner is waited for instead: a driver that is not paced by a clock -- an offline render, one
-        // loop per member -- would otherwise run through its input while the build lasts.)
-        if (_evict.load(std::memory_order_seq_cst)) return false;
-        if (spins > 2000) {
-            std::this_thread::yield();
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(_opt.sharedTimeoutMs ? _opt.sharedTimeoutMs : 200)) {
-                dropStalled(gen);
-                t0 = std::chrono::steady_clock::now();
-            }
-        }
-    }
-    if (!usable || !_batchOk.load(std::memory_order_acquire)) return false;
+    if (!waitGeneration(c, nframes, gen)) return false;
+    if (!usable || _okGen.load(std::memory_order_acquire) != gen + 1) return false;
     const float *src = _out + (size_t)idx * 2 * nframes;
     memcpy(L, src, nframes * sizeof(float));
     memcpy(R, src + nframes, nframes * sizeof(float));
     return true;
+}
+
+// engine.shared_latency 1: nobody waits for anybody inside a cycle.  A member hands in its block for generation g, takes
+// the output of generation g - 1 (one period of extra latency for every member alike) and returns; the member that
+// completes the set runs the batch before it returns.  For hosts that call their clients ONE AFTER THE OTHER on one
+// thread (jack1, a plain loop), where a rendezvous inside the callback can never be met.  Input and output are double
+// buffered by generation parity.  A member that comes back before the generation it already handed a block to has
+// ended (a driver without a clock running ahead; a member of the set stalled) waits for that end first, with the same
+// timeout / set-aside rules as the rendezvous.
+bool SharedEngine::processPipelined(Convolution *c, int idx, const float *in1, const float *in2, float *L, float *R, size_t nframes)
+{
+    uint64_t gen = genOf(_state.load(std::memory_order_acquire));
+    if (_active[idx].load(std::memory_order_acquire) && _arrivedGen[idx].load(std::memory_order_acquire) == gen + 1) {
+        if (!waitGeneration(c, nframes, gen)) return false;
+    }
+    if (!enterStaging(idx)) return false;
+    uint64_t s = _state.load(std::memory_order_acquire);
+    gen = genOf(s);
+    const bool usable = _ok.load(std::memory_order_acquire) && !_dirty.load(std::memory_order_acquire) && _period == nframes && (size_t)idx < _builtMembers;
+    const size_t half = _builtMembers * 2 * nframes;  // floats of one generation's buffer
+    // the block this member handed in one generation ago, processed by that generation's batch
+    const bool have = usable && gen > 0 && _stagedGen[idx].load(std::memory_order_relaxed) == gen && _okGen.load(std::memory_order_acquire) == gen;
+    if (have) {
+        const float *src = _out + ((gen - 1) & 1) * half + (size_t)idx * 2 * nframes;
+        memcpy(L, src, nframes * sizeof(float));
+        memcpy(R, src + nframes, nframes * sizeof(float));
+    }
+    if (usable) {
+        float *dst = _in + (gen & 1) * half + (size_t)idx * 2 * nframes;
+        memcpy(dst, in1, nframes * sizeof(float));
+        memcpy(dst + nframes, in2, nframes * sizeof(float));
+        c->pushParamsTo(_engine, (uint32_t)idx, (size_t)idx * _slotsPerMember, false);
+        _stagedGen[idx].store(gen + 1, std::memory_order_relaxed);
+    }
+    _staging.fetch_sub(1, std::memory_order_seq_cst);
+    bool counted = false;
+    while (genOf(s) == gen) {
+        if (_state.compare_exchange_weak(s, s + 1, std::memory_order_acq_rel, std::memory_order_acquire)) { counted = true; break; }
+    }
+    if (!counted) return have;
+    _arrivedGen[idx].store(gen + 1, std::memory_order_release);
+    // the member that completes the set runs the batch now, on its own thread; everybody else is already gone
+    if (everybodyArrived(_state.load(std::memory_order_seq_cst), gen)) {
+        bool expected = false;
+        if (_runner.compare_exchange_strong(expected, true, std::memory_order_seq_cst)) {
+            if (everybodyArrived(_state.load(std::memory_order_seq_cst), gen)) runBatch(c, nframes, gen);
+            _runner.store(false, std::memory_order_seq_cst);
+        }
+    }
+    return have;
 }

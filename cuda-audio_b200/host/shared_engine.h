@@ -41,6 +41,10 @@ private:
     explicit SharedEngine(const EngineOptions &opt);
     bool build(size_t period, float sampleRate);  // under _buildMutex, nobody else inside process()'s buffer accesses
     void runBatch(Convolution *c, size_t nframes, uint64_t gen);
+    bool everybodyArrived(uint64_t state, uint64_t gen) const;
+    bool waitGeneration(Convolution *c, size_t nframes, uint64_t gen);
+    bool enterStaging(int idx);
+    bool processPipelined(Convolution *c, int idx, const float *in1, const float *in2, float *L, float *R, size_t nframes);
     void dropStalled(uint64_t gen);
 
     EngineOptions _opt;
@@ -56,11 +60,12 @@ private:
     // on the thread of whichever waiting member finds everybody arrived; it ends the generation.
     std::atomic<uint64_t> _state{0};
     std::atomic<bool> _runner{false};
-    std::atomic<bool> _batchOk{false};
+    std::atomic<uint64_t> _okGen{0};  // generation + 1 of the last batch that ran and succeeded
     // members are expected at the rendezvous from join() until they stop arriving (sharedTimeoutMs), stand down or
     // leave(); a member that was set aside takes part again with its next call
     std::unique_ptr<std::atomic<bool>[]> _active;
     std::unique_ptr<std::atomic<uint64_t>[]> _arrivedGen;  // generation + 1 of the member's last arrival
+    std::unique_ptr<std::atomic<uint64_t>[]> _stagedGen;   // engine.shared_latency 1: generation + 1 the member last handed a block to
     std::atomic<int> _live{0};
     // build exclusion: a builder raises _exclusive, then needs _inside == 0 (buildNow: waits) or _staging == 0
     // (rebuild at the rendezvous: gives up for this cycle); members raise their counter first, then read _exclusive

@@ -58,7 +58,12 @@ struct Member {
         hj_port_set_buffer(c->playback[0], L.data());
         hj_port_set_buffer(c->playback[1], R.data());
     }
-    // one JACK cycle with a known input; the expected output follows from the select values of THIS period
+    // one JACK cycle with a known input; the expected output follows from the select values and the input of THIS period
+    // (engine.shared_latency 1: of the previous call)
+    int latency = 0;
+    std::vector<float> pin1, pin2;
+    size_t ps0 = 0, ps1 = 0;
+    bool havePrev = false;
     void cycle(uint64_t p)
     {
         size_t s0 = (p / 40) % 2, s1 = (p / 64) % 2;
@@ -71,24 +76,28 @@ struct Member {
         const uint64_t skippedBefore = c->skippedPeriods();
         hj_cycle(c->handle, (jack_nframes_t)B);
         const bool skipped = c->skippedPeriods() != skippedBefore;
-        bool isSilent = true, isExact = true;
+        const std::vector<float> &e1 = latency ? pin1 : in1, &e2 = latency ? pin2 : in2;
+        const size_t es0 = latency ? ps0 : s0, es1 = latency ? ps1 : s1;
+        bool isSilent = true, isExact = !latency || havePrev;
         for (size_t i = 0; i < B; i++) {
             isSilent = isSilent && L[i] == 0.f && R[i] == 0.f;
-            isExact = isExact && L[i] == tapOf(k, s0) * in1[i] && R[i] == tapOf(k, s1) * in2[i];
+            isExact = isExact && L[i] == tapOf(k, es0) * e1[i] && R[i] == tapOf(k, es1) * e2[i];
         }
         if (isExact && !skipped) good++;
         else if (isSilent) silent++;
-        else { wrong++; if (wrong < 4) fprintf(stderr, "member %d period %llu: L[0] = %g, expected %g or silence (skipped %d)\n", k, (unsigned long long)p, L[0], tapOf(k, s0) * in1[0], (int)skipped); }
+        else { wrong++; if (wrong < 4) fprintf(stderr, "member %d period %llu: L[0] = %g, expected %g or silence (skipped %d)\n", k, (unsigned long long)p, L[0], tapOf(k, es0) * (e1.empty() ? 0.f : e1[0]), (int)skipped); }
+        if (latency) { pin1 = in1; pin2 = in2; ps0 = s0; ps1 = s1; havePrev = true; }
         done.fetch_add(1, std::memory_order_release);
     }
 };
 
 using Members = std::vector<std::unique_ptr<Member>>;
 
-Members makeGroup(int K, uint32_t timeoutMs, bool prebuild, bool periodKnown = true)
+Members makeGroup(int K, uint32_t timeoutMs, bool prebuild, bool periodKnown = true, int latency = 0)
 {
     EngineOptions o;
     o.shared = (uint32_t)K;
+    o.sharedLatency = (uint32_t)latency;
     o.period = periodKnown ? (uint32_t)B : 0;  // 0: nobody knows the period before the first callback (plain harness)
     o.sharedTimeoutMs = timeoutMs;
     o.flags = CA_FLAG_STREAMING;
@@ -97,6 +106,7 @@ Members makeGroup(int K, uint32_t timeoutMs, bool prebuild, bool periodKnown = t
     for (int k = 0; k < K; k++) {
         m.emplace_back(new Member());
         m.back()->open(k);
+        m.back()->latency = latency;
         prepareIR(*m.back()->c, k, 0);
         prepareIR(*m.back()->c, k, 1);
     }
@@ -185,6 +195,52 @@ void unpacedDriverFirstBuild(int K, uint64_t P)
     for (auto &x : m) CHECK(x->wrong == 0 && x->silent <= 2 && x->good + x->silent == P, "member %d: good %llu silent %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent);
     auto g = m[0]->c->sharedGroup();
     fprintf(stderr, "   rebuilds %llu batches %llu dropped %llu\n", (unsigned long long)g->rebuilds(), (unsigned long long)g->batches(), (unsigned long long)g->dropped());
+}
+
+// engine.shared_latency 1: hand in / take out one period later, nobody waits inside a cycle.  The host that needs it
+// calls its clients one after the other on ONE thread (jack1); the same mode must also hold with one thread per
+// member, paced or not, and with prepare() against the running batch.
+void pipelinedMode(int K, uint64_t P)
+{
+    fprintf(stderr, "== engine.shared_latency 1: sequential host, threads, prepare(): %d members\n", K);
+    const uint64_t v0 = fake_violations();
+    {
+        Members m = makeGroup(K, 5000, true, true, 1);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (uint64_t p = 0; p < P; p++)
+            for (auto &x : m) x->cycle(p);  // one thread, one client after the other
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (auto &x : m) x->c->stop();
+        auto g = m[0]->c->sharedGroup();
+        CHECK(sec < 3.0 && g->dropped() == 0, "sequential host: %.2f s, %llu members set aside", sec, (unsigned long long)g->dropped());
+        CHECK(g->batches() == P, "sequential host: %llu batches for %llu cycles", (unsigned long long)g->batches(), (unsigned long long)P);
+        for (auto &x : m) CHECK(x->wrong == 0 && x->silent == 1 && x->good == P - 1, "sequential host, member %d: good %llu silent %llu wrong %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent, (unsigned long long)x->wrong);
+    }
+    {
+        Members m = makeGroup(K, 5000, true, true, 1);
+        runThreads(m, P);  // unpaced threads: a member that runs ahead waits for the generation it already handed a block to
+        for (auto &x : m) CHECK(x->wrong == 0 && x->silent <= 2 && x->good + x->silent == P, "threads, member %d: good %llu silent %llu wrong %llu", x->k, (unsigned long long)x->good, (unsigned long long)x->silent, (unsigned long long)x->wrong);
+    }
+    {
+        fake_set_create_delay_us(2000);
+        g_paceUs.store(150);
+        Members m = makeGroup(K, 5000, false, true, 1);
+        runThreads(m, P, [&] {
+            for (int round = 0; round < 9; round++) {
+                std::this_thread::sleep_for(std::chrono::milliseconds(8));
+                Member &x = *m[round % K];
+                prepareIR(*x.c, x.k, round % 2 ? 2 : 1, 300 + 50 * round);
+                if (round % 3 == 2) CHECK(x.c->buildNow(B), "buildNow on a live pipelined group failed");
+                if (round % 2) x.ir2Ready.store(true, std::memory_order_release);
+            }
+        });
+        fake_set_create_delay_us(0);
+        g_paceUs.store(0);
+        CHECK(sum(m, &Member::wrong) == 0, "prepare on a pipelined group: %llu wrong periods", (unsigned long long)sum(m, &Member::wrong));
+        CHECK(sum(m, &Member::good) > sum(m, &Member::silent), "prepare on a pipelined group: more silence than sound");
+        for (auto &x : m) CHECK(x->good + x->silent == P, "member %d lost periods", x->k);
+    }
+    CHECK(fake_violations() == v0, "contract violations");
 }
 
 void prepareOnLiveGroup(int K, uint64_t P)
@@ -377,6 +433,7 @@ int main(int argc, char **argv)
     if (want("failure")) buildFailureThenRecovery(3, P / 2);
     if (want("single")) singleObjectPrepareWhileRunning(P);
     if (want("multigpu")) multiGpuOptions(P);
+    if (want("pipelined")) pipelinedMode(K, P);
     fprintf(stderr, "engines created %llu destroyed %llu, batches %llu, IR loads %llu, violations %llu\n", (unsigned long long)fake_engines_created(),
             (unsigned long long)fake_engines_destroyed(), (unsigned long long)fake_periods_processed(), (unsigned long long)fake_ir_loads(), (unsigned long long)fake_violations());
     printf("HOSTSIM %s failures=%d violations=%llu\n", g_failures || fake_violations() ? "FAIL" : "OK", g_failures, (unsigned long long)fake_violations());

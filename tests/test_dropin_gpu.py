@@ -214,6 +214,19 @@ def test_shared_batched_engine_through_the_class_api():
 
 
 @needs_libs
+def test_shared_batched_engine_one_period_late_without_rendezvous():
+    """`engine.shared_latency 1` / CA_ENGINE_SHARED_LATENCY: the same three objects on three threads hand their block in
+    and take the previous period's out -- nobody waits inside a cycle (hosts that call their clients one after the other);
+    every object's output is the fp64 result delayed by exactly one period."""
+    import sys
+    env = dict(os.environ, CA_ENGINE_SHARED="3", CA_ENGINE_TIERS="auto", CA_ENGINE_SHARED_LATENCY="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_shared_worker.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("SHARED_RESULT ")][-1].split(" ", 1)[1])
+    assert res["K"] == 3 and max(res["rel_l2"]) < 5e-6, res
+
+
+@needs_libs
 @pytest.mark.parametrize("G", [1, 2])
 def test_ir_split_group_through_the_class_api(G):
     """`engine.ir_split` / CA_ENGINE_IR_SPLIT: the engine behind ONE mirror Convolution object is a ca_group over G GPUs
