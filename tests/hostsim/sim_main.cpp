@@ -15,6 +15,7 @@
 
 #include "convolution.h"
 #include "headless_jack.h"
+#include "settings_file.h"
 #include "shared_engine.h"
 #include "fake_engine.h"
 
@@ -389,6 +390,33 @@ void multiGpuOptions(uint64_t P)
     CHECK(fake_violations() == v0, "contract violations");
 }
 
+// the engine.* keys of the settings file (host/convolution.h) and their environment twins reach EngineOptions
+void optionsFromSettingsAndEnvironment()
+{
+    fprintf(stderr, "== engine.* settings keys / CA_ENGINE_* environment\n");
+    Settings st;
+    st.parse("# engine keys\nengine.device 2\nengine.tiers auto\nengine.tier_growth 4\nengine.tier_max_block 4096\nengine.period 128\n"
+             "engine.shared 6\nengine.shared_timeout_ms 50\nengine.shared_latency 1\nengine.gpus 4\nengine.async_tiers true\n"
+             "engine.l2_persist yes\nengine.ref_quirks true\nengine.graph true\n");
+    EngineOptions o = EngineOptions::fromSettings(st);
+    CHECK(o.device == 2 && o.autoTiers && o.tierGrowth == 4 && o.tierMaxBlock == 4096 && o.period == 128, "device / tiers / period keys");
+    CHECK(o.shared == 6 && o.sharedTimeoutMs == 50 && o.sharedLatency == 1 && o.gpus == 4, "shared / gpus keys");
+    CHECK((o.flags & CA_FLAG_ASYNC_TIERS) && (o.flags & CA_FLAG_L2_PERSIST) && (o.flags & CA_FLAG_REF_QUIRKS), "flag keys");
+    CHECK(!(o.flags & CA_FLAG_GRAPH) && (o.flags & CA_FLAG_STREAMING), "a shared batch runs host-driven launches, whatever engine.graph says");
+    Settings st2;
+    st2.parse("engine.ir_split 2\nengine.exchange nccl\nengine.shared 8\nengine.graph false\n");
+    o = EngineOptions::fromSettings(st2);
+    CHECK(o.irSplit == 2 && o.exchange == CA_EXCHANGE_NCCL && o.shared == 0 && !(o.flags & CA_FLAG_GRAPH), "ir_split keys (one object is the whole group: no shared batch)");
+    Settings none;
+    none.parse("conv.count 2\n");
+    o = EngineOptions::fromSettings(none);
+    CHECK(o.device == 0 && !o.autoTiers && o.shared == 0 && o.gpus == 1 && o.irSplit == 0 && (o.flags & CA_FLAG_GRAPH), "defaults: one private uniform engine per object, one CUDA graph per period");
+    setenv("CA_ENGINE_SHARED", "3", 1); setenv("CA_ENGINE_TIERS", "auto", 1); setenv("CA_ENGINE_GPUS", "2", 1); setenv("CA_ENGINE_SHARED_LATENCY", "1", 1);
+    o = EngineOptions::fromEnv();
+    CHECK(o.shared == 3 && o.autoTiers && o.gpus == 2 && o.sharedLatency == 1 && (o.flags & CA_FLAG_STREAMING), "environment twins");
+    unsetenv("CA_ENGINE_SHARED"); unsetenv("CA_ENGINE_TIERS"); unsetenv("CA_ENGINE_GPUS"); unsetenv("CA_ENGINE_SHARED_LATENCY");
+}
+
 void singleObjectPrepareWhileRunning(uint64_t P)
 {
     fprintf(stderr, "== one Convolution of its own: prepare() from a control thread against the running callback\n");
@@ -424,6 +452,7 @@ int main(int argc, char **argv)
     hj_set_sample_rate(48000);
     const std::string only = argc > 3 ? argv[3] : "";  // run one scenario only (debugging)
     auto want = [&](const char *name) { return only.empty() || only == name; };
+    if (want("options")) optionsFromSettingsAndEnvironment();
     if (want("steady")) steady(K, P);
     if (want("lockstep")) lockstepHost(K, P);
     if (want("unpaced")) unpacedDriverFirstBuild(3, P);
