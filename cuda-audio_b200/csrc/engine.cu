@@ -44,6 +44,15 @@ thread_local std::string g_last_error;
         }                                                                                          \
     } while (0)
 
+// Streams, events and graphs belong to the engine's GPU: a launch into them fails when the calling thread's
+// current device is another one (a JACK callback thread starts on device 0 whatever GPU its engine was built
+// on: engine.gpus).  One thread-local read when the device is already current.
+#define CA_BIND(e)                                                                                 \
+    do {                                                                                           \
+        int _cur = -1;                                                                             \
+        if (cudaGetDevice(&_cur) != cudaSuccess || _cur != (e)->device) CA_CUDA(cudaSetDevice((e)->device)); \
+    } while (0)
+
 typedef void (*fwd_fn)(const FwdArgs);
 typedef void (*ir_fn)(const IrArgs);
 typedef void (*mac_fn)(const MacArgs);
@@ -1695,6 +1704,7 @@ int ca_set_active(ca_engine *e, uint32_t n)
     if (!e || !n || n > e->n_inst) return CA_ERR_INVALID;
     if (n == e->n_active) return CA_OK;
     if (e->persistent) return CA_ERR_UNSUPPORTED;
+    CA_BIND(e);
     int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));
@@ -1722,6 +1732,7 @@ int ca_process_device(ca_engine *e, const float *d_in, float *d_out, uint32_t nf
     if (!e || !d_in || !d_out) return CA_ERR_INVALID;
     if (nframes != e->B) return CA_ERR_PERIOD;
     if (e->persistent) { g_last_error = "CA_FLAG_PERSISTENT engines are driven through ca_process"; return CA_ERR_UNSUPPORTED; }
+    CA_BIND(e);
     const double t0 = now_us();
     int rc;
     if (use_pipeline(e)) {
@@ -1741,6 +1752,7 @@ int ca_process(ca_engine *e, const float *in, float *out, uint32_t nframes)
 {
     if (!e || !in || !out) return CA_ERR_INVALID;  // the reference silently returns on null ports (conv.cu:297)
     if (nframes != e->B) return CA_ERR_PERIOD;
+    CA_BIND(e);
     const double t0 = now_us();
     if (e->persistent) {
         const int rc = process_persistent(e, in, out);
@@ -1840,6 +1852,7 @@ int ca_sync(ca_engine *e)
 {
     if (!e) return CA_ERR_INVALID;
     if (e->persistent) return CA_OK;  // ca_process is synchronous; the resident kernel keeps the stream busy by design
+    CA_BIND(e);
     const int rc = drain_all(e);
     if (rc) return rc;
     CA_CUDA(cudaStreamSynchronize(e->stream));

@@ -26,6 +26,9 @@
  * All functions return 0 (CA_OK) or a negative error code; none aborts.
  * Thread model: ca_process* from one thread per engine; ca_set_params from any thread
  * (lock-free hand-off, applied at the next ca_process*); ca_load_ir* may block.
+ * Device: every entry point that touches the GPU makes the engine's device (ca_config.device) the calling
+ * thread's current CUDA device and leaves it so; callers with CUDA work of their own on another device
+ * re-select theirs afterwards.
  */
 #ifndef CUDA_AUDIO_B200_H
 #define CUDA_AUDIO_B200_H
