@@ -1559,6 +1559,8 @@ int ca_create(const ca_config *cfg, ca_engine **out)
     if (cfg->n_in < 1 || cfg->n_in > 2 || cfg->n_out < 1 || cfg->n_out > 2) { g_last_error = "n_in / n_out must be 1 or 2"; return CA_ERR_INVALID; }
     if (cfg->max_voices > (uint32_t)kMaxVoices) { g_last_error = "max_voices must be <= 4"; return CA_ERR_INVALID; }
     if (!cfg->n_instances || !cfg->max_ir_frames || !cfg->n_ir_slots) { g_last_error = "n_instances, max_ir_frames, n_ir_slots must be > 0"; return CA_ERR_INVALID; }
+    // item indices (instance x input / output) and per-launch instance counts are 32-bit: far above what 180 GB hold at any geometry worth running
+    if (cfg->n_instances > (1u << 20)) { g_last_error = "n_instances must be <= 1048576"; return CA_ERR_INVALID; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
         (void)cudaGetLastError();

@@ -102,7 +102,7 @@ typedef struct ca_config {
     uint32_t struct_size;   /* sizeof(ca_config) */
     int32_t device;         /* CUDA device ordinal */
     uint32_t period;        /* frames per ca_process call (JACK nframes); power of two, 32..1024 */
-    uint32_t n_instances;   /* instances batched in one engine */
+    uint32_t n_instances;   /* instances batched in one engine, 1 .. 1048576 */
     uint32_t n_in, n_out;   /* 1 or 2 each (2,2 = the reference's true-stereo instance) */
     uint32_t max_ir_frames; /* IR capacity L; longer IRs are truncated like conv.cu:239 */
     uint32_t n_ir_slots;    /* size of the IR bank shared by the engine's instances */

@@ -153,7 +153,7 @@ def test_invalid_configs_are_refused_before_any_cuda_call():
         return rc, L.ca_last_error_string().decode()
 
     for bad in (dict(period=0), dict(period=48), dict(period=16), dict(period=2048), dict(n_in=0), dict(n_in=3), dict(n_out=0), dict(n_out=3),
-                dict(n_instances=0), dict(max_ir_frames=0), dict(n_ir_slots=0), dict(max_voices=5), dict(struct_size=8)):
+                dict(n_instances=0), dict(n_instances=(1 << 20) + 1), dict(max_ir_frames=0), dict(n_ir_slots=0), dict(max_voices=5), dict(struct_size=8)):
         rc, why = create(**bad)
         assert rc == -1 and why, (bad, rc, why)
     assert L.ca_create(None, None) == -1
